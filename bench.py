@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- bead-moves/sec of the PIMC hot path on N B200s (BASELINE.json metric), roofline and CPU baseline.
+
+A "step" is one `run!(s, iters, updates; Zmeasurements=[Energy])` over all chains resident on the GPU
+(sweep schedule), i.e. one pass of the hot path (staging-bridge moves + centre-of-mass moves + Delta-U +
+Metropolis + Energy estimator) over one batch of synthetic worldlines.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                     # CPU arm: the oracle port of the reference on host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): examples/energy_2d_free_bose_gas.jl scaled to
+V=0, lambda=1, T=1, N=64, M=128, L=16, Ncycle=2, 4096 chains per GPU (weak scaling), updates
+SingleCenterOfMass(1.0):1 + ReshapeLinear(20):1, Energy measured every Ncycle iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_ALG = 48.0   # algorithmic bytes per bead-move: read+write of position (2x8 B) and cached link action (8 B)
+F_ALG = 47.0   # algorithmic flops per bead-move, V = 0
+WORKLOADS = {
+    "c2": dict(name="C2 2D free Bose gas N=64 M=128", pot="zero", dv="identity", dim=2, N=64, M=128, L=16.0, T=1.0, lam=1.0, Ncycle=2,
+               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 20)]),
+    "c5": dict(name="C5 2D trapped gas N=1024 M=64", pot="harmonic", dv="identity", dim=2, N=1024, M=64, L=100.0, T=1.0, lam=0.5, Ncycle=10,
+               chains=512, updates=[("com", 1, 1.0), ("reshape", 1, 2)]),
+    "c1": dict(name="C1 2D trap N=1 M=5 (as shipped)", pot="harmonic", dv="identity", dim=2, N=1, M=5, L=100.0, T=1.0, lam=0.5, Ncycle=10,
+               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 2)]),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def oracle_arm(wl, threads, iters, seed=1, therm=60):
+    """The CPU restatement (oracle port of the reference) on `threads` host threads, one chain per thread
+    (mirrors the example scripts' pmap over independent runs). Returns (bead_moves, seconds)."""
+    import oracle_binding as ob
+    ob.build()
+    kind = {"com": ob.UPD_SINGLE_COM, "reshape": ob.UPD_RESHAPE_LINEAR, "swap": ob.UPD_RESHAPE_SWAP, "pcom": ob.UPD_POLYMER_COM}
+    systems = []
+    for t in range(threads):
+        s = ob.System(ob.make_potential(wl["pot"], wl["dv"]), dim=wl["dim"], M=wl["M"], N=wl["N"], L=wl["L"], T=wl["T"], lam=wl["lam"],
+                      Ncycle=wl["Ncycle"], seed=seed, chain=t)
+        ups = [(every, ob.Update(s, kind[k], v0)) for k, every, v0 in wl["updates"]]
+        en = ob.Energy(max(16, (therm + iters) // wl["Ncycle"] + 16))
+        systems.append((s, ups, en))
+
+    def work(i, n, measure):
+        s, ups, en = systems[i]
+        s.run(n, ups, energies=[en] if measure else [], sched=ob.SCHED_SWEEP)
+
+    def par(n, measure):
+        th = [threading.Thread(target=work, args=(i, n, measure)) for i in range(threads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    par(therm, False)  # let the adaptive slice count / step settle like the GPU arm
+    bm0 = sum(u.get()["bead_moves"] for s, ups, en in systems for _, u in ups)
+    t0 = time.perf_counter()
+    par(iters, True)
+    dt = time.perf_counter() - t0
+    bm1 = sum(u.get()["bead_moves"] for s, ups, en in systems for _, u in ups)
+    return bm1 - bm0, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--iters", type=int, default=100, help="run! iterations per step")
+    ap.add_argument("--therm", type=int, default=300, help="untimed thermalisation iterations before the warm-up")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=0)
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.chains:
+        wl["chains"] = args.chains
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncpu = os.cpu_count() or 1
+    config = {"workload": wl["name"], "chains_per_gpu": wl["chains"], "N": wl["N"], "M": wl["M"], "dim": wl["dim"],
+              "updates": "SingleCenterOfMass(1.0):1 + ReshapeLinear:1", "schedule": "sweep", "iters_per_step": args.iters,
+              "measure": f"Energy every {wl['Ncycle']} iterations", "l2": "state (chains x 192 KiB) larger than L2"}
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path: Julia is absent from this image, so the oracle port is timed
+        if rank != 0:
+            return
+        per_step = args.cpu_iters or max(8, 2000 // max(1, (args.steps + args.warmup)))
+        threads = ncpu
+        tot_bm, tot_t = 0, 0.0
+        for step in range(args.warmup + args.steps):
+            bm, dt = oracle_arm(wl, threads, per_step, seed=1 + step)
+            if step >= args.warmup:
+                tot_bm += bm
+                tot_t += dt
+        val = tot_bm / tot_t
+        sample = f"{threads} chains (one per host thread) x {per_step} sweep iterations per step, oracle port (C, -O2), not Julia"
+        line = {"metric": "bead-moves/sec", "value": val, "unit": "bead-moves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": "bead-moves/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "bead-moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import pimc_jl_b200 as pj
+    from pimc_jl_b200 import _lib as L
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    Cc = wl["chains"]
+    e = pj.Engine(pj.make_potential(wl["pot"], wl["dv"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
+                  T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank)
+    kind = {"com": L.UPD_SINGLE_COM, "reshape": L.UPD_RESHAPE_LINEAR, "swap": L.UPD_RESHAPE_SWAP, "pcom": L.UPD_POLYMER_COM}
+    ups = [(every, e.update_create(kind[k], v0)) for k, every, v0 in wl["updates"]]
+    nmeas_total = (args.therm + (args.warmup + args.steps) * args.iters * 2) // wl["Ncycle"] + 64
+    en = e.energy_create(nmeas_total)
+    stream = torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    e.run(args.therm, ups, sched=L.SCHED_SWEEP)  # thermalisation: adaptive slice count / step settle
+
+    def block_allreduce(n_before):
+        """per-block all-reduce of the estimator accumulators: chain-mean E, Ev of this step's measurements (NCCL)"""
+        E, Ev, n = e.energy_read(en, -1)
+        blk = torch.from_numpy(np.stack([E[n_before:], Ev[n_before:]])).cuda()
+        if dist is not None:
+            dist.all_reduce(blk)
+            blk /= world
+        return blk, n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: `value` ----
+    n_seen = e.energy_read(en, -1, cap=0)[2]
+    for _ in range(args.warmup):
+        e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        _, n_seen = block_allreduce(n_seen)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    l0 = lib.pimc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bead_moves, kern_ms = 0, 0.0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        st = e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        bead_moves += st["bead_moves"]
+        kern_ms += st["kernel_ms"]
+        blk, n_seen = block_allreduce(n_seen)
+    ev1.record(stream)
+    barrier()
+    launches = lib.pimc_launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    t = torch.tensor([ms, kern_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bead_moves)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms, kern_ms, total_bm = float(t[0]), float(t[1]), float(tot[0])
+    value = total_bm / (ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----
+    per = wl["N"] * wl["dim"] * wl["M"]
+    host_r = torch.empty((Cc, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
+    e.get_r_into(host_r)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_bm = 0
+    for _ in range(args.steps):
+        e.set_paths(host_r)                                    # H2D: this step's worldlines (pinned host memory)
+        st = e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        e2e_bm += st["bead_moves"]
+        blk, n_seen = block_allreduce(n_seen)                  # estimator block (all-reduced over GPUs)
+        e.get_r_into(host_r)                                   # D2H: updated worldlines
+        blk_host = blk.cpu()                                   # D2H: the step's result
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    be = torch.tensor([float(e2e_bm)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(be)
+    e2e_val = float(be[0]) / float(te[0])
+    h2d = per * Cc * 8
+    d2h = per * Cc * 8 + 2 * 8 * (args.iters // wl["Ncycle"])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    hbm, how = peaks()
+    per_gpu = total_bm / world / (kern_ms * 1e-3)          # dominant kernel: k_run, per launch == per step
+    achieved = per_gpu * B_ALG / 1e9
+    fp64 = C.c_double(0.0)
+    lib.pimc_measure_fp64_peak(C.byref(fp64))
+    roofline = {"bound": "hbm", "kernel": "k_run", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json ({how})", "alg_bytes_per_bead_move": B_ALG,
+                "fp64": {"achieved_tflops": per_gpu * F_ALG / 1e12, "peak_tflops_measured_dfma": fp64.value,
+                         "frac": (per_gpu * F_ALG / 1e12 / fp64.value) if fp64.value else None, "alg_flops_per_bead_move": F_ALG}}
+    Em = float(blk_host[0].mean()) if blk_host.numel() else None
+    line = {"metric": "bead-moves/sec", "value": value, "unit": "bead-moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": sampler.summary() if sampler else None,
+            "e2e": {"value": e2e_val, "unit": "bead-moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "kernel_ms_per_step": kern_ms / args.steps,
+            "check": {"E_mean_last_block": Em, "E_expected_boltzmannon": wl["dim"] * wl["N"] / 2.0 * wl["T"] if wl["pot"] == "zero" else None}}
+    if not args.no_cpu_baseline:
+        it = args.cpu_iters or 150
+        bm, dt = oracle_arm(wl, ncpu, it)
+        line["cpu_baseline"] = {"value": bm / dt, "unit": "bead-moves/s", "cores": ncpu, "kind": "port",
+                                "sample": f"{ncpu} chains (one per host thread) x {it} sweep iterations after 60 thermalisation iterations; "
+                                          f"oracle port of the reference (C, -O2), not Julia"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,9 @@ void pimc_destroy(pimc_handle *h);                                      /* Julia
 const char *pimc_last_error(const pimc_handle *h);                      /* NULL handle: last create error     */
 int  pimc_version(void);
 int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run kernels on this cudaStream_t   */
+int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
+/* measurement utility (no reference counterpart): sustained non-tensor fp64 FMA rate of the current device, in TFLOP/s */
+int  pimc_measure_fp64_peak(double *tflops);
 
 /* ---- state: s.world[n].{r,V,bins,next} (src/system.jl:1-6), host layout = reference layout:
  *      r[chain][n][dim][M] (per particle the M x dim column-major matrix), V[chain][n][M], bins, next[chain][n] ---- */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "pimc_last_error": (C.c_char_p, [_vp]),
     "pimc_version": (C.c_int, []),
     "pimc_set_stream": (C.c_int, [_vp, _vp]),
+    "pimc_launch_count": (C.c_int64, []),
+    "pimc_measure_fp64_peak": (C.c_int, [f64p]),
     "pimc_get_paths": (C.c_int, [_vp, _i32, _i32, f64p, f64p, i64p, i64p]),
     "pimc_set_paths": (C.c_int, [_vp, _i32, _i32, f64p, i64p]),
     "pimc_get_scalars": (C.c_int, [_vp, f64p, i64p]),

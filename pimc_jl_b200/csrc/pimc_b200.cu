@@ -399,6 +399,8 @@ struct pimc_handle {
     int device;
 };
 static char g_err[512] = "";
+static long long g_launches = 0;
+#define LAUNCHED() (++g_launches)
 
 #define SETERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); else snprintf(g_err, sizeof g_err, __VA_ARGS__); } while (0)
 #define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { SETERR(h, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return PIMC_ERR_CUDA; } } while (0)
@@ -424,6 +426,40 @@ static void pot_to_dev(const pimc_potential *p, PotDev *d)
 static int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 
 extern "C" int pimc_version(void) { return 100; }
+extern "C" int64_t pimc_launch_count(void) { return g_launches; }
+
+// dependent-free DFMA streams: 8 accumulators per thread, 4096 FMAs each per loop
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+extern "C" int pimc_measure_fp64_peak(double *tflops)
+{
+    int nd = 0; if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { snprintf(g_err, sizeof g_err, "no CUDA device"); return PIMC_ERR_CUDA; }
+    int dev; cudaGetDevice(&dev); cudaDeviceProp pr; cudaGetDeviceProperties(&pr, dev);
+    int blocks = pr.multiProcessorCount * 8, threads = 256, iters = 2000;
+    double *o; if (cudaMalloc(&o, sizeof(double) * blocks * threads) != cudaSuccess) return PIMC_ERR_NOMEM;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0); k_fp64_peak<<<blocks, threads>>>(o, iters); LAUNCHED(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 8 * 64 * (double)iters * blocks * threads;
+        if (rep > 0 && ms > 0 && fl / ms * 1e-9 > best) best = fl / ms * 1e-9;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(o);
+    if (cudaGetLastError() != cudaSuccess) return PIMC_ERR_CUDA;
+    *tflops = best; return PIMC_OK;
+}
 extern "C" const char *pimc_last_error(const pimc_handle *h) { return h ? h->err : g_err; }
 
 extern "C" void pimc_destroy(pimc_handle *h)
@@ -501,9 +537,9 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         for (int c = 0; c < S.C; ++c) for (int n = 0; n < S.N; ++n) nx[(size_t)c * S.N + n] = n;
         CKC(cudaMemcpy(S.next, nx.data(), nx.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
-    if (cfg->init) { k_init_world<<<S.C, 128>>>(S); CKC(cudaGetLastError()); }
-    else { k_relink<<<grid_for(nb, 256), 256>>>(S, 0, S.C); CKC(cudaGetLastError()); }
-    if (S.need_cells) { k_cells_build<<<grid_for((size_t)S.C * S.M, 128), 128>>>(S, 0, S.C); CKC(cudaGetLastError()); }
+    if (cfg->init) { k_init_world<<<S.C, 128>>>(S); LAUNCHED(); CKC(cudaGetLastError()); }
+    else { k_relink<<<grid_for(nb, 256), 256>>>(S, 0, S.C); LAUNCHED(); CKC(cudaGetLastError()); }
+    if (S.need_cells) { k_cells_build<<<grid_for((size_t)S.C * S.M, 128), 128>>>(S, 0, S.C); LAUNCHED(); CKC(cudaGetLastError()); }
     CKC(cudaDeviceSynchronize());
     *out = h;
     return PIMC_OK;
@@ -534,7 +570,7 @@ extern "C" int pimc_get_paths(pimc_handle *h, int32_t c0, int32_t nc, double *r,
     if (V) CK(h, cudaMemcpy(V, S.Vl + (size_t)c0 * per, sizeof(double) * nc * per, cudaMemcpyDeviceToHost));
     if (bins) {
         long long *tmp; CK(h, cudaMalloc(&tmp, sizeof(long long) * nc * per));
-        k_bins_export<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc, tmp);
+        k_bins_export<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc, tmp); LAUNCHED();
         cudaError_t e = cudaMemcpy(bins, tmp, sizeof(long long) * nc * per, cudaMemcpyDeviceToHost);
         cudaFree(tmp); CK(h, e);
     }
@@ -559,8 +595,8 @@ extern "C" int pimc_set_paths(pimc_handle *h, int32_t c0, int32_t nc, const doub
         }
         CK(h, cudaMemcpy(S.next + (size_t)c0 * S.N, nx.data(), sizeof(int) * nx.size(), cudaMemcpyHostToDevice));
     }
-    k_relink<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc);
-    if (S.need_cells) k_cells_build<<<grid_for((size_t)nc * S.M, 128), 128, 0, h->stream>>>(S, c0, nc);
+    k_relink<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc); LAUNCHED();
+    if (S.need_cells) { k_cells_build<<<grid_for((size_t)nc * S.M, 128), 128, 0, h->stream>>>(S, c0, nc); LAUNCHED(); }
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     return PIMC_OK;
@@ -570,7 +606,7 @@ extern "C" int pimc_update_nnbins(pimc_handle *h)
     if (!h) return PIMC_ERR_INVALID;
     if (!h->S.need_cells) return PIMC_OK;
     CK(h, cudaSetDevice(h->device));
-    k_cells_build<<<grid_for((size_t)h->S.C * h->S.M, 128), 128, 0, h->stream>>>(h->S, 0, h->S.C);
+    k_cells_build<<<grid_for((size_t)h->S.C * h->S.M, 128), 128, 0, h->stream>>>(h->S, 0, h->S.C); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     return PIMC_OK;
 }
@@ -588,14 +624,14 @@ extern "C" int pimc_distance(int64_t n, const double *x1, const double *x2, doub
 {
     NEEDGPU(); TmpBuf t; double *a = t.up(x1, n), *b = t.up(x2, n), *o = t.up((double *)nullptr, n);
     if (!a || !b || !o) return PIMC_ERR_NOMEM;
-    k_distance<<<grid_for(n, 256), 256>>>(n, a, b, L, o); CKG(cudaGetLastError());
+    k_distance<<<grid_for(n, 256), 256>>>(n, a, b, L, o); LAUNCHED(); CKG(cudaGetLastError());
     CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
 extern "C" int pimc_teleport(int64_t n, const double *x, double L, double *out)
 {
     NEEDGPU(); TmpBuf t; double *a = t.up(x, n), *o = t.up((double *)nullptr, n);
     if (!a || !o) return PIMC_ERR_NOMEM;
-    k_teleport<<<grid_for(n, 256), 256>>>(n, a, L, o); CKG(cudaGetLastError());
+    k_teleport<<<grid_for(n, 256), 256>>>(n, a, L, o); LAUNCHED(); CKG(cudaGetLastError());
     CKG(cudaMemcpy(out, o, n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
 extern "C" int pimc_lnK(int64_t n, const double *r1, const double *r2, int32_t dim, double tau, double lambda, double L, double *out)
@@ -618,7 +654,7 @@ extern "C" int pimc_potential_eval(int64_t n, const double *r, int32_t dim, cons
     NEEDGPU(); TmpBuf t; double *a = t.up(r, n * dim), *o = t.up((double *)nullptr, n), *g = t.up((double *)nullptr, n * dim);
     if (!a || !o || !g) return PIMC_ERR_NOMEM;
     PotDev pd; pot_to_dev(p, &pd);
-    k_pot<<<grid_for(n, 256), 256>>>(n, a, dim, pd, o, g); CKG(cudaGetLastError());
+    k_pot<<<grid_for(n, 256), 256>>>(n, a, dim, pd, o, g); LAUNCHED(); CKG(cudaGetLastError());
     if (V) CKG(cudaMemcpy(V, o, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (dV) CKG(cudaMemcpy(dV, g, n * dim * sizeof(double), cudaMemcpyDeviceToHost));
     CKG(cudaDeviceSynchronize()); return PIMC_OK;
@@ -629,14 +665,14 @@ extern "C" int pimc_levy_bridge(double *r, int32_t rows, int32_t dim, double tau
     if (rows < 2 || dim < 1 || dim > 2 || nb < 1) { snprintf(g_err, sizeof g_err, "levy_bridge: rows >= 2, dim in {1,2}, nb >= 1"); return PIMC_ERR_INVALID; }
     TmpBuf t; double *a = t.up(r, (size_t)nb * rows * dim), *x = t.up(xi, (size_t)nb * (rows - 2) * dim + 1);
     if (!a || !x) return PIMC_ERR_NOMEM;
-    k_levy<<<grid_for(nb, 128), 128>>>(a, rows, dim, tau, L, lambda, x, nb); CKG(cudaGetLastError());
+    k_levy<<<grid_for(nb, 128), 128>>>(a, rows, dim, tau, L, lambda, x, nb); LAUNCHED(); CKG(cudaGetLastError());
     CKG(cudaMemcpy(r, a, (size_t)nb * rows * dim * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
 extern "C" int pimc_gauss_pairs(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, int64_t n, double *g)
 {
     NEEDGPU(); TmpBuf t; double *o = t.up((double *)nullptr, 2 * n);
     if (!o) return PIMC_ERR_NOMEM;
-    k_gauss<<<grid_for(n, 256), 256>>>(seed, chain, iter, slot, kind, retry, bead0, n, o); CKG(cudaGetLastError());
+    k_gauss<<<grid_for(n, 256), 256>>>(seed, chain, iter, slot, kind, retry, bead0, n, o); LAUNCHED(); CKG(cudaGetLastError());
     CKG(cudaMemcpy(g, o, 2 * n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
 
@@ -647,7 +683,7 @@ extern "C" int pimc_energy_now(pimc_handle *h, double *E, double *Ev, double *pa
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; int C = h->S.C; double *e = t.up((double *)nullptr, C), *ev = t.up((double *)nullptr, C), *p = t.up((double *)nullptr, 3 * (size_t)C);
     if (!e || !ev || !p) return PIMC_ERR_NOMEM;
-    k_energy_now<<<C, 256, 0, h->stream>>>(h->S, e, ev, p); CK(h, cudaGetLastError());
+    k_energy_now<<<C, 256, 0, h->stream>>>(h->S, e, ev, p); LAUNCHED(); CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     if (E) CK(h, cudaMemcpy(E, e, C * sizeof(double), cudaMemcpyDeviceToHost));
     if (Ev) CK(h, cudaMemcpy(Ev, ev, C * sizeof(double), cudaMemcpyDeviceToHost));
@@ -660,7 +696,7 @@ extern "C" int pimc_action(pimc_handle *h, double *cached, double *recomputed)
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; int C = h->S.C; double *a = t.up((double *)nullptr, C), *b = t.up((double *)nullptr, C);
     if (!a || !b) return PIMC_ERR_NOMEM;
-    k_action<<<C, 256, 0, h->stream>>>(h->S, a, b); CK(h, cudaGetLastError());
+    k_action<<<C, 256, 0, h->stream>>>(h->S, a, b); LAUNCHED(); CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     if (cached) CK(h, cudaMemcpy(cached, a, C * sizeof(double), cudaMemcpyDeviceToHost));
     if (recomputed) CK(h, cudaMemcpy(recomputed, b, C * sizeof(double), cudaMemcpyDeviceToHost));
@@ -673,7 +709,7 @@ extern "C" int pimc_find_nn(pimc_handle *h, int32_t chain, const double *r, int6
     if (slice < 1 || slice > h->S.M) { SETERR(h, "slice outside 1..M"); return PIMC_ERR_INVALID; }
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; long long *o = t.up((long long *)nullptr, 1); if (!o) return PIMC_ERR_NOMEM;
-    k_find_nn<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o);
+    k_find_nn<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     long long v; CK(h, cudaMemcpy(&v, o, sizeof v, cudaMemcpyDeviceToHost)); *nn = v; return PIMC_OK;
 }
@@ -684,7 +720,7 @@ extern "C" int pimc_find_nns(pimc_handle *h, int32_t chain, const double *r, int
     if (slice < 1 || slice > h->S.M) { SETERR(h, "slice outside 1..M"); return PIMC_ERR_INVALID; }
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; long long *o = t.up((long long *)nullptr, cap + 1), *cn = t.up((long long *)nullptr, 1); if (!o || !cn) return PIMC_ERR_NOMEM;
-    k_find_nns<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o, cap, cn);
+    k_find_nns<<<1, 32, 0, h->stream>>>(h->S, chain, r[0], h->S.dim > 1 ? r[1] : 0.0, (int)slice - 1, (int)exception - 1, o, cap, cn); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     long long v; CK(h, cudaMemcpy(&v, cn, sizeof v, cudaMemcpyDeviceToHost)); *count = v;
     long long ncopy = v < cap ? v : cap;
@@ -706,7 +742,7 @@ extern "C" int pimc_reshape_linear_explicit(pimc_handle *h, int32_t chain, int64
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; double *x = t.up(xi, (size_t)(m - 1) * h->S.dim + 1), *rp = t.up((double *)nullptr, (size_t)(m + 1) * h->S.dim);
     MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!x || !rp || !o) return PIMC_ERR_NOMEM;
-    k_reshape_linear_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, (int)j0, (int)m, x, u, commit, o, rp);
+    k_reshape_linear_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, (int)j0, (int)m, x, u, commit, o, rp); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
     if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
@@ -721,7 +757,7 @@ extern "C" int pimc_reshape_swap_explicit(pimc_handle *h, int32_t chain, int64_t
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; size_t nx = (size_t)(m - 1) * h->S.dim + 1; double *x1 = t.up(xi1, nx), *x2 = t.up(xi2, nx);
     MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!x1 || !x2 || !o) return PIMC_ERR_NOMEM;
-    k_reshape_swap_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)n2 - 1, (int)j0, (int)m, x1, x2, u, commit, o);
+    k_reshape_swap_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)n2 - 1, (int)j0, (int)m, x1, x2, u, commit, o); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
     if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
@@ -735,7 +771,7 @@ extern "C" int pimc_com_explicit(pimc_handle *h, int32_t chain, int64_t n, int32
     (void)polymer; // the cycle of n is moved as a whole in both variants (SingleCenterOfMass only picks n with next == n)
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; double *dd = t.up(d, 2); MoveOut *o = t.up((MoveOut *)nullptr, 1); if (!dd || !o) return PIMC_ERR_NOMEM;
-    k_com_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, dd, u, commit, o);
+    k_com_explicit<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n - 1, dd, u, commit, o); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     MoveOut mo; CK(h, cudaMemcpy(&mo, o, sizeof mo, cudaMemcpyDeviceToHost));
     if (w_initial) *w_initial = mo.wi; if (w_updated) *w_updated = mo.wu; if (acc) *acc = mo.acc;
@@ -746,7 +782,7 @@ extern "C" int pimc_swap_weights(pimc_handle *h, int32_t chain, int64_t n1, int6
     int rc = check_move(h, chain, n1, j0, m); if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
     TmpBuf t; double *o = t.up((double *)nullptr, h->S.N); if (!o) return PIMC_ERR_NOMEM;
-    k_swap_weights<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)j0, (int)m, o);
+    k_swap_weights<<<1, 32, 0, h->stream>>>(h->S, chain, (int)n1 - 1, (int)j0, (int)m, o); LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaMemcpy(w, o, sizeof(double) * h->S.N, cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
@@ -851,6 +887,7 @@ extern "C" int pimc_energy_read(pimc_handle *h, int32_t id, int32_t chain, doubl
     TmpBuf t; double *a = t.up((double *)nullptr, m), *b = t.up((double *)nullptr, m); if (!a || !b) return PIMC_ERR_NOMEM;
     if (chain < 0) k_energy_chain_mean<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, m, a, b);
     else k_energy_chain_series<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, chain, m, a, b);
+    LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     if (E) CK(h, cudaMemcpy(E, a, m * sizeof(double), cudaMemcpyDeviceToHost));
     if (Ev) CK(h, cudaMemcpy(Ev, b, m * sizeof(double), cudaMemcpyDeviceToHost));
@@ -880,7 +917,7 @@ extern "C" int pimc_density_measure(pimc_handle *h, int32_t id)
 {
     if (!h || id < 0 || id >= h->nde) return PIMC_ERR_INVALID;
     CK(h, cudaSetDevice(h->device));
-    k_density_now<<<h->S.C, 256, 0, h->stream>>>(h->S, h->T.de[id]); CK(h, cudaGetLastError());
+    k_density_now<<<h->S.C, 256, 0, h->stream>>>(h->S, h->T.de[id]); LAUNCHED(); CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     h->de_ndata[id] += (long long)h->S.M * h->S.C;
     return PIMC_OK;
@@ -893,7 +930,7 @@ extern "C" int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64
     DeDev &D = h->T.de[id]; size_t sz = h->S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins;
     if (dens) {
         TmpBuf t; double *o = t.up((double *)nullptr, sz); if (!o) return PIMC_ERR_NOMEM;
-        k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(D.dens, sz, o); CK(h, cudaGetLastError());
+        k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(D.dens, sz, o); LAUNCHED(); CK(h, cudaGetLastError());
         CK(h, cudaStreamSynchronize(h->stream));
         CK(h, cudaMemcpy(dens, o, sz * sizeof(double), cudaMemcpyDeviceToHost));
     }
@@ -934,7 +971,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
     int launches = 0;
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    if (n > 0) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); launches++; }
+    if (n > 0) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
     CK(h, cudaEventRecord(h->ev1, h->stream));
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));

@@ -1,0 +1,305 @@
+"""CPU tests (no GPU): the oracle against independent numpy / mpmath re-derivations of the reference formulas,
+against the constants the reference's own example and tests hold, and against closed-form finite-M answers."""
+import ctypes as C
+import math
+import numpy as np
+import pytest
+
+
+# ---------- independent second opinions (pure Python / numpy, written from the Julia source, not from the C) ----------
+def teleport_py(x, L):                      # src/propagator.jl:30-32
+    return (x + L) - math.floor(x / (2 * L) + 0.5) * (2 * L) - L
+
+
+def distance_py(a, b, L):                   # src/propagator.jl:6-9
+    dx = abs(a - b)
+    return min((2 * L) - dx, dx)
+
+
+def levy_py(r, tau, L, lam, xi):            # src/updates/helper.jl:118-139 ; r rows x dim (row index first)
+    r = r.copy()
+    rows, dim = r.shape
+    for k in range(dim):
+        if abs(r[0, k] - r[-1, k]) > L:
+            r[-1, k] += np.sign(r[0, k]) * (2 * L)
+    m = rows - 2
+    for j in range(1, m + 1):
+        alpha = (m + 1 - j) / (m + 2 - j)
+        r[j, :] = alpha * r[j - 1, :] + (1 - alpha) * r[-1, :] + xi[j - 1, :] * math.sqrt(2 * lam * alpha * tau)
+    for j in range(rows):
+        for k in range(dim):
+            r[j, k] = teleport_py(r[j, k], L)
+    return r
+
+
+def energy_py(r, nxt, L, tau, lam, V, dV):  # src/measurement.jl:92-122 ; r[n][dim][M]
+    N, dim, M = r.shape
+    link = pot = vkin = 0.0
+    for i in range(N):
+        for j in range(M):
+            inext = nxt[i] - 1 if j == M - 1 else i
+            jn = (j + 1) % M
+            a, b = r[i, :, j], r[inext, :, jn]
+            dr = np.array([distance_py(a[k], b[k], L) for k in range(dim)])
+            link += float(dr @ dr)
+            pot += V(a) + V(b)
+            vkin += float(a @ dV(a))
+    E = dim * N / (2 * tau) - 1 / (4 * lam * tau ** 2 * M) * link + 1 / (2 * M) * pot
+    Ev = 1 / (2 * M) * vkin + 1 / (2 * M) * pot
+    return E, Ev
+
+
+def test_teleport_distance_against_python(oracle):
+    ob = oracle
+    rng = np.random.default_rng(0)
+    for L in (4.0, 100.0, 0.37):
+        for x in np.concatenate([rng.uniform(-5 * L, 5 * L, 500), [L, -L, 0.0, 3 * L, -3 * L, 1e-300, -1e-17]]):
+            assert ob.lib().ora_teleport(x, L) == teleport_py(x, L)
+            t = ob.lib().ora_teleport(x, L)
+            assert -L <= t <= L
+            y = rng.uniform(-L, L)
+            assert ob.lib().ora_distance(x, y, L) == distance_py(x, y, L)
+
+
+@pytest.mark.parametrize("dim", [1, 2])
+def test_levy_against_numpy(oracle, dim):
+    ob = oracle
+    rng = np.random.default_rng(1)
+    for rows, L, lam, tau in [(3, 4.0, 1.0, 0.01), (12, 100.0, 0.5, 0.2), (100, 4.0, 1.0, 0.01), (6, 0.5, 2.0, 0.3)]:
+        for trial in range(20):
+            r = np.zeros((rows, dim))
+            r[0], r[-1] = rng.uniform(-L, L, dim), rng.uniform(-L, L, dim)
+            if trial == 0:
+                r[0], r[-1] = 0.95 * L, -0.95 * L
+            xi = rng.standard_normal((rows - 2, dim))
+            ref = levy_py(r, tau, L, lam, xi)
+            cm = np.ascontiguousarray(r.T)  # oracle layout: column-major rows x dim
+            ob.lib().ora_levy(ob._p(cm), rows, dim, tau, L, lam, ob._p(np.ascontiguousarray(xi)))
+            assert np.array_equal(cm.T, ref)
+            # bridge sanity: endpoints fixed (mod box), interior finite
+            assert np.all(np.abs(cm) <= L)
+
+
+def test_bridge_statistics(oracle):
+    """Levy bridge between equal endpoints: bead t of an m-link bridge has variance 2*lam*tau*t*(m-t)/m (free particle)."""
+    ob = oracle
+    rng = np.random.default_rng(2)
+    rows, L, lam, tau, nb = 9, 1e6, 0.7, 0.13, 20000
+    out = np.zeros((nb, rows))
+    for b in range(nb):
+        cm = np.zeros((1, rows))
+        xi = rng.standard_normal((rows - 2, 1))
+        ob.lib().ora_levy(ob._p(cm), rows, 1, tau, L, lam, ob._p(xi))
+        out[b] = cm[0]
+    m = rows - 1
+    for t in range(1, m):
+        var = 2 * lam * tau * t * (m - t) / m
+        assert abs(out[:, t].var() / var - 1) < 0.05
+
+
+def test_energy_density_against_numpy(oracle):
+    ob = oracle
+    rng = np.random.default_rng(3)
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=7, N=4, L=3.0, T=0.8, lam=0.5, seed=5)
+    r = rng.uniform(-3, 3, (4, 2, 7))
+    nxt = np.array([2, 1, 3, 4], dtype=np.int64)  # one exchange cycle of length 2
+    s.set_paths(r, nxt)
+    E, Ev, parts = s.energy_now()
+    Er, Evr = energy_py(r, nxt, 3.0, s.tau, 0.5, lambda x: 0.5 * (x[0] ** 2 + x[1] ** 2), lambda x: x)
+    assert abs(E - Er) <= 1e-12 * abs(4 * 2 / (2 * s.tau)) and abs(Ev - Evr) <= 1e-12 * abs(Evr)
+    # Density (src/measurement.jl:45-55): compat (shifted, floor-bin 0 dropped) vs numpy
+    d = ob.Density(s, 10)
+    d.measure(s)
+    dens, nd, binw = d.read()
+    ref = np.zeros((10, 10))
+    for n in range(4):
+        for m in range(7):
+            ib = np.floor((r[n, :, m] + 3.0) / binw).astype(int)
+            if np.all(ib > 0) and np.all(ib < 11):
+                ref[ib[0] - 1, ib[1] - 1] += 1
+    assert np.array_equal(dens, ref) and nd == 7 and binw == 0.6
+
+
+def test_lattice_intensity_reference_kat(oracle):
+    """test/testpotential.jl:26-30: the 3-beam lattice intensity is 1.0 at the origin and at two lattice peaks."""
+    ob = oracle
+    p = ob.make_potential("lattice", depth=1.0, scale=1.0, sgn=1.0, angles=[2 * math.pi * k / 3 for k in range(3)])
+    for pt in ([0.0, 0.0], [2 / math.sqrt(3), 0.0], [0.0, 2 / 3]):
+        v = ob.lib().ora_potential_eval(C.byref(p), ob._p(np.array(pt)), 2)
+        assert v == pytest.approx(1.0, rel=1e-12)
+
+
+def test_system_constructor_smoke_reference_tests(oracle):
+    """test/testsystem.jl:8-35: default System(v1d) has N == 2; the 2-D lattice system has N == 5."""
+    ob = oracle
+    s = ob.System(ob.make_potential("sin2_1d", depth=8.0, scale=0.5), dim=1)
+    assert s.N == 2 and s.M == 100 and s.nbins == 8 and s.a == 0.0
+    ang = [2 * math.pi * k / 4 for k in range(4)]
+    s = ob.System(ob.make_potential("lattice", depth=8.0, scale=0.5, sgn=1.0, angles=ang), dim=2, M=100, N=5, L=4.0, T=1.0)
+    assert s.N == 5
+    r, V, bins, nxt = s.paths()
+    assert np.all(np.abs(r) <= 4.0) and np.array_equal(nxt, np.arange(1, 6))
+    assert np.array_equal(r[:, :, 0], r[:, :, -1])  # closed ring: last slice sits on the first (system.jl:53-54)
+
+
+def test_periodic_bounds_reference_test(oracle):
+    """test/testsystem.jl:37-56: after 10 000 mixed updates on V = 0 no bead has left the box."""
+    ob = oracle
+    s = ob.System(ob.make_potential("zero"), seed=42)
+    ups = [(2, ob.Update(s, ob.UPD_SINGLE_COM, 3.0)), (1, ob.Update(s, ob.UPD_RESHAPE_LINEAR, 20)), (1, ob.Update(s, ob.UPD_RESHAPE_SWAP, 20))]
+    s.run(10000, ups)
+    r, V, bins, nxt = s.paths()
+    assert np.all(r <= s.L) and np.all(r >= -s.L)
+    assert sorted(nxt.tolist()) == [1, 2]  # still a permutation
+    assert np.allclose(V, 0.0)
+    for _, u in ups:
+        g = u.get()
+        assert g["tries"] > 1000 and 0 <= g["acc_window"] <= 1
+
+
+def test_density_normalisation_reference_test(oracle):
+    """test/testmeasurements.jl:1-33: sum(dens)/ndata ~ N within 1e-2 (the tolerance absorbs the dropped floor-bin 0)."""
+    ob = oracle
+    s = ob.System(ob.make_potential("sin2_1d", depth=8.0, scale=0.5), dim=1, seed=9)
+    ups = [(2, ob.Update(s, ob.UPD_SINGLE_COM, 3.0)), (1, ob.Update(s, ob.UPD_RESHAPE_LINEAR, 20)), (1, ob.Update(s, ob.UPD_RESHAPE_SWAP, 20))]
+    d = ob.Density(s, 500)
+    s.run(10000, ups, densities=[d])
+    dens, nd, _ = d.read()
+    assert nd == (10000 // 10) * 100
+    assert abs(dens.sum() / nd - s.N) < 1e-2
+
+
+def harmonic_energy_finite_M(M, beta=1.0, dim=2, omega=1.0):
+    """closed form for the primitive action: Z_M = [2 sinh(M theta/2)]^-dim, cosh(theta) = 1 + (omega tau)^2/2."""
+    import mpmath as mp
+    mp.mp.dps = 30
+
+    def lnZ(b):
+        tau = b / M
+        th = mp.acosh(1 + (omega * tau) ** 2 / 2)
+        return -dim * mp.log(2 * mp.sinh(M * th / 2))
+    return float(-mp.diff(lnZ, beta))
+
+
+def test_closed_form_constants():
+    assert harmonic_energy_finite_M(5) == pytest.approx(2.156259612426946, rel=1e-10)
+    assert harmonic_energy_finite_M(10) == pytest.approx(2.162019287996358, rel=1e-10)
+    assert 1 / math.tanh(0.5) == pytest.approx(2.1639534137386534, rel=1e-14)  # examples/energy_2d_harmonically_trapped_bose_gas.jl:28
+
+
+def _chain_means(ob, chains, therm, n, seed0, M=5):
+    Es, Evs = [], []
+    for c in range(chains):
+        s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=1, L=100.0, T=1.0, lam=0.5, Ncycle=10, seed=seed0, chain=c)
+        ups = [(1, ob.Update(s, ob.UPD_SINGLE_COM, 1.0)), (1, ob.Update(s, ob.UPD_RESHAPE_LINEAR, 2))]
+        s.run(therm, ups)
+        e = ob.Energy(n // 10 + 1)
+        s.run(n, ups, energies=[e])
+        E, Ev = e.read()
+        Es.append(E.mean())
+        Evs.append(Ev.mean())
+    return np.array(Es), np.array(Evs)
+
+
+def test_c1_energy_z_test(oracle):
+    """C1 as shipped (examples/energy_2d_harmonically_trapped_bose_gas.jl): sampled <E_thermo>, <E_virial> agree with the
+    finite-M closed form 2.1562596 within |z| < 4 (independent chains give the error bar)."""
+    ob = oracle
+    Es, Evs = _chain_means(ob, 24, 30000, 150000, seed0=123)
+    target = 2.156259612426946
+    for x in (Es, Evs):
+        z = (x.mean() - target) / (x.std(ddof=1) / math.sqrt(len(x)))
+        assert abs(z) < 4, (x.mean(), z)
+
+
+def test_adjust_rules(oracle):
+    ob = oracle
+    L = ob.lib()
+    assert L.ora_adjust_step(1.0, 0.1, 2.0, 0.4, 0.6, 0.3) == 0.9
+    assert L.ora_adjust_step(1.0, 0.1, 2.0, 0.4, 0.6, 0.7) == 1.1
+    assert L.ora_adjust_step(3.0, 0.1, 2.0, 0.4, 0.6, 0.5) == 2.0
+    assert L.ora_adjust_step(3.0, 0.1, 2.0, 0.4, 0.6, float("nan")) == 2.0  # empty window: only the clamps act
+    assert L.ora_adjust_slices(5, 2, 8, 0.6, 0.8, 0.5) == 4
+    assert L.ora_adjust_slices(8, 2, 8, 0.6, 0.8, 0.9) == 8
+    assert L.ora_adjust_slices(2, 2, 8, 0.6, 0.8, 0.1) == 2
+    assert L.ora_metropolis(1.0, 0.999) == 1 and L.ora_metropolis(0.5, 0.6) == 0 and L.ora_metropolis(0.5, 0.4) == 1
+    assert L.ora_metropolis(float("nan"), 0.0) == 0
+
+
+def test_cycles_and_bins(oracle):
+    ob = oracle
+    s = ob.System(ob.make_potential("zero"), dim=2, M=6, N=5, L=4.0, seed=2)
+    r = s.paths()[0]
+    s.set_paths(r, np.array([3, 2, 5, 4, 1], dtype=np.int64))  # cycle 1->3->5->1, fixed points 2, 4
+    cyc = np.zeros(6, dtype=np.int64)
+    n = ob.lib().ora_subcycle(s.h, 1, ob._pi(cyc))
+    assert n == 3 and cyc[:3].tolist() == [1, 3, 5]
+    assert ob.lib().ora_cycle_findprev(s.h, 1) == 5
+    pol = np.array([1, 3, 5], dtype=np.int64)
+    got = [ob.lib().ora_pcycle(j, ob._pi(pol), 3, 6) for j in (1, 6, 7, 12, 13, 18, 19)]
+    assert got == [1, 1, 3, 3, 5, 5, 1]  # helper.jl:113-115
+    nb = np.zeros(9, dtype=np.int64)
+    ob.lib().ora_bin_neighbors(1, 8, 2, ob._pi(nb))
+    assert nb.tolist() == [1, 16, 9, 10, 8, 2, 64, 57, 58]  # nearest_neighbours.jl:55-65 (periodic 3x3 stencil)
+    assert ob.lib().ora_bin(ob._p(np.array([-4.0, -4.0])), 2, 8, 4.0) == 1
+    assert ob.lib().ora_bin(ob._p(np.array([3.99, -4.0])), 2, 8, 4.0) == 8
+    assert ob.lib().ora_bin(ob._p(np.array([-4.0, 3.99])), 2, 8, 4.0) == 57
+    # every bead is filed in the cell its stored bin names
+    r, V, bins, nxt = s.paths()
+    for j in (1, 4):
+        for n_ in range(1, 6):
+            out = np.zeros(16, dtype=np.int64)
+            k = ob.lib().ora_nn_cell(s.h, j, int(bins[n_ - 1, j - 1]), ob._pi(out))
+            assert n_ in out[:k].tolist()
+
+
+def test_find_nn_brute_force(oracle):
+    ob = oracle
+    s = ob.System(ob.make_potential("zero"), dim=2, M=4, N=40, L=4.0, r_a=1.0, seed=8)
+    r = s.paths()[0]
+    rng = np.random.default_rng(5)
+    for t in range(50):
+        q = rng.uniform(-4, 4, 2)
+        j = int(rng.integers(1, 5))
+        exc = np.array([int(rng.integers(1, 41))], dtype=np.int64)
+        out = np.zeros(400, dtype=np.int64)
+        cnt = ob.lib().ora_find_nns_pos(s.h, ob._p(q.copy()), j, ob._pi(exc), 1, ob._pi(out))
+        d = np.sqrt(sum(np.minimum(np.abs(r[:, k, j - 1] - q[k]), 8 - np.abs(r[:, k, j - 1] - q[k])) ** 2 for k in range(2)))
+        brute = sorted(int(i + 1) for i in np.nonzero(d <= 1.0)[0] if i + 1 != exc[0])
+        assert sorted(out[:cnt].tolist()) == brute  # cell width == cutoff: the stencil holds every particle within range
+        nn = ob.lib().ora_find_nn(s.h, ob._p(q.copy()), j, ob._pi(exc), 1)
+        if brute:
+            dm = d.copy()
+            dm[exc[0] - 1] = np.inf
+            assert nn == int(np.argmin(dm)) + 1
+
+
+def test_swap_detailed_state(oracle):
+    """an accepted swap exchanges `next`, rewrites the bridged beads and swaps the tails (reshape.jl:250-278); the link cache
+    stays consistent with the positions."""
+    ob = oracle
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=8, N=3, L=4.0, T=1.0, lam=0.5, seed=4)
+    r0, V0, _, n0 = s.paths()
+    rng = np.random.default_rng(6)
+    xi1, xi2 = 0.01 * rng.standard_normal((2, 2)), 0.01 * rng.standard_normal((2, 2))
+    wi, wu = C.c_double(), C.c_double()
+    acc = ob.lib().ora_reshape_swap_explicit(s.h, 1, 2, 2, 3, ob._p(xi1), ob._p(xi2), 0.0, 1, C.byref(wi), C.byref(wu))
+    assert acc == 1  # u = 0 accepts whenever delta > 0
+    r1, V1, _, n1 = s.paths()
+    assert n1.tolist() == [2, 1, 3]
+    assert np.array_equal(r1[0, :, 5:], r0[1, :, 5:]) and np.array_equal(r1[1, :, 5:], r0[0, :, 5:])  # tails j_m+1..M swapped
+    assert np.array_equal(r1[0, :, :2], r0[0, :, :2]) and np.array_equal(r1[2], r0[2])
+    assert abs(ob.lib().ora_action_links(s.h) - ob.lib().ora_action_links_recomputed(s.h)) < 1e-12
+
+
+def test_sweep_equals_sequential_definition(oracle):
+    """the sweep schedule is executed sequentially by the oracle; total proposals per iteration equal N for the staging move."""
+    ob = oracle
+    s = ob.System(ob.make_potential("zero"), dim=2, M=16, N=7, L=4.0, seed=3)
+    u = ob.Update(s, ob.UPD_RESHAPE_LINEAR, 5)
+    s.run(11, [(1, u)], sched=ob.SCHED_SWEEP)
+    g = u.get()
+    assert g["tries"] == 77 and g["accepted"] == 77 and g["var"] == 12.0  # free particles: always accepted; m grows by one whenever tries crosses a multiple of adj (7 of 11 sweeps)
+    with pytest.raises(RuntimeError):
+        s2 = ob.System(ob.make_potential("zero"), dim=2, M=8, N=3, L=4.0, interactions=True, g=1.5, r_a=1.0)
+        s2.run(1, [(1, ob.Update(s2, ob.UPD_RESHAPE_LINEAR, 3))], sched=ob.SCHED_SWEEP)
