@@ -1,0 +1,125 @@
+"""GPU tests through the host-side mirror of the reference API (pimc_jl_b200.pimc): the reference's own tests and example
+scripts restated, sampled observables against closed forms and against the CPU oracle (|z| < 3)."""
+import math
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from pimc_jl_b200.pimc import (System, SingleCenterOfMass, PolymerCenterOfMass, ReshapeLinear, ReshapeSwapLinear, Energy, Density,
+                               run_b, acceptance, harmonic, zero_potential, sin2_1d, generate_V, levy_b, distance, teleport, bin, subcycle)
+
+E_M5 = 2.156259612426946  # finite-M closed form for the shipped trapped example
+
+
+def zscore(x, target):
+    return (x.mean() - target) / (x.std(ddof=1) / math.sqrt(len(x)))
+
+
+@pytest.mark.parametrize("schedule", ["faithful", "sweep"])
+def test_example_energy_2d_harmonically_trapped(schedule):
+    """examples/energy_2d_harmonically_trapped_bose_gas.jl as shipped (M=5, N=1, L=100, T=1), 2048 chains."""
+    s = System(harmonic(), dV="identity", lam=0.5, M=5, N=1, L=100.0, T=1.0, length_measurement_cycle=10, chains=2048, seed=2024, schedule=schedule)
+    updates = [(1, SingleCenterOfMass(s, 1.0)), (1, ReshapeLinear(s, 2))]
+    mea = [Energy(s, 4000)]
+    run_b(s, 10_000, updates)
+    while s.N_MC[s.N] < 3000:
+        run_b(s, 10_000, updates, Zmeasurements=mea)
+    n, E, Ev = mea[0].chain_stats()
+    assert np.all(n == 3000)
+    assert abs(zscore(E, E_M5)) < 3 and abs(zscore(Ev, E_M5)) < 3, (E.mean(), Ev.mean())
+    series = mea[0].energy[s.N]
+    assert len(series) == 3000 and abs(series.mean() - E.mean()) < 1e-9
+    assert 0.3 < acceptance(updates[0][1].counter_var.queue) < 0.7  # COM step adapted into its 0.4-0.6 band
+    assert updates[1][1].var.m == 3  # maxslices = M - 2
+    assert abs(E.mean() - 2.1639534137386534) < 0.05  # the script's `exact` (continuum) is 0.0077 above the M=5 value
+
+
+def test_example_energy_2d_free(oracle):
+    """examples/energy_2d_free_bose_gas.jl (N=1, M=10, L=100): <E_thermo> = dim/(2 beta) = 1; GPU and oracle agree within errors."""
+    s = System(zero_potential(), dV="identity", lam=1.0, L=100.0, M=10, N=1, T=1.0, length_measurement_cycle=2, chains=1024, seed=5)
+    ups = [(1, SingleCenterOfMass(s, 1.0)), (1, ReshapeLinear(s, 20))]
+    mea = [Energy(s, 6000)]
+    run_b(s, 4000, ups)
+    run_b(s, 10_000, ups, Zmeasurements=mea)
+    n, E, Ev = mea[0].chain_stats()
+    assert abs(zscore(E, 1.0)) < 3
+    ob = oracle
+    Eo = []
+    for c in range(48):
+        so = ob.System(ob.make_potential("zero", "identity"), dim=2, M=10, N=1, L=100.0, T=1.0, lam=1.0, Ncycle=2, seed=77, chain=c)
+        uo = [(1, ob.Update(so, ob.UPD_SINGLE_COM, 1.0)), (1, ob.Update(so, ob.UPD_RESHAPE_LINEAR, 20))]
+        so.run(4000, uo)
+        eo = ob.Energy(6000)
+        so.run(10_000, uo, energies=[eo])
+        Eo.append(eo.read()[0].mean())
+    Eo = np.array(Eo)
+    z = (E.mean() - Eo.mean()) / math.sqrt(E.var(ddof=1) / len(E) + Eo.var(ddof=1) / len(Eo))
+    assert abs(z) < 3, (E.mean(), Eo.mean(), z)
+
+
+def test_two_bosons_exchange_runs_and_conserves_structure():
+    """swap moves on the GPU keep `next` a permutation and the link cache consistent with the positions"""
+    s = System(harmonic(), dV="identity", lam=0.5, M=20, N=4, L=6.0, T=0.5, chains=64, seed=3)
+    ups = [(1, PolymerCenterOfMass(s, 1.0)), (1, ReshapeLinear(s, 10)), (1, ReshapeSwapLinear(s, 10))]
+    run_b(s, 3000, ups)
+    r, V, bins, nxt = s.engine.paths()
+    assert all(sorted(row.tolist()) == [1, 2, 3, 4] for row in nxt)
+    assert any(not np.array_equal(row, [1, 2, 3, 4]) for row in nxt)  # some chain holds an exchange cycle
+    a, b = s.engine.action()
+    assert np.all(np.abs(a - b) <= 1e-10 * np.maximum(1.0, np.abs(a)))
+    w = s.world_of(5)
+    npol, pol = subcycle(w, 1)
+    assert 1 <= npol <= 4 and pol[0] == 1
+
+
+def test_reference_testsystem_periodic_bounds():
+    """test/testsystem.jl:37-56"""
+    s = System(zero_potential(), chains=32, seed=1)
+    updates = [(2, SingleCenterOfMass(s, 3.0)), (1, ReshapeLinear(s, 20)), (1, ReshapeSwapLinear(s, 20))]
+    run_b(s, 10_000, updates)
+    for c in (0, 7, 31):
+        for p in s.world_of(c):
+            assert not np.any(np.all(p.r > s.L, axis=1)) and not np.any(np.all(p.r < -s.L, axis=1))
+            assert np.all(np.abs(p.r) <= s.L)
+
+
+def test_reference_testmeasurements_density():
+    """test/testmeasurements.jl:1-33"""
+    s = System(sin2_1d(8.0, 0.5), dim=1, chains=16, seed=4)
+    assert s.N == 2  # test/testsystem.jl:15-17
+    updates = [(2, SingleCenterOfMass(s, 3.0)), (1, ReshapeLinear(s, 20)), (1, ReshapeSwapLinear(s, 20))]
+    d = Density(s)
+    run_b(s, 10000, updates, Zmeasurements=[d])
+    numb = d.dens.sum() / d.ndata
+    assert abs(numb - s.N) < 1e-2
+    assert d.ndata == 16 * 1000 * s.M and d.dens.shape == (500,)
+
+
+def test_reference_testsystem_initialization2d_and_lattice_density():
+    s = System(generate_V(0.5, 8.0, "cubic", attractive=False), dim=2, M=100, N=5, L=4.0, T=1.0, chains=8)
+    assert s.N == 5  # test/testsystem.jl:20-34
+    d = Density(s, nbins=64)
+    ups = [(1, SingleCenterOfMass(s, 1.0)), (1, ReshapeLinear(s, 5)), (1, ReshapeSwapLinear(s, 20))]
+    run_b(s, 2000, ups)
+    run_b(s, 3000, ups, Zmeasurements=[d])
+    dens = d.dens
+    assert dens.shape == (64, 64) and abs(dens.sum() / d.ndata - 5) < 0.2
+    # repulsive 4-beam lattice: density avoids the intensity maximum at the origin relative to the mean
+    assert dens[31:33, 31:33].mean() < dens.mean()
+
+
+def test_debug_exports():
+    assert distance(3.5, -3.5, 4.0) == 1.0 and teleport(5.0, 4.0) == -3.0
+    assert bin([-4.0, -4.0], 8, 4.0) == 1 and bin([3.9, 3.9], 8, 4.0) == 64
+    r = np.zeros((6, 2))
+    r[0], r[-1] = [0.5, -0.5], [1.0, 1.0]
+    xi = np.random.default_rng(0).standard_normal((4, 2))
+    out = levy_b(r.copy(), 0.01, 4.0, 1.0, xi)
+    assert np.array_equal(out[0], r[0]) and np.array_equal(out[-1], r[-1]) and np.all(np.abs(out) <= 4)
+    with pytest.raises(TypeError):
+        System(lambda r: 0.0)
+    s = System(zero_potential(), M=8, N=2, chains=1)
+    e = Energy(s, 3)
+    with pytest.raises(Exception):
+        run_b(s, 100, [(1, ReshapeLinear(s, 3))], Zmeasurements=[e])  # 10 measurements into a vector of 3: the reference errors too
