@@ -43,11 +43,12 @@ typedef struct {
     double ang[PIMC_MAX_ANGLES];
 } pimc_potential;
 
-/* compat flags: set = reproduce the reference as shipped (SURVEY.md 2.2 B3, B4, B5) */
+/* compat flags: set = reproduce the reference as shipped (SURVEY.md 2.2 B3, B4, B5; DESIGN.md B13, B14) */
 #define PIMC_COMPAT_PAIR_BYVALUE  1
 #define PIMC_COMPAT_SWAP_SIGN     2
 #define PIMC_COMPAT_DENSITY_SHIFT 4
-#define PIMC_COMPAT_ALL           7
+#define PIMC_COMPAT_SWAP_STALE_LINK 8 /* B14: an accepted swap leaves the cached link at slice j_m un-exchanged (reshape.jl:269-275) */
+#define PIMC_COMPAT_ALL           15
 
 /* keyword arguments of System(...) (src/system.jl:129-145) + batching / sharding / seed */
 typedef struct {
@@ -92,6 +93,9 @@ void pimc_destroy(pimc_handle *h);                                      /* Julia
 const char *pimc_last_error(const pimc_handle *h);                      /* NULL handle: last create error     */
 int  pimc_version(void);
 int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run kernels on this cudaStream_t   */
+/* engine options (no reference counterpart). PIMC_OPT_SWEEP_IMPL: 0 auto, 1 persistent kernel (k_run), 2 per-iteration sweep kernels */
+#define PIMC_OPT_SWEEP_IMPL 1
+int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
 /* measurement utility (no reference counterpart): sustained non-tensor fp64 FMA rate of the current device, in TFLOP/s */
 int  pimc_measure_fp64_peak(double *tflops);

@@ -681,6 +681,9 @@ static int reshape_swap_core(ora_system *s, int64_t n1, int64_t n2, int64_t j0, 
                     double vv = V_(s, n1, j); V_(s, n1, j) = V_(s, n2, j); V_(s, n2, j) = vv;
                 }
             }
+            if (!(s->compat & ORA_COMPAT_SWAP_STALE_LINK) && jm <= M) { /* intended: the link leaving slice j_m changes owner too */
+                double vv = V_(s, n1, jm); V_(s, n1, jm) = V_(s, n2, jm); V_(s, n2, jm) = vv;
+            }
             add_nn(s, pol1, Np1); add_nn(s, pol2, Np2); /* merged cycles are added twice, as in the reference */
         }
     }

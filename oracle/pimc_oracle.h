@@ -39,7 +39,8 @@ typedef struct {
 #define ORA_COMPAT_PAIR_BYVALUE  1 /* B3: interaction_action! mutates a by-value Float64 -> no effect */
 #define ORA_COMPAT_SWAP_SIGN     2 /* B4: new-configuration lnU added to w_initial                   */
 #define ORA_COMPAT_DENSITY_SHIFT 4 /* B5: Density drops floor-bin 0, shifted by one bin               */
-#define ORA_COMPAT_ALL           7
+#define ORA_COMPAT_SWAP_STALE_LINK 8 /* B14: accepted swap leaves the cached link at slice j_m un-exchanged */
+#define ORA_COMPAT_ALL           15
 
 typedef struct {
     int32_t dim, M, N;

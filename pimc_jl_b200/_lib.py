@@ -15,7 +15,8 @@ POT_ZERO, POT_HARMONIC, POT_SIN2_1D, POT_LATTICE = 0, 1, 2, 3
 DV_ZERO, DV_IDENTITY, DV_GRADIENT = 0, 1, 2
 UPD_RESHAPE_LINEAR, UPD_RESHAPE_SWAP, UPD_SINGLE_COM, UPD_POLYMER_COM = 0, 1, 2, 3
 SCHED_FAITHFUL, SCHED_SWEEP = 0, 1
-COMPAT_PAIR_BYVALUE, COMPAT_SWAP_SIGN, COMPAT_DENSITY_SHIFT, COMPAT_ALL = 1, 2, 4, 7
+OPT_SWEEP_IMPL = 1
+COMPAT_PAIR_BYVALUE, COMPAT_SWAP_SIGN, COMPAT_DENSITY_SHIFT, COMPAT_SWAP_STALE_LINK, COMPAT_ALL = 1, 2, 4, 8, 15
 
 f64p = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)
@@ -59,6 +60,7 @@ SIGNATURES = {
     "pimc_last_error": (C.c_char_p, [_vp]),
     "pimc_version": (C.c_int, []),
     "pimc_set_stream": (C.c_int, [_vp, _vp]),
+    "pimc_set_option": (C.c_int, [_vp, _i32, _i64]),
     "pimc_launch_count": (C.c_int64, []),
     "pimc_measure_fp64_peak": (C.c_int, [f64p]),
     "pimc_get_paths": (C.c_int, [_vp, _i32, _i32, f64p, f64p, i64p, i64p]),

@@ -1,6 +1,7 @@
 // pimc_b200.cu -- kernels and C ABI of libpimc_b200.so (sm_100a).  See include/pimc_b200.h and DESIGN.md.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include "pimc_moves.cuh"
+#include "pimc_sweep.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -395,6 +396,7 @@ struct pimc_handle {
     std::vector<void *> allocs;
     long long de_ndata[PIMC_MAXD];
     double r_a; double vol;
+    int opt_sweep_impl;
     cudaEvent_t ev0, ev1;
     int device;
 };
@@ -491,7 +493,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0;
     memset(&h->T, 0, sizeof h->T);
     int rc = PIMC_OK;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
@@ -531,6 +533,14 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
     }
     RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4));
+    {   // staging tables: alpha_k = (k-1)/k, sigma_k = sqrt(((2 lambda) alpha_k) tau), k = 2..M (same IEEE operations as levy!)
+        std::vector<double> ta(S.M + 1, 0.0), ts(S.M + 1, 0.0);
+        for (int k = 2; k <= S.M; ++k) { volatile double al = (double)(k - 1) / (double)k; volatile double v = 2 * S.lambda; v = v * al; v = v * S.tau; ta[k] = al; ts[k] = sqrt((double)v); }
+        double *da, *ds; RCC(dalloc(h, &da, ta.size())); RCC(dalloc(h, &ds, ts.size()));
+        CKC(cudaMemcpy(da, ta.data(), ta.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(ds, ts.data(), ts.size() * sizeof(double), cudaMemcpyHostToDevice));
+        S.tab_alpha = da; S.tab_sig = ds;
+    }
     CKC(cudaEventCreate(&h->ev0)); CKC(cudaEventCreate(&h->ev1));
     {   // identity permutation
         std::vector<int> nx((size_t)S.C * S.N);
@@ -546,6 +556,12 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
 }
 
 extern "C" int pimc_set_stream(pimc_handle *h, void *s) { if (!h) return PIMC_ERR_INVALID; h->stream = (cudaStream_t)s; return PIMC_OK; }
+extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
+    SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
+}
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
 extern "C" int pimc_get_scalars(pimc_handle *h, double *o, int64_t *io)
 {
@@ -970,8 +986,59 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
     int launches = 0;
+    // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
+    const int pk = S.pot.kind;
+    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (size_t)S.N + 16;
+    const size_t smem_cs = (size_t)(SWEEP_THREADS / 32) * 3 * S.M * sizeof(double) + (size_t)S.N + 16;
+    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M + 1 <= SWEEP_BCAP && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
+    bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
+    if (h->opt_sweep_impl == 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", SWEEP_BCAP - 1); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    if (n > 0) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
+    if (n > 0 && !batched) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
+    if (n > 0 && batched) {
+        bool has_rs = false, has_com = false, has_swap = false;
+        for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_HARMONIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_HARMONIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        SweepParams SP; memset(&SP, 0, sizeof SP);
+        SP.nupd = nupd; SP.stats = h->dstats;
+        for (int i = 0; i < nupd; ++i) { SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; }
+        MeasParams MP; memset(&MP, 0, sizeof MP);
+        MP.nen = nen; MP.nde = nde;
+        for (int i = 0; i < nen; ++i) MP.en_id[i] = P.en_id[i];
+        for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
+        for (long long it = 0; it < n; ++it) {
+            SP.iter = h->iter + (unsigned long long)it;
+            if (has_com) {
+                if (pk == PIMC_POT_ZERO) k_com_sweep<PIMC_POT_ZERO><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
+                else if (pk == PIMC_POT_HARMONIC) k_com_sweep<PIMC_POT_HARMONIC><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
+                else k_com_sweep<PIMC_POT_LATTICE><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
+                LAUNCHED(); launches++;
+            }
+            if (has_rs) {
+                if (pk == PIMC_POT_ZERO) k_reshape_sweep<PIMC_POT_ZERO><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
+                else if (pk == PIMC_POT_HARMONIC) k_reshape_sweep<PIMC_POT_HARMONIC><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
+                else k_reshape_sweep<PIMC_POT_LATTICE><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
+                LAUNCHED(); launches++;
+            }
+            if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if (nen + nde > 0) {
+                long long ctrv = h->Nctr + it + 1;
+                if (ctrv % h->cfg.Ncycle == 0) {
+                    MP.k = h->N_MC + ctrv / h->cfg.Ncycle - 1;
+                    k_measure<<<S.C, 256, 0, h->stream>>>(S, h->dT, MP); LAUNCHED(); launches++;
+                }
+            }
+        }
+    }
     CK(h, cudaEventRecord(h->ev1, h->stream));
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));

@@ -30,6 +30,7 @@ struct DevSys {
     double *r, *Vl;
     int *next;
     double *prop, *propV, *wtab;
+    const double *tab_alpha, *tab_sig; // [M+1] staging tables indexed by k = rows left: alpha_k = (k-1)/k, sigma_k = sqrt(((2 lambda) alpha_k) tau)  (helper.jl:131-134)
     // cell list (replaces src/nearest_neighbours.jl): per (chain, slice) singly linked lists
     int need_cells, nbins, ncell;
     double cellw;

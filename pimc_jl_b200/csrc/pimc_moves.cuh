@@ -196,6 +196,9 @@ __device__ __forceinline__ int d_reshape_swap(const DevSys &S, int c, int n1, in
                     }
                 }
             }
+            if (!(S.compat & PIMC_COMPAT_SWAP_STALE_LINK) && jm <= M) { // intended: the link leaving slice j_m changes owner too
+                double tv = S.Vl[VIDX(S, c, n1, jm - 1)]; S.Vl[VIDX(S, c, n1, jm - 1)] = S.Vl[VIDX(S, c, n2, jm - 1)]; S.Vl[VIDX(S, c, n2, jm - 1)] = tv;
+            }
             if (S.need_cells) {
                 // rm_nn!(old cycles) ... add_nn!(new pol1), add_nn!(new pol2) (reshape.jl:250-251,277-278): when the swap MERGED two
                 // cycles the new pol1 and pol2 are the same set and every member is pushed twice into every slice's list

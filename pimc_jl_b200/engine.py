@@ -65,6 +65,9 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.lib.pimc_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, option, value):
+        self._ck(self.lib.pimc_set_option(self.h, option, value))
+
     def set_iter(self, it):
         self._ck(self.lib.pimc_set_iter(self.h, it))
 

@@ -13,7 +13,7 @@ are sharded over the ranks (one process per GPU) and estimator read-outs are all
 import math
 import os
 import numpy as np
-from . import _lib as L
+from . import _lib as _L
 from . import engine as _eng
 from .engine import Engine
 
@@ -30,7 +30,7 @@ class PotentialSpec(dict):
 
     def __call__(self, r):
         r = np.atleast_2d(np.asarray(r, dtype=np.float64))
-        return _eng.potential_eval(r, L.make_potential(**self))[0]
+        return _eng.potential_eval(r, _L.make_potential(**self))[0]
 
 
 def zero_potential():            # _ -> 0.0
@@ -144,12 +144,12 @@ class _Update:
     def __call__(self, s):
         """functor call f(s)::Bool on every chain (one faithful iteration of this update); returns chain 0's outcome"""
         before = self._get()["accepted"]
-        s.engine.run(1, [(1, self.id)], sched=L.SCHED_FAITHFUL)
+        s.engine.run(1, [(1, self.id)], sched=_L.SCHED_FAITHFUL)
         return self._get()["accepted"] > before
 
 
 class ReshapeLinear(_Update):      # src/updates/reshape.jl:7-29
-    KIND = L.UPD_RESHAPE_LINEAR
+    KIND = _L.UPD_RESHAPE_LINEAR
 
     def __init__(self, s, slices, minslices=2, maxslices=None, minacc=0.6, maxacc=0.8, adj=10, range=10_000):
         maxslices = s.M - 2 if maxslices is None else maxslices
@@ -157,18 +157,18 @@ class ReshapeLinear(_Update):      # src/updates/reshape.jl:7-29
 
 
 class ReshapeSwapLinear(ReshapeLinear):  # src/updates/reshape.jl:99-121
-    KIND = L.UPD_RESHAPE_SWAP
+    KIND = _L.UPD_RESHAPE_SWAP
 
 
 class SingleCenterOfMass(_Update):  # src/updates/com.jl:112-133
-    KIND = L.UPD_SINGLE_COM
+    KIND = _L.UPD_SINGLE_COM
 
     def __init__(self, s, step, minstep=1e-1, maxstep=None, minacc=0.4, maxacc=0.6, adj=10, range=10_000):
         super().__init__(s, float(step), minstep, s.L / 2 if maxstep is None else maxstep, minacc, maxacc, adj, range)
 
 
 class PolymerCenterOfMass(SingleCenterOfMass):  # src/updates/com.jl:7-28 (worms = 0 reading)
-    KIND = L.UPD_POLYMER_COM
+    KIND = _L.UPD_POLYMER_COM
 
 
 def acceptance(q):                  # src/simulation.jl:1
@@ -234,7 +234,7 @@ class Density:                      # src/measurement.jl:31-55
 
 class System:                       # src/system.jl:93-168
     def __init__(self, potential, dV="zero", dim=2, M=100, N=2, mu=0.0, L=4.0, T=1.0, lam=1.0, interactions=False, propint=None,
-                 g=0.0, r_a=0.0, length_measurement_cycle=10, measure_scheme="c", chains=None, seed=None, compat=L.COMPAT_ALL,
+                 g=0.0, r_a=0.0, length_measurement_cycle=10, measure_scheme="c", chains=None, seed=None, compat=_L.COMPAT_ALL,
                  schedule=None, device=-1):
         if isinstance(potential, PotentialSpec):
             spec = dict(potential)
@@ -255,7 +255,7 @@ class System:                       # src/system.jl:93-168
             if propint is None or not isinstance(propint, dict):
                 raise TypeError("interactions=True needs propint = dict(tab=..., lo=..., hi=...) (the sampled term table of build_prop_int)")
             tab, tab_lo, tab_hi = propint["tab"], propint["lo"], propint["hi"]
-        self.engine = Engine(L.make_potential(**spec), dim=dim, M=M, N=N, chains=cnt, chain_offset=off, mu=mu, L_=L, T=T, lam=lam,
+        self.engine = Engine(_L.make_potential(**spec), dim=dim, M=M, N=N, chains=cnt, chain_offset=off, mu=mu, L_=L, T=T, lam=lam,
                              interactions=interactions, g=g, r_a=r_a, Ncycle=length_measurement_cycle, compat=compat, seed=seed,
                              tab=tab, tab_lo=tab_lo or 0.0, tab_hi=tab_hi or 1.0, device=device)
         e = self.engine
@@ -285,7 +285,7 @@ class System:                       # src/system.jl:93-168
         return self.world_of(0)
 
     def lnV(self, x1, x2):
-        return _eng.lnV(np.atleast_2d(x1), np.atleast_2d(x2), self.tau, L.make_potential(**self.V))[0]
+        return _eng.lnV(np.atleast_2d(x1), np.atleast_2d(x2), self.tau, _L.make_potential(**self.V))[0]
 
     def lnK(self, x1, x2, tau):
         return _eng.lnK(np.atleast_2d(x1), np.atleast_2d(x2), self.lam, tau, self.L)[0]  # (lambda, tau) slot order of system.jl:163
@@ -295,7 +295,7 @@ def run_b(s, n, updates, Zmeasurements=()):
     """run!(s, n, updates; Zmeasurements) -- src/simulation.jl:29-42, on every chain."""
     en = [m.id for m in Zmeasurements if isinstance(m, Energy)]
     de = [m.id for m in Zmeasurements if isinstance(m, Density)]
-    sched = L.SCHED_SWEEP if s.schedule == "sweep" else L.SCHED_FAITHFUL
+    sched = _L.SCHED_SWEEP if s.schedule == "sweep" else _L.SCHED_FAITHFUL
     return s.engine.run(n, [(every, u.id) for every, u in updates], energies=en, densities=de, sched=sched)
 
 

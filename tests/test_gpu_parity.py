@@ -206,20 +206,22 @@ def _mk_updates(ob, e, s_list, spec):
     return ge, oo
 
 
-@pytest.mark.parametrize("sched", [L.SCHED_FAITHFUL, L.SCHED_SWEEP])
-@pytest.mark.parametrize("cfg", CONFIGS)
-def test_run_trajectory_bit_exact(oracle, cfg, sched):
+@pytest.mark.parametrize("sched,impl", [(L.SCHED_FAITHFUL, 0), (L.SCHED_SWEEP, 1), (L.SCHED_SWEEP, 2)],
+                         ids=["faithful", "sweep-persistent", "sweep-batched"])
+@pytest.mark.parametrize("cfg", CONFIGS + [dict(pot="harmonic", dim=2, M=40, N=70, L=6.0, T=0.5, lam=0.5, Ncycle=4)], ids=lambda c: f"{c['pot']}-N{c['N']}-M{c['M']}")
+def test_run_trajectory_bit_exact(oracle, cfg, sched, impl):
     """Same seed, same schedule: the GPU Markov chains follow the oracle's chains bit for bit, including the adaptive
     step / slice variables, acceptance windows, and the measured energies / density histograms."""
     ob = oracle
     e, os_ = make_pair(ob, cfg, chains=3, seed=21)
+    e.set_option(L.OPT_SWEEP_IMPL, impl)
     spec = [(2, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 6)]
     if cfg["N"] > 1:
         spec += [(1, L.UPD_RESHAPE_SWAP, 5), (3, L.UPD_POLYMER_COM, 0.7)]
     ge, oo = _mk_updates(ob, e, os_, spec)
     exact = cfg["pot"] in ("zero", "harmonic")
     # thermalisation leg (no measurements), then a measured leg; two calls exercise counter persistence
-    n1, n2 = (300, 400) if sched == L.SCHED_FAITHFUL else (60, 90)
+    n1, n2 = (300, 400) if sched == L.SCHED_FAITHFUL else ((60, 90) if cfg["N"] < 50 else (30, 40))
     e.run(n1, ge, sched=sched)
     for s, ups in zip(os_, oo):
         s.run(n1, ups, sched=sched)
@@ -258,7 +260,7 @@ def test_run_trajectory_bit_exact(oracle, cfg, sched):
 def test_density_compat_and_intended(oracle):
     ob = oracle
     cfg = CONFIGS[1]
-    for compat in (L.COMPAT_ALL, 0):
+    for compat in (L.COMPAT_ALL, 0):  # 0 also clears B14 (stale link) -- no interactions here so B3/B4 are moot
         e, os_ = make_pair(ob, cfg, chains=2, seed=3, compat=compat)
         did = e.density_create(16)
         e.density_measure(did)
@@ -271,6 +273,12 @@ def test_density_compat_and_intended(oracle):
         assert np.array_equal(dg, tot) and nd == 2 * cfg["M"]
         if compat == 0:
             assert dg.sum() == 2 * cfg["N"] * cfg["M"]  # intended mode counts every bead
+            spec = [(1, L.UPD_RESHAPE_SWAP, 5), (1, L.UPD_RESHAPE_LINEAR, 5)]
+            ge, oo = _mk_updates(ob, e, os_, spec)
+            e.run(300, ge)
+            for s, ups in zip(os_, oo):
+                s.run(300, ups)
+            _sync_paths(e, os_)
 
 
 def synthetic_table(n=64, hi=12.0):
