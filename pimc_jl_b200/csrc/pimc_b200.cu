@@ -386,6 +386,7 @@ struct pimc_handle {
     DevSys S;
     DevTables T;        // host mirror
     DevTables *dT;
+    DevSys *dS;         // device copy of S
     cudaStream_t stream;
     char err[512];
     unsigned long long iter;
@@ -532,7 +533,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         CKC(cudaMemcpy(t, cfg->tab, sizeof(double) * cfg->tab_n * cfg->tab_n, cudaMemcpyHostToDevice));
         S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
     }
-    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4));
+    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4)); RCC(dalloc(h, &h->dS, 1));
     {   // staging tables: alpha_k = (k-1)/k, sigma_k = sqrt(((2 lambda) alpha_k) tau), k = 2..M (same IEEE operations as levy!)
         std::vector<double> ta(S.M + 1, 0.0), ts(S.M + 1, 0.0);
         for (int k = 2; k <= S.M; ++k) { volatile double al = (double)(k - 1) / (double)k; volatile double v = 2 * S.lambda; v = v * al; v = v * S.tau; ta[k] = al; ts[k] = sqrt((double)v); }
@@ -988,28 +989,28 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
-    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (size_t)S.N + 16;
-    const size_t smem_cs = (size_t)(SWEEP_THREADS / 32) * 3 * S.M * sizeof(double) + (size_t)S.N + 16;
-    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M + 1 <= SWEEP_BCAP && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
+    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1) * sizeof(double) + 16;
+    const size_t smem_cs = (size_t)S.N + 16;
+    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 48 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
-    if (h->opt_sweep_impl == 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", SWEEP_BCAP - 1); return PIMC_ERR_UNSUPPORTED; }
+    if (h->opt_sweep_impl == 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
     if (n > 0 && !batched) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
     if (n > 0 && batched) {
         bool has_rs = false, has_com = false, has_swap = false;
         for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_HARMONIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_reshape_sweep<PIMC_POT_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_HARMONIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_com_sweep<PIMC_POT_LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_done = true;
-        }
+        const int KM = (S.M + 31) / 32;
+        typedef void (*kfn)(DevSys, const DevTables *, SweepParams);
+        kfn k_rs = pk == PIMC_POT_ZERO ? k_reshape_sweep<PIMC_POT_ZERO> : (pk == PIMC_POT_HARMONIC ? k_reshape_sweep<PIMC_POT_HARMONIC> : k_reshape_sweep<PIMC_POT_LATTICE>);
+        kfn k_cs = nullptr;
+#define PICK_COM(P_) (KM <= 1 ? k_com_sweep<P_, 1> : KM <= 2 ? k_com_sweep<P_, 2> : KM <= 4 ? k_com_sweep<P_, 4> : k_com_sweep<P_, 8>)
+        k_cs = pk == PIMC_POT_ZERO ? PICK_COM(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_COM(PIMC_POT_HARMONIC) : PICK_COM(PIMC_POT_LATTICE));
+#undef PICK_COM
+        cudaFuncSetAttribute(k_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_rs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         SweepParams SP; memset(&SP, 0, sizeof SP);
-        SP.nupd = nupd; SP.stats = h->dstats;
+        SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS;
+        CK(h, cudaMemcpyAsync(h->dS, &S, sizeof(DevSys), cudaMemcpyHostToDevice, h->stream));
         for (int i = 0; i < nupd; ++i) { SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; }
         MeasParams MP; memset(&MP, 0, sizeof MP);
         MP.nen = nen; MP.nde = nde;
@@ -1017,18 +1018,8 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if (has_com) {
-                if (pk == PIMC_POT_ZERO) k_com_sweep<PIMC_POT_ZERO><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
-                else if (pk == PIMC_POT_HARMONIC) k_com_sweep<PIMC_POT_HARMONIC><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
-                else k_com_sweep<PIMC_POT_LATTICE><<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP);
-                LAUNCHED(); launches++;
-            }
-            if (has_rs) {
-                if (pk == PIMC_POT_ZERO) k_reshape_sweep<PIMC_POT_ZERO><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
-                else if (pk == PIMC_POT_HARMONIC) k_reshape_sweep<PIMC_POT_HARMONIC><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
-                else k_reshape_sweep<PIMC_POT_LATTICE><<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP);
-                LAUNCHED(); launches++;
-            }
+            if (has_com) { k_cs<<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if (has_rs) { k_rs<<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;

@@ -17,6 +17,7 @@
 
 struct SweepParams {
     unsigned long long iter;
+    const DevSys *Sg;   // device copy of the system descriptor (for out-of-line slow paths)
     int nupd; int upd_id[PIMC_MAXU]; double w[PIMC_MAXU];
     unsigned long long *stats;
 };
@@ -45,28 +46,49 @@ __device__ __forceinline__ int d_pick_update(const SweepParams &P, const pimc_u4
     return d_sample_weighted(P.w, P.nupd, pimc_u01_co(di.w[0], di.w[1]));
 }
 
-// apply! bookkeeping of one sweep (simulation.jl:19-27), one thread
+// apply! bookkeeping of one sweep (simulation.jl:19-27), one thread.  Same final state as d_ring_push per proposal, but the
+// ring words are buffered in registers (one global read/write per 32 proposals instead of a dependent RMW per proposal).
 __device__ __forceinline__ void d_bookkeep_sweep(const UpdDev &U, int c, const unsigned char *flag, int ntask, unsigned long long beads,
                                                  unsigned long long *stats)
 {
-    RingReg R; R.head = U.ring_head[c]; R.len = U.ring_len[c]; R.sum = U.ring_sum[c]; R.tries = U.tries_var[c];
-    const long long tries0 = R.tries; long long tr = U.tries[c], ac = U.accepted[c]; int cnt = 0;
+    unsigned *ring = U.ring + (size_t)c * U.ring_words;
+    const int cap = (int)U.range + 1, range = (int)U.range;
+    int head = U.ring_head[c], len = U.ring_len[c], sum = U.ring_sum[c];
+    long long tries = U.tries_var[c];
+    const long long tries0 = tries;
+    long long tr = U.tries[c], ac = U.accepted[c];
+    int cnt = 0, tail = head + len; if (tail >= cap) tail -= cap;
+    int cw = -1, ew = -1; unsigned cword = 0, eword = 0;
     for (int slot = 0; slot < ntask; ++slot) {
-        int f = flag[slot];
+        const int f = flag[slot];
         if (f == 2) continue;
         cnt += 1; tr += 1;
         if (f == 3) continue;
-        ac += f; d_ring_push(U, c, R, f);
+        ac += f; tries += 1;
+        const int w = tail >> 5;
+        if (w != cw) { if (cw >= 0) ring[cw] = cword; cw = w; cword = ring[w]; }
+        const unsigned bit = 1u << (tail & 31);
+        cword = f ? (cword | bit) : (cword & ~bit);
+        tail = tail + 1 == cap ? 0 : tail + 1;
+        len += 1; sum += f;
+        if (len > range) {
+            const int hw = head >> 5; unsigned eb;
+            if (hw == cw) eb = (cword >> (head & 31)) & 1u;
+            else { if (hw != ew) { ew = hw; eword = ring[hw]; } eb = (eword >> (head & 31)) & 1u; }
+            sum -= (int)eb; head = head + 1 == cap ? 0 : head + 1; len -= 1;
+        }
     }
-    bool adj = cnt > 0 && (R.tries / U.adj) != (tries0 / U.adj);
-    U.ring_head[c] = R.head; U.ring_len[c] = R.len; U.ring_sum[c] = R.sum; U.tries_var[c] = R.tries;
+    if (cw >= 0) ring[cw] = cword;
+    RingReg R; R.head = head; R.len = len; R.sum = sum; R.tries = tries;
+    bool adj = cnt > 0 && (tries / U.adj) != (tries0 / U.adj);
+    U.ring_head[c] = head; U.ring_len[c] = len; U.ring_sum[c] = sum; U.tries_var[c] = tries;
     U.tries[c] = tr; U.accepted[c] = ac; U.bead_moves[c] += (long long)beads;
     if (adj) d_adjust(U, c, R);
     if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
 }
 
 template <int POT>
-__global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
 {
     extern __shared__ double sm[];
     double *xs = sm, *ys = sm + SWEEP_BCAP, *pv = sm + 2 * SWEEP_BCAP;               // pv only touched when POT != 0
@@ -75,6 +97,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, co
     int *t_off = t_m + SWEEP_TBMAX;            // [TBMAX] first staged row
     unsigned char *map = (unsigned char *)(t_off + SWEEP_TBMAX);   // [BCAP] row -> task
     unsigned char *flag = map + SWEEP_BCAP;    // [N] outcome per slot
+    double *s_alpha = (double *)(flag + ((S.N + 15) & ~15));  // [M+1] staging table alpha_k
     __shared__ int s_scan[SWEEP_THREADS / 32];
     __shared__ unsigned long long s_bead;
 
@@ -90,6 +113,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, co
     const int nx_stride = N; (void)nx_stride;
     const int *nextc = S.next + (size_t)c * N;
     if (tid == 0) s_bead = 0;
+    for (int i = tid; i <= M; i += SWEEP_THREADS) s_alpha[i] = S.tab_alpha[i];
     unsigned long long my_beads = 0;
 
     for (int t0 = 0; t0 < N;) {
@@ -150,10 +174,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, co
             const int base = t_off[q], mq = t_m[q];
             double prev = arr[base];
             const double e = arr[base + mq];
+            const double *al = s_alpha + mq + 1;  // alpha of row `row` is al[-row]
+            double *ar = arr + base;
+#pragma unroll 4
             for (int row = 1; row < mq; ++row) {
-                const double a = S.tab_alpha[mq + 1 - row];
-                prev = a * prev + (1 - a) * e + arr[base + row];
-                arr[base + row] = prev;
+                const double a = al[-row];
+                prev = a * prev + (1 - a) * e + ar[row];
+                ar[row] = prev;
             }
         }
         __syncthreads();
@@ -178,9 +205,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, co
             wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
             int acc = 0;
             if (lane == 0) {
-                const double delta = pimc_exp(wu - wi);
-                if (delta >= 1.0) acc = 1;
-                else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                const double dw = wu - wi;     // exp(dw) >= 1 for dw >= 0: accepted without the exponential or the uniform
+                if (dw >= 0.0) acc = 1;
+                else {
+                    const double delta = pimc_exp(dw);
+                    if (delta >= 1.0) acc = 1;
+                    else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                }
                 flag[n] = (unsigned char)acc;
             }
             acc = __shfl_sync(0xffffffffu, acc, 0);
@@ -202,14 +233,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_reshape_sweep(DevSys S, co
     if (tid == 0) d_bookkeep_sweep(U, c, flag, N, s_bead, P.stats);
 }
 
-template <int POT>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_com_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+// generic centre-of-mass proposal for a permutation cycle of several worldlines (rare in a sweep): kept out of line so that it
+// does not cost the fast path registers
+__device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, double maxd, pimc_stream st, int *npol)
+{
+    const DevSys &S = *Sg;
+    pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1);
+    DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)n;
+    return d_com_warp(S, c, n, maxd, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, npol);
+}
+
+// KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
+template <int POT, int KM>
+__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 4 : 3)) k_com_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
 {
     extern __shared__ double sm[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = SWEEP_THREADS / 32;
     const int M = S.M, N = S.N, dim = S.dim;
-    double *sx = sm + (size_t)warp * 3 * M, *sy = sx + M, *sv = sy + M;
-    unsigned char *flag = (unsigned char *)(sm + (size_t)NW * 3 * M);
+    unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
     pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
@@ -223,54 +264,85 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_com_sweep(DevSys S, const 
     for (int i = tid; i < N; i += SWEEP_THREADS) flag[i] = 2;
     __syncthreads();
     unsigned long long my_beads = 0;
-    for (int n = warp; n < N; n += NW) {
-        const int nx = nextc[n];
-        bool single = nx == n, run_it = single;
-        if (polymer && !single) { run_it = true; int p = nx, cnt = 0; while (p != n && cnt <= N) { if (p < n) run_it = false; p = nextc[p]; cnt++; } }
-        if (!run_it) continue;
-        if (!single) { // a permutation cycle of several worldlines: generic path
-            pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1);
-            DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)n;
-            int npol = 1;
-            int r = d_com_warp(S, c, n, maxd, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
-            if (lane == 0) { flag[n] = r == 1 ? 1 : 0; my_beads += (unsigned long long)M * npol; }
-            continue;
+    // groups of 32 proposals per warp: lane l draws the displacement of the l-th proposal of the group (one Philox per lane
+    // instead of one per warp and proposal); the proposals themselves run one after the other, lanes striding the slices
+    for (int g0 = warp; g0 < N; g0 += NW * 32) {
+        const int nl = g0 + lane * NW;
+        double dxl = 0.0, dyl = 0.0;
+        if (nl < N) {
+            pimc_u4 w = pimc_draw(st, (uint32_t)nl, PIMC_K_COM, 0, 0);
+            dxl = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5);
+            dyl = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
         }
-        pimc_u4 w = pimc_draw(st, (uint32_t)n, PIMC_K_COM, 0, 0);
-        const double dx = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5);
-        const double dy = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
-        double *rx = S.r + RIDX(S, c, n, 0, 0), *ry = rx + M, *vl = S.Vl + VIDX(S, c, n, 0);
-        double wi = 0.0, wu = 0.0;
-        for (int j = lane; j < M; j += 32) {
-            wi += vl[j];
-            double x = d_teleport_fast(rx[j] + dx, L, twoL, inv2L), y = 0.0;
-            if (dim > 1) y = d_teleport_fast(ry[j] + dy, L, twoL, inv2L);
-            sx[j] = x; sy[j] = y;
-            if (POT != PIMC_POT_ZERO) sv[j] = d_pot_t<POT>(S.pot, x, y, dim);
-        }
-        __syncwarp();
-        if (POT != PIMC_POT_ZERO)
-            for (int j = lane; j < M; j += 32) wu += mht * (sv[j] + sv[j == M - 1 ? 0 : j + 1]);
-        else
-            for (int j = lane; j < M; j += 32) wu += mht * (0.0 + 0.0);
-        wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
-        int acc = 0;
-        if (lane == 0) {
-            const double delta = pimc_exp(wu - wi);
-            if (delta >= 1.0) acc = 1;
-            else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
-            flag[n] = (unsigned char)acc;
-            my_beads += (unsigned long long)M;
-        }
-        acc = __shfl_sync(0xffffffffu, acc, 0);
-        if (acc) {
-            for (int j = lane; j < M; j += 32) {
-                rx[j] = sx[j];
-                if (dim > 1) ry[j] = sy[j];
-                vl[j] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (sv[j] + sv[j == M - 1 ? 0 : j + 1]);
+        for (int t = 0; t < 32; ++t) {
+            const int n = g0 + t * NW;
+            if (n >= N) break;
+            const double dx = __shfl_sync(0xffffffffu, dxl, t), dy = __shfl_sync(0xffffffffu, dyl, t);
+            const int nx = nextc[n];
+            const bool single = nx == n;
+            bool run_it = single;
+            if (polymer && !single) { run_it = true; int p = nx, cnt = 0; while (p != n && cnt <= N) { if (p < n) run_it = false; p = nextc[p]; cnt++; } }
+            if (!run_it) continue;
+            if (!single) {
+                int npol = 1;
+                int r = d_com_cycle_generic(P.Sg, c, n, maxd, st, &npol);
+                if (lane == 0) { flag[n] = r == 1 ? 1 : 0; my_beads += (unsigned long long)M * npol; }
+                continue;
+            }
+            double *rx = S.r + RIDX(S, c, n, 0, 0), *ry = rx + M, *vl = S.Vl + VIDX(S, c, n, 0);
+            double x[KM], y[KM], v[KM], wi = 0.0, wu = 0.0;
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+                const int j = lane + 32 * k;
+                x[k] = j < M ? rx[j] : 0.0;
+                y[k] = (dim > 1 && j < M) ? ry[j] : 0.0;
+                v[k] = j < M ? vl[j] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+                wi += (lane + 32 * k < M) ? v[k] : 0.0;
+                x[k] = d_teleport_fast(x[k] + dx, L, twoL, inv2L);
+                if (dim > 1) y[k] = d_teleport_fast(y[k] + dy, L, twoL, inv2L);
+                v[k] = (POT == PIMC_POT_ZERO) ? 0.0 : d_pot_t<POT>(S.pot, x[k], y[k], dim);
+            }
+            // link j -> j+1: the next bead's potential sits one lane up (lane 31: lane 0 of the next register); last bead -> bead 0
+            const double v00 = __shfl_sync(0xffffffffu, v[0], 0);
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+                const int j = lane + 32 * k;
+                double up = 0.0;
+                if (POT != PIMC_POT_ZERO) {
+                    up = __shfl_down_sync(0xffffffffu, v[k], 1);
+                    const double nextreg = __shfl_sync(0xffffffffu, (k + 1 < KM) ? v[(k + 1 < KM) ? k + 1 : k] : 0.0, 0);
+                    if (lane == 31) up = nextreg;
+                    if (j == M - 1) up = v00;
+                }
+                const double lk = mht * (v[k] + up);
+                v[k] = lk;                      // v now holds the new link action
+                if (j < M) wu += lk;
+            }
+            wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
+            int acc = 0;
+            if (lane == 0) {
+                const double dw = wu - wi;
+                if (dw >= 0.0) acc = 1;
+                else {
+                    const double delta = pimc_exp(dw);
+                    if (delta >= 1.0) acc = 1;
+                    else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                }
+                flag[n] = (unsigned char)acc;
+                my_beads += (unsigned long long)M;
+            }
+            acc = __shfl_sync(0xffffffffu, acc, 0);
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < M) { rx[j] = x[k]; if (dim > 1) ry[j] = y[k]; vl[j] = v[k]; }
+                }
             }
         }
-        __syncwarp();
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
