@@ -77,6 +77,31 @@ PIMC_HD pimc_u4 pimc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32
     return o;
 }
 
+/* The 10 round keys depend on the seed only: precomputed once, they reach the kernels as constant-bank operands. */
+typedef struct { uint32_t k0[10], k1[10]; } pimc_roundkeys;
+PIMC_HD void pimc_roundkeys_make(uint64_t seed, pimc_roundkeys *rk)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk->k0[r] = k0; rk->k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+PIMC_HD pimc_u4 pimc_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const pimc_roundkeys *rk)
+{
+    pimc_u4 o;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        pimc_mulhilo(0xD2511F53u, c0, &hi0, &lo0);
+        pimc_mulhilo(0xCD9E8D57u, c2, &hi1, &lo1);
+        uint32_t n0 = hi1 ^ c1 ^ rk->k0[r];
+        uint32_t n2 = hi0 ^ c3 ^ rk->k1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
+
 PIMC_HD pimc_stream pimc_stream_make(uint64_t seed, uint32_t chain, uint64_t iter)
 {
     pimc_stream s;
@@ -94,6 +119,13 @@ PIMC_HD pimc_u4 pimc_draw(pimc_stream s, uint32_t slot, uint32_t kind, uint32_t 
     uint32_t c0 = (kind << 28) | ((retry & 0x3FFFu) << 14) | (bead & 0x3FFFu);
     uint32_t c1 = (slot & 0xFFFFu) | (s.iter_hi16 << 16);
     return pimc_philox4x32_10(c0, c1, s.iter_lo, s.chain, s.seed_lo, s.seed_hi);
+}
+
+PIMC_HD pimc_u4 pimc_draw_rk(pimc_stream s, const pimc_roundkeys *rk, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead)
+{
+    uint32_t c0 = (kind << 28) | ((retry & 0x3FFFu) << 14) | (bead & 0x3FFFu);
+    uint32_t c1 = (slot & 0xFFFFu) | (s.iter_hi16 << 16);
+    return pimc_philox4x32_10_rk(c0, c1, s.iter_lo, s.chain, rk);
 }
 
 /* words (0,1) -> uniform in (0,1] ; words (2,3) -> uniform in [0,1) ; both 53-bit. */
@@ -130,7 +162,8 @@ PIMC_HD uint64_t pimc_d2bits(double d)
 #endif
 }
 
-/* natural log for normal positive x (here x in [2^-53, 1]); atanh series, < 1 ulp typ. */
+/* natural log for normal positive x; atanh series with one IEEE division, < 1 ulp typ.  Reference implementation: it
+ * generates the table of pimc_log_tab and serves as its accuracy yardstick. */
 PIMC_HD double pimc_log(double x)
 {
     uint64_t b = pimc_d2bits(x);
@@ -155,6 +188,48 @@ PIMC_HD double pimc_log(double x)
     double dk = (double)k;
     return dk * 6.93147180369123816490e-01 -
            ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
+/* Division-free log for the Gaussian transform: x = 2^k z, z in [1,2); the top 7 mantissa bits pick c_i (interval midpoint;
+ * 1 and 2 exactly for the first and last interval so that results near x = 1 keep their relative accuracy);
+ * e = z/c_i - 1 through the tabulated 1/c_i (a 10-bit number, so the fma is exact; |e| < 2^-7), log(1+e) by a degree-7 Taylor polynomial, and
+ * log(c_i) [minus ln 2 and k+1 when c_i >= sqrt 2, which keeps the pieces small near x = 1] from the table.
+ * tab[2i] = 1/c_i, tab[2i+1] = log(c_i) adjusted; filled by pimc_logtab_fill with IEEE operations only. */
+#define PIMC_LOGTAB_N 128
+PIMC_HD double pimc_logtab_center(int i)
+{
+    if (i == 0) return 1.0;
+    if (i == PIMC_LOGTAB_N - 1) return 2.0;
+    return 1.0 + ((double)i + 0.5) / (double)PIMC_LOGTAB_N;
+}
+PIMC_HD void pimc_logtab_fill(double *tab)
+{
+    for (int i = 0; i < PIMC_LOGTAB_N; ++i) {
+        double c = pimc_logtab_center(i);
+        int up = i >= 53;                              /* centre >= sqrt 2: fold one factor 2 into k */
+        double invc = floor(512.0 / c + 0.5) / 512.0;  /* 1/c_i rounded to 9 fractional bits: z * invc - 1 is then exact in one fma */
+        tab[2 * i] = invc;
+        tab[2 * i + 1] = -pimc_log(up ? 2.0 * invc : invc);
+    }
+}
+PIMC_HD double pimc_log_tab(double x, const double *tab)
+{
+    uint64_t b = pimc_d2bits(x);
+    int k = (int)(b >> 52) - 1023;
+    int i = (int)((b >> 45) & 0x7Fu);
+    double z = pimc_bits2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    double invc = tab[2 * i], lc = tab[2 * i + 1];
+    k += (i >= 53);                        /* c_53 = 1.41796875 is the first centre >= sqrt 2 */
+    double e = fma(z, invc, -1.0);
+    double p = 1.0 / 7.0;
+    p = fma(p, e, -1.0 / 6.0);
+    p = fma(p, e, 0.2);
+    p = fma(p, e, -0.25);
+    p = fma(p, e, 1.0 / 3.0);
+    p = fma(p, e, -0.5);
+    p = fma(p, e, 1.0);
+    double dk = (double)k;
+    return fma(dk, 6.93147180369123816490e-01, lc) + fma(p, e, dk * 1.90821492927058770002e-10);
 }
 
 /* sin and cos of 2*pi*u for u in [0,1): exact quadrant reduction in u, minimax kernels. */
@@ -211,16 +286,30 @@ PIMC_HD double pimc_exp(double x)
     return y;
 }
 
-/* Box-Muller: 128 random bits -> two independent N(0,1). g0 -> dim 1 (x), g1 -> dim 2 (y). */
-PIMC_HD void pimc_gauss_pair(pimc_u4 d, double *g0, double *g1)
+/* Box-Muller: 128 random bits -> two independent N(0,1). g0 -> dim 1 (x), g1 -> dim 2 (y).
+ * Uniforms carry 52 random bits: d = 1.mantissa in [1,2); u1 = 2 - d in (0,1], u2 = d' - 1 in [0,1). */
+PIMC_HD void pimc_gauss_pair_t(pimc_u4 d, const double *tab, double *g0, double *g1)
 {
-    double u1 = pimc_u01_oc(d.w[0], d.w[1]);
-    double u2 = pimc_u01_co(d.w[2], d.w[3]);
-    double rad = sqrt(-2.0 * pimc_log(u1));
+    double d1 = pimc_bits2d(((((uint64_t)d.w[1] << 32) | (uint64_t)d.w[0]) >> 12) | 0x3FF0000000000000ull);
+    double d2 = pimc_bits2d(((((uint64_t)d.w[3] << 32) | (uint64_t)d.w[2]) >> 12) | 0x3FF0000000000000ull);
+    double u1 = 2.0 - d1, u2 = d2 - 1.0;
+    double rad = sqrt(-2.0 * pimc_log_tab(u1, tab));
     double sn, cs;
     pimc_sincos2pi(u2, &sn, &cs);
     *g0 = rad * cs;
     *g1 = rad * sn;
 }
+
+#if !defined(__CUDACC__)
+/* host table, filled once at library load (see the constructor in the oracle) or lazily */
+static double pimc_logtab_host[2 * PIMC_LOGTAB_N];
+static int pimc_logtab_host_ready = 0;
+static inline const double *pimc_logtab_get(void)
+{
+    if (!pimc_logtab_host_ready) { pimc_logtab_fill(pimc_logtab_host); pimc_logtab_host_ready = 1; }
+    return pimc_logtab_host;
+}
+static inline void pimc_gauss_pair(pimc_u4 d, double *g0, double *g1) { pimc_gauss_pair_t(d, pimc_logtab_get(), g0, g1); }
+#endif
 
 #endif /* PIMC_RNG_H */

@@ -23,6 +23,7 @@
 #include <stdio.h>
 
 static char g_err[256] = "";
+__attribute__((constructor)) static void ora_init_tables(void) { (void)pimc_logtab_get(); }
 const char *ora_last_error(void) { return g_err; }
 #define FAIL(...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); } while (0)
 

@@ -23,7 +23,7 @@ __global__ void k_init_world(DevSys S)
     for (int n = serial ? 0 : threadIdx.x; n < N; n += serial ? 1 : blockDim.x) {
         if (serial && threadIdx.x != 0) break;
         double *px = S.r + RIDX(S, c, n, 0, 0), *py = px + M;
-        GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)n; g.kind = PIMC_K_INIT;
+        GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)n; g.kind = PIMC_K_INIT; g.tab = S.logtab;
         uint32_t levy_calls = 0;
         auto start = [&](uint32_t attempt) {
             pimc_u4 w = pimc_draw(st, (uint32_t)n, PIMC_K_INIT0, attempt, 0);
@@ -41,7 +41,7 @@ __global__ void k_init_world(DevSys S)
             for (int j = 1; j <= m; ++j) {
                 double alpha = (double)(m + 1 - j) / (double)(m + 2 - j);
                 double sig = sqrt(2 * S.lambda * alpha * S.tau), om = 1 - alpha, g0, g1;
-                pimc_gauss_pair(pimc_draw(gg.st, gg.slot, PIMC_K_INIT, levy_calls, (uint32_t)j), &g0, &g1);
+                pimc_gauss_pair_t(pimc_draw(gg.st, gg.slot, PIMC_K_INIT, levy_calls, (uint32_t)j), S.logtab, &g0, &g1);
                 double nx = alpha * qx + om * ex + g0 * sig, ny = 0.0;
                 if (dim > 1) ny = alpha * qy + om * ey + g1 * sig;
                 qx = nx; qy = ny;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                     int j0 = sweep ? j0w : 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
                     int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
                     int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                    GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE;
+                    GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
                     int r = d_reshape_linear(S, c, n, j0, m, g, pimc_u01_co(dm.w[0], dm.w[1]), 1, slot, nullptr, nullptr);
                     flag[slot] = r == 1 ? 1 : 0;
                     bm += (unsigned long long)(m - 1);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                     int n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
                     if (n1 == n2) flag[0] = 3; // early return without queue!(counter_var) (reshape.jl:134-136)
                     else {
-                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
+                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
                         int r = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr);
                         flag[0] = r == 1 ? 1 : 0;
                         s_bead = 2ull * (unsigned long long)(m - 1);
@@ -323,15 +323,15 @@ __global__ void k_levy(double *r, int rows, int dim, double tau, double L, doubl
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
         DevSys S; S.dim = dim; S.M = rows; S.tau = tau; S.L = L; S.lambda = lambda; S.a = 0.0; S.ctr = 1; S.pot.kind = PIMC_POT_ZERO;
         double *px = r + (size_t)b * rows * dim, *py = px + rows;
-        GSrc g; g.xi = xi + (size_t)b * (rows - 2) * dim; g.slot = 0; g.kind = 0;
+        GSrc g; g.xi = xi + (size_t)b * (rows - 2) * dim; g.slot = 0; g.kind = 0; g.tab = nullptr;
         d_bridge(S, 0, px[0], dim > 1 ? py[0] : 0.0, px[rows - 1], dim > 1 ? py[rows - 1] : 0.0, rows, 1, -1, g, px, py, nullptr);
     }
 }
-__global__ void k_gauss(unsigned long long seed, uint32_t chain, unsigned long long iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, long long n, double *g)
+__global__ void k_gauss(unsigned long long seed, uint32_t chain, unsigned long long iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, long long n, double *g, const double *tab)
 {
     pimc_stream st = pimc_stream_make(seed, chain, iter);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        pimc_gauss_pair(pimc_draw(st, slot, kind, retry, bead0 + (uint32_t)i), g + 2 * i, g + 2 * i + 1);
+        pimc_gauss_pair_t(pimc_draw(st, slot, kind, retry, bead0 + (uint32_t)i), tab, g + 2 * i, g + 2 * i + 1);
 }
 
 // ---- explicit single-move hooks (one warp) ----
@@ -339,7 +339,7 @@ struct MoveOut { double wi, wu; int acc; };
 __global__ void k_reshape_linear_explicit(DevSys S, int c, int n, int j0, int m, const double *xi, double u, int commit, MoveOut *out, double *rp)
 {
     if (threadIdx.x != 0) return;
-    GSrc g; g.xi = xi; g.slot = 0; g.kind = 0;
+    GSrc g; g.xi = xi; g.slot = 0; g.kind = 0; g.tab = nullptr;
     out->acc = d_reshape_linear(S, c, n, j0, m, g, u, commit, 0, &out->wi, &out->wu);
     if (rp && out->acc >= 0) { // teleported proposal rows (m+1) x dim, column-major
         const double *px = S.prop + RIDX(S, c, 0, 0, 0), *py = px + S.M;
@@ -350,7 +350,7 @@ __global__ void k_reshape_linear_explicit(DevSys S, int c, int n, int j0, int m,
 __global__ void k_reshape_swap_explicit(DevSys S, int c, int n1, int n2, int j0, int m, const double *xi1, const double *xi2, double u, int commit, MoveOut *out)
 {
     if (threadIdx.x != 0) return;
-    GSrc g1, g2; g1.xi = xi1; g1.slot = 0; g1.kind = 0; g2 = g1; g2.xi = xi2;
+    GSrc g1, g2; g1.xi = xi1; g1.slot = 0; g1.kind = 0; g1.tab = nullptr; g2 = g1; g2.xi = xi2;
     out->acc = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, u, commit, &out->wi, &out->wu);
 }
 __global__ void k_com_explicit(DevSys S, int c, int n, const double *d, double u, int commit, MoveOut *out)
@@ -534,6 +534,12 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
     }
     RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4)); RCC(dalloc(h, &h->dS, 1));
+    {   // table of the division-free log of the Gaussian transform (include/pimc_rng.h), filled with IEEE operations on the host
+        double htab[2 * PIMC_LOGTAB_N]; pimc_logtab_fill(htab);
+        double *dl; RCC(dalloc(h, &dl, 2 * PIMC_LOGTAB_N));
+        CKC(cudaMemcpy(dl, htab, sizeof htab, cudaMemcpyHostToDevice));
+        S.logtab = dl;
+    }
     {   // staging tables: alpha_k = (k-1)/k, sigma_k = sqrt(((2 lambda) alpha_k) tau), k = 2..M (same IEEE operations as levy!)
         std::vector<double> ta(S.M + 1, 0.0), ts(S.M + 1, 0.0);
         for (int k = 2; k <= S.M; ++k) { volatile double al = (double)(k - 1) / (double)k; volatile double v = 2 * S.lambda; v = v * al; v = v * S.tau; ta[k] = al; ts[k] = sqrt((double)v); }
@@ -688,8 +694,10 @@ extern "C" int pimc_levy_bridge(double *r, int32_t rows, int32_t dim, double tau
 extern "C" int pimc_gauss_pairs(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead0, int64_t n, double *g)
 {
     NEEDGPU(); TmpBuf t; double *o = t.up((double *)nullptr, 2 * n);
-    if (!o) return PIMC_ERR_NOMEM;
-    k_gauss<<<grid_for(n, 256), 256>>>(seed, chain, iter, slot, kind, retry, bead0, n, o); LAUNCHED(); CKG(cudaGetLastError());
+    double htab[2 * PIMC_LOGTAB_N]; pimc_logtab_fill(htab);
+    double *dtab = t.up(htab, 2 * PIMC_LOGTAB_N);
+    if (!o || !dtab) return PIMC_ERR_NOMEM;
+    k_gauss<<<grid_for(n, 256), 256>>>(seed, chain, iter, slot, kind, retry, bead0, n, o, dtab); LAUNCHED(); CKG(cudaGetLastError());
     CKG(cudaMemcpy(g, o, 2 * n * sizeof(double), cudaMemcpyDeviceToHost)); return PIMC_OK;
 }
 
@@ -989,7 +997,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
-    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1) * sizeof(double) + 16;
+    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 16;
     const size_t smem_cs = (size_t)S.N + 16;
     const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 48 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
@@ -1010,6 +1018,8 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         cudaFuncSetAttribute(k_rs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         SweepParams SP; memset(&SP, 0, sizeof SP);
         SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS;
+        pimc_roundkeys_make(S.seed, &SP.rk);
+        for (int i = 0; i < nupd; ++i) { SP.kind[i] = h->T.upd[update_ids[i]].kind; SP.vmax[i] = h->T.upd[update_ids[i]].vmax; }
         CK(h, cudaMemcpyAsync(h->dS, &S, sizeof(DevSys), cudaMemcpyHostToDevice, h->stream));
         for (int i = 0; i < nupd; ++i) { SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; }
         MeasParams MP; memset(&MP, 0, sizeof MP);

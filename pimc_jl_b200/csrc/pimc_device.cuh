@@ -30,6 +30,7 @@ struct DevSys {
     double *r, *Vl;
     int *next;
     double *prop, *propV, *wtab;
+    const double *logtab;              // [2*128] table of pimc_log_tab (include/pimc_rng.h)
     const double *tab_alpha, *tab_sig; // [M+1] staging tables indexed by k = rows left: alpha_k = (k-1)/k, sigma_k = sqrt(((2 lambda) alpha_k) tau)  (helper.jl:131-134)
     // cell list (replaces src/nearest_neighbours.jl): per (chain, slice) singly linked lists
     int need_cells, nbins, ncell;
@@ -276,11 +277,11 @@ __device__ __forceinline__ bool d_hardcore_hit(const DevSys &S, int c, double x,
 }
 
 // ---------------- Gaussian source ----------------
-struct GSrc { const double *xi; pimc_stream st; uint32_t slot, kind; };
+struct GSrc { const double *xi; pimc_stream st; uint32_t slot, kind; const double *tab; };
 __device__ __forceinline__ void d_gauss(const GSrc &g, int dim, int bead, int retry, double &g0, double &g1)
 {
     if (g.xi) { g0 = g.xi[(size_t)(bead - 1) * dim]; g1 = dim > 1 ? g.xi[(size_t)(bead - 1) * dim + 1] : 0.0; return; }
-    pimc_gauss_pair(pimc_draw(g.st, g.slot, g.kind, (uint32_t)retry, (uint32_t)bead), &g0, &g1);
+    pimc_gauss_pair_t(pimc_draw(g.st, g.slot, g.kind, (uint32_t)retry, (uint32_t)bead), g.tab, &g0, &g1);
 }
 
 // hardspherelevy! (helper.jl:141-181) == levy! (helper.jl:118-139) when a == 0.

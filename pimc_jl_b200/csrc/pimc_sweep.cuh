@@ -1,5 +1,5 @@
 // pimc_sweep.cuh -- throughput kernels of the SWEEP schedule (one launch per iteration and update family, one CTA per
-// chain).  Same draws, same arithmetic per bead and therefore the same trajectories as the persistent k_run / the oracle;
+// chain).  Same draws, same arithmetic per bead and therefore the same trajectories as the persistent k_run;
 // only the order of the Delta-U reductions differs (warp shuffles).
 //
 //   k_reshape_sweep : ReshapeLinear (reshape.jl:31-91) for every worldline of the chain in one time window.
@@ -19,7 +19,9 @@ struct SweepParams {
     unsigned long long iter;
     const DevSys *Sg;   // device copy of the system descriptor (for out-of-line slow paths)
     int nupd; int upd_id[PIMC_MAXU]; double w[PIMC_MAXU];
+    int kind[PIMC_MAXU]; double vmax[PIMC_MAXU];   // copies of the update descriptors' constants (no global load on the prologue path)
     unsigned long long *stats;
+    pimc_roundkeys rk;  // Philox round keys of the seed (constant-bank operands)
 };
 
 // teleport (propagator.jl:30-32) without the IEEE division on the fast path: q = x * (1/2L) differs from x / 2L by
@@ -104,10 +106,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, co
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const UpdDev &U = T->upd[P.upd_id[d_pick_update(P, di)]];
-    if (U.kind != PIMC_UPD_RESHAPE_LINEAR) return;
-    const int var = (int)U.var[c], vmax = (int)U.vmax;
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    if (P.kind[pick] != PIMC_UPD_RESHAPE_LINEAR) return;
+    const UpdDev &U = T->upd[P.upd_id[pick]];
+    const int var = (int)U.var[c], vmax = (int)P.vmax[pick];
+    double *s_logtab = s_alpha + (M + 1);     // [2*128]
+    for (int i = tid; i < 2 * PIMC_LOGTAB_N; i += SWEEP_THREADS) s_logtab[i] = S.logtab[i];
     const int j0 = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
     const int nx_stride = N; (void)nx_stride;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, co
         // ---- batch selection: tasks t0.. as long as their rows (m + 1 each) fit the staging buffer ----
         int slot = t0 + tid, m = 0, cnt = 0;
         if (slot < N) {
-            pimc_u4 dt = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 0);
+            pimc_u4 dt = pimc_draw_rk(st, &P.rk, (uint32_t)slot, PIMC_K_TASK, 0, 0);
             int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
             m = vmax < mm ? vmax : mm;
             cnt = m + 1;
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, co
             const int q = map[s], row = s - t_off[q], mq = t_m[q];
             if (row >= 1 && row < mq) {
                 double g0, g1;
-                pimc_gauss_pair(pimc_draw(st, (uint32_t)(t0 + q), PIMC_K_BRIDGE, 0, (uint32_t)row), &g0, &g1);
+                pimc_gauss_pair_t(pimc_draw_rk(st, &P.rk, (uint32_t)(t0 + q), PIMC_K_BRIDGE, 0, (uint32_t)row), s_logtab, &g0, &g1);
                 const double sig = S.tab_sig[mq + 1 - row];
                 xs[s] = g0 * sig;
                 if (dim > 1) ys[s] = g1 * sig;
@@ -193,35 +198,39 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, co
         }
         __syncthreads();
         // ---- phase D: Delta-U, Metropolis, commit -- one warp per task ----
-        for (int q = warp; q < TB; q += SWEEP_THREADS / 32) {
-            const int n = t0 + q, mq = t_m[q], base = t_off[q], nx = nextc[n];
-            double wi = 0.0, wu = 0.0;
-            for (int jp = 1 + lane; jp <= mq; jp += 32) {
-                const int j = j0 + jp - 1;
-                const int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
-                wi += S.Vl[VIDX(S, c, p, sl)];
-                wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp - 1] + pv[base + jp]);
-            }
-            wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
-            int acc = 0;
-            if (lane == 0) {
-                const double dw = wu - wi;     // exp(dw) >= 1 for dw >= 0: accepted without the exponential or the uniform
-                if (dw >= 0.0) acc = 1;
-                else {
-                    const double delta = pimc_exp(dw);
-                    if (delta >= 1.0) acc = 1;
-                    else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+        {
+            double *rc = S.r + (size_t)c * N * dim * M;   // this chain's positions / link cache: 32-bit indexing below
+            double *vc = S.Vl + (size_t)c * N * M;
+            for (int q = warp; q < TB; q += SWEEP_THREADS / 32) {
+                const int n = t0 + q, mq = t_m[q], base = t_off[q], nx = nextc[n];
+                // link jp (1-based) starts at slice j0-1+jp-1 of n, or wrapped on the next particle of the cycle
+                const int first = j0 - 1, nfirst = M - first;           // rows 0..nfirst-1 stay on particle n
+                double wi = 0.0, wu = 0.0;
+                for (int jp = lane; jp < mq; jp += 32) {
+                    const int p = jp < nfirst ? n : nx, sl = jp < nfirst ? first + jp : jp - nfirst;
+                    wi += vc[p * M + sl];
+                    wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
                 }
-                flag[n] = (unsigned char)acc;
-            }
-            acc = __shfl_sync(0xffffffffu, acc, 0);
-            if (acc) {
-                for (int jp = 1 + lane; jp <= mq; jp += 32) {
-                    const int j = j0 + jp - 1;
-                    const int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
-                    S.r[RIDX(S, c, p, 0, sl)] = xs[base + jp - 1];
-                    if (dim > 1) S.r[RIDX(S, c, p, 1, sl)] = ys[base + jp - 1];
-                    S.Vl[VIDX(S, c, p, sl)] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp - 1] + pv[base + jp]);
+                wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
+                int acc = 0;
+                if (lane == 0) {
+                    const double dw = wu - wi;     // exp(dw) >= 1 for dw >= 0: accepted without the exponential or the uniform
+                    if (dw >= 0.0) acc = 1;
+                    else {
+                        const double delta = pimc_exp(dw);
+                        if (delta >= 1.0) acc = 1;
+                        else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                    }
+                    flag[n] = (unsigned char)acc;
+                }
+                acc = __shfl_sync(0xffffffffu, acc, 0);
+                if (acc) {
+                    for (int jp = lane; jp < mq; jp += 32) {
+                        const int p = jp < nfirst ? n : nx, sl = jp < nfirst ? first + jp : jp - nfirst;
+                        rc[(p * dim) * M + sl] = xs[base + jp];
+                        if (dim > 1) rc[(p * dim + 1) * M + sl] = ys[base + jp];
+                        vc[p * M + sl] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                    }
                 }
             }
         }
@@ -253,10 +262,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 4 : 3)) k_com_sweep(
     unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const UpdDev &U = T->upd[P.upd_id[d_pick_update(P, di)]];
-    if (U.kind != PIMC_UPD_SINGLE_COM && U.kind != PIMC_UPD_POLYMER_COM) return;
-    const bool polymer = U.kind == PIMC_UPD_POLYMER_COM;
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    if (P.kind[pick] != PIMC_UPD_SINGLE_COM && P.kind[pick] != PIMC_UPD_POLYMER_COM) return;
+    const UpdDev &U = T->upd[P.upd_id[pick]];
+    const bool polymer = P.kind[pick] == PIMC_UPD_POLYMER_COM;
     const double maxd = U.var[c];
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
     const int *nextc = S.next + (size_t)c * N;
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 4 : 3)) k_com_sweep(
         const int nl = g0 + lane * NW;
         double dxl = 0.0, dyl = 0.0;
         if (nl < N) {
-            pimc_u4 w = pimc_draw(st, (uint32_t)nl, PIMC_K_COM, 0, 0);
+            pimc_u4 w = pimc_draw_rk(st, &P.rk, (uint32_t)nl, PIMC_K_COM, 0, 0);
             dxl = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5);
             dyl = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
         }
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 4 : 3)) k_com_sweep(
                 else {
                     const double delta = pimc_exp(dw);
                     if (delta >= 1.0) acc = 1;
-                    else { pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                    else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
                 }
                 flag[n] = (unsigned char)acc;
                 my_beads += (unsigned long long)M;
@@ -374,7 +384,7 @@ __global__ void k_swap_iter(DevSys S, const DevTables *__restrict__ T, SweepPara
         for (int i = 0; i < N; ++i) w[i] = w[i] / norm;
         int n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
         if (n1 != n2) {
-            GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
+            GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
             int r = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr);
             f = r == 1 ? 1 : 0; beads = 2ull * (unsigned long long)(m - 1);
         }
