@@ -1035,7 +1035,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
                 long long ctrv = h->Nctr + it + 1;
                 if (ctrv % h->cfg.Ncycle == 0) {
                     MP.k = h->N_MC + ctrv / h->cfg.Ncycle - 1;
-                    k_measure<<<S.C, 256, 0, h->stream>>>(S, h->dT, MP); LAUNCHED(); launches++;
+                    if (pk == PIMC_POT_ZERO) k_measure<PIMC_POT_ZERO><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
+                    else if (pk == PIMC_POT_HARMONIC) k_measure<PIMC_POT_HARMONIC><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
+                    else k_measure<PIMC_POT_LATTICE><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
+                    LAUNCHED(); launches++;
                 }
             }
         }

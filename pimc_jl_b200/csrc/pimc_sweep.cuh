@@ -11,8 +11,8 @@
 #pragma once
 #include "pimc_moves.cuh"
 
-#define SWEEP_THREADS 256
-#define SWEEP_BCAP 2048   // staged rows per batch (xs, ys, pv: 24 B each)
+#define SWEEP_THREADS 128
+#define SWEEP_BCAP 1024   // staged rows per batch (xs, ys, pv: 24 B each)
 #define SWEEP_TBMAX 256   // tasks per batch
 
 struct SweepParams {
@@ -90,7 +90,7 @@ __device__ __forceinline__ void d_bookkeep_sweep(const UpdDev &U, int c, const u
 }
 
 template <int POT>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__global__ void __launch_bounds__(SWEEP_THREADS, 1024 / SWEEP_THREADS) k_reshape_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
 {
     extern __shared__ double sm[];
     double *xs = sm, *ys = sm + SWEEP_BCAP, *pv = sm + 2 * SWEEP_BCAP;               // pv only touched when POT != 0
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_reshape_sweep(DevSys S, co
         for (int w = 0; w < warp; ++w) wbase += s_scan[w];
         incl += wbase;
         const int excl = incl - cnt;
-        const bool fits = slot < N && incl <= SWEEP_BCAP;
+        const bool fits = slot < N && incl <= SWEEP_BCAP && tid < SWEEP_TBMAX;
         const int TB = __syncthreads_count(fits);      // prefix property: the fitting tasks are exactly the first TB
         if (fits) { t_m[tid] = m; t_off[tid] = excl; }
         __syncthreads();
@@ -254,7 +254,7 @@ __device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, 
 
 // KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
 template <int POT, int KM>
-__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 4 : 3)) k_com_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_com_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
 {
     extern __shared__ double sm[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = SWEEP_THREADS / 32;
@@ -401,6 +401,43 @@ __global__ void k_swap_iter(DevSys S, const DevTables *__restrict__ T, SweepPara
 
 // measurement_Z_sector (measurement.jl:1-17) for every chain at one cadence hit; k = 0-based measurement index
 struct MeasParams { int nen; int en_id[PIMC_MAXE]; int nde; int de_id[PIMC_MAXD]; long long k; };
+// Energy functor (measurement.jl:92-122) with one warp per worldline (lanes stride the slices: coalesced, no index division)
+template <int POT>
+__device__ __forceinline__ void d_energy_block_fast(const DevSys &S, int c, double *red, double *E, double *Ev)
+{
+    const int M = S.M, N = S.N, dim = S.dim, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double L = S.L, twoL = 2 * S.L;
+    const double *rc = S.r + (size_t)c * N * dim * M;
+    const int *nextc = S.next + (size_t)c * N;
+    double link = 0.0, pot = 0.0, vkin = 0.0;
+    for (int n = warp; n < N; n += nw) {
+        const double *rx = rc + (size_t)(n * dim) * M, *ry = rx + M;
+        const int nx = nextc[n];
+        const double *qx = rc + (size_t)(nx * dim) * M, *qy = qx + M;
+        for (int j = lane; j < M; j += 32) {
+            const double ax = rx[j], ay = dim > 1 ? ry[j] : 0.0;
+            const double bx = j == M - 1 ? qx[0] : rx[j + 1], by = dim > 1 ? (j == M - 1 ? qy[0] : ry[j + 1]) : 0.0;
+            double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
+            double d2 = dx * dx;
+            if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
+            link += d2;
+            if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
+            vkin += d_rdv(S.pot, ax, ay, dim);
+        }
+    }
+    (void)L;
+    link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
+    __syncthreads();
+    if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        link = 0.0; pot = 0.0; vkin = 0.0;
+        for (int i = 0; i < nw; ++i) { link += red[i]; pot += red[32 + i]; vkin += red[64 + i]; }
+        *E = (double)(S.dim * S.N) / (2 * S.tau) - 1 / (4 * S.lambda * (S.tau * S.tau) * S.M) * link + 1.0 / (2 * S.M) * pot;
+        *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
+    }
+}
+template <int POT>
 __global__ void __launch_bounds__(256) k_measure(DevSys S, const DevTables *__restrict__ T, MeasParams P)
 {
     __shared__ double red[96];
@@ -408,7 +445,7 @@ __global__ void __launch_bounds__(256) k_measure(DevSys S, const DevTables *__re
     for (int e = 0; e < P.nen; ++e) {
         const EnDev &En = T->en[P.en_id[e]];
         double E, Ev;
-        d_energy_block(S, c, red, &E, &Ev, nullptr);
+        d_energy_block_fast<POT>(S, c, red, &E, &Ev);
         if (threadIdx.x == 0) {
             if (P.k < En.cap) { En.E[(size_t)P.k * S.C + c] = E; En.Ev[(size_t)P.k * S.C + c] = Ev; }
             double *a = En.acc + (size_t)c * 5;
