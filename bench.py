@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--iters", type=int, default=100, help="run! iterations per step")
+    ap.add_argument("--iters", type=int, default=400, help="run! iterations per step")
     ap.add_argument("--therm", type=int, default=300, help="untimed thermalisation iterations before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=0)

@@ -1,5 +1,6 @@
 // pimc_b200.cu -- kernels and C ABI of libpimc_b200.so (sm_100a).  See include/pimc_b200.h and DESIGN.md.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cstdio>
 #include "pimc_moves.cuh"
 #include "pimc_sweep.cuh"
 #include <cstdio>
@@ -997,7 +998,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
-    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_TBMAX * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 16;
+    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 3 : 4) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 16;
     const size_t smem_cs = (size_t)S.N + 16;
     const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 48 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
@@ -1009,13 +1010,11 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
         const int KM = (S.M + 31) / 32;
         typedef void (*kfn)(DevSys, const DevTables *, SweepParams);
-        kfn k_rs = pk == PIMC_POT_ZERO ? k_reshape_sweep<PIMC_POT_ZERO> : (pk == PIMC_POT_HARMONIC ? k_reshape_sweep<PIMC_POT_HARMONIC> : k_reshape_sweep<PIMC_POT_LATTICE>);
-        kfn k_cs = nullptr;
-#define PICK_COM(P_) (KM <= 1 ? k_com_sweep<P_, 1> : KM <= 2 ? k_com_sweep<P_, 2> : KM <= 4 ? k_com_sweep<P_, 4> : k_com_sweep<P_, 8>)
-        k_cs = pk == PIMC_POT_ZERO ? PICK_COM(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_COM(PIMC_POT_HARMONIC) : PICK_COM(PIMC_POT_LATTICE));
-#undef PICK_COM
-        cudaFuncSetAttribute(k_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_rs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#define PICK_SWEEP(P_) (KM <= 1 ? k_sweep<P_, 1> : KM <= 2 ? k_sweep<P_, 2> : KM <= 4 ? k_sweep<P_, 4> : k_sweep<P_, 8>)
+        kfn k_sw = pk == PIMC_POT_ZERO ? PICK_SWEEP(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP(PIMC_POT_HARMONIC) : PICK_SWEEP(PIMC_POT_LATTICE));
+#undef PICK_SWEEP
+        cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         SweepParams SP; memset(&SP, 0, sizeof SP);
         SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS;
         pimc_roundkeys_make(S.seed, &SP.rk);
@@ -1028,8 +1027,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if (has_com) { k_cs<<<S.C, SWEEP_THREADS, smem_cs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
-            if (has_rs) { k_rs<<<S.C, SWEEP_THREADS, smem_rs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, smem_rs > smem_cs ? smem_rs : smem_cs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;

@@ -14,6 +14,11 @@
 #define SWEEP_THREADS 128
 #define SWEEP_BCAP 1024   // staged rows per batch (xs, ys, pv: 24 B each)
 #define SWEEP_TBMAX 256   // tasks per batch
+#ifdef EXP_TIMING
+#define TICK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
 
 struct SweepParams {
     unsigned long long iter;
@@ -30,9 +35,9 @@ __device__ __forceinline__ double d_teleport_fast(double x, double L, double two
 {
     double s = x * inv2L + 0.5;
     double f = floor(s);
-    double d = s - f;
-    double eps = 1e-9 * fmax(1.0, fabs(s));
-    if (d < eps || d > 1.0 - eps) f = floor(x / twoL + 0.5);
+    double d = s - f;                       // in [0, 1): distance of q + 0.5 to the integer below
+    // |q_fast - q_exact| < 1e-9 for |s| < 1e6, so the floors agree unless d is within 1e-9 of 0 or 1 (NaN also lands here)
+    if (!(fabs(d - 0.5) <= 0.5 - 1e-9) || !(fabs(s) < 1e6)) f = floor(x / twoL + 0.5);
     return ((x + L) - f * twoL) - L;
 }
 
@@ -89,126 +94,209 @@ __device__ __forceinline__ void d_bookkeep_sweep(const UpdDev &U, int c, const u
     if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
 }
 
+// ---- warp-cooperative variant: 32 outcomes per step are gathered with ballots and appended to the ring with word operations.
+// Final state (head, len, sum, tries, ring bits, adaptive variable) is identical to pushing the outcomes one by one.
+__device__ __forceinline__ unsigned d_ring_read_bits(const unsigned *ring, int cap, int pos, int n) // n <= 32 bits starting at pos (wraps at cap)
+{
+    const int n1 = n < cap - pos ? n : cap - pos;
+    const int w = pos >> 5, o = pos & 31;
+    unsigned long long two = (unsigned long long)ring[w];
+    if (o + n1 > 32) two |= (unsigned long long)ring[w + 1] << 32;
+    unsigned out = (unsigned)((two >> o) & ((n1 >= 32) ? 0xFFFFFFFFull : ((1ull << n1) - 1ull)));
+    if (n1 < n) out |= (ring[0] & ((1u << (n - n1)) - 1u)) << n1;
+    return out;
+}
+__device__ __forceinline__ void d_ring_write_seg(unsigned *ring, int pos, int n, unsigned bits) // n <= 32 bits, no wrap inside
+{
+    const int w = pos >> 5, o = pos & 31;
+    const unsigned long long m = ((n >= 32) ? 0xFFFFFFFFull : ((1ull << n) - 1ull)) << o;
+    const unsigned long long v = ((unsigned long long)bits << o) & m;
+    ring[w] = (ring[w] & ~(unsigned)m) | (unsigned)v;
+    if (o + n > 32) ring[w + 1] = (ring[w + 1] & ~(unsigned)(m >> 32)) | (unsigned)(v >> 32);
+}
+__device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, const unsigned char *flag, int ntask, unsigned long long beads,
+                                                      unsigned long long *stats)
+{
+    const int lane = threadIdx.x & 31;
+    if (U.range < 64) { if (lane == 0) d_bookkeep_sweep(U, c, flag, ntask, beads, stats); return; }
+    unsigned *ring = U.ring + (size_t)c * U.ring_words;
+    const int cap = (int)U.range + 1, range = (int)U.range;
+    int head = U.ring_head[c], len = U.ring_len[c], sum = U.ring_sum[c];
+    long long tries = U.tries_var[c];
+    const long long tries0 = tries;
+    long long tr = U.tries[c], ac = U.accepted[c];
+    int cnt = 0;
+    for (int base = 0; base < ntask; base += 32) {
+        const int f = base + lane < ntask ? flag[base + lane] : 2;
+        const unsigned valid = __ballot_sync(0xffffffffu, f < 2), accb = __ballot_sync(0xffffffffu, f == 1), early = __ballot_sync(0xffffffffu, f == 3);
+        if (lane != 0) continue;
+        cnt += __popc(valid | early); tr += __popc(valid | early);
+        unsigned todo = valid;
+        while (todo) {
+            // longest run of consecutive valid outcomes starting at the lowest set bit
+            const int lo = __ffs(todo) - 1;
+            const unsigned run = todo >> lo;
+            const int k = (run == 0xFFFFFFFFu) ? 32 : (__ffs(~run) - 1);
+            const unsigned bits = (accb >> lo) & ((k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u));
+            todo &= (k + lo >= 32) ? 0u : ~((1u << (k + lo)) - 1u);
+            const int e = len + k - range;
+            if (e > 0) { sum -= __popc(d_ring_read_bits(ring, cap, head, e)); head += e; if (head >= cap) head -= cap; len -= e; }
+            int tail = head + len; if (tail >= cap) tail -= cap;
+            const int k1 = k < cap - tail ? k : cap - tail;
+            d_ring_write_seg(ring, tail, k1, bits);
+            if (k1 < k) d_ring_write_seg(ring, 0, k - k1, bits >> k1);
+            len += k; sum += __popc(bits); tries += k; ac += __popc(bits);
+        }
+    }
+    if (lane != 0) return;
+    RingReg R; R.head = head; R.len = len; R.sum = sum; R.tries = tries;
+    bool adj = cnt > 0 && (tries / U.adj) != (tries0 / U.adj);
+    U.ring_head[c] = head; U.ring_len[c] = len; U.ring_sum[c] = sum; U.tries_var[c] = tries;
+    U.tries[c] = tr; U.accepted[c] = ac; U.bead_moves[c] += (long long)beads;
+    if (adj) d_adjust(U, c, R);
+    if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
+}
+
 template <int POT>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1024 / SWEEP_THREADS) k_reshape_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevTables *__restrict__ T, const SweepParams &P, const pimc_stream &st,
+                                                     const pimc_u4 &di, const int pick)
 {
     extern __shared__ double sm[];
-    double *xs = sm, *ys = sm + SWEEP_BCAP, *pv = sm + 2 * SWEEP_BCAP;               // pv only touched when POT != 0
-    double *pend = (POT == PIMC_POT_ZERO) ? sm + 2 * SWEEP_BCAP : sm + 3 * SWEEP_BCAP;
-    int *t_m = (int *)pend;                    // [TBMAX] links of the task
-    int *t_off = t_m + SWEEP_TBMAX;            // [TBMAX] first staged row
-    unsigned char *map = (unsigned char *)(t_off + SWEEP_TBMAX);   // [BCAP] row -> task
+    double *xs = sm, *ys = sm + SWEEP_BCAP, *vo = sm + 2 * SWEEP_BCAP;               // vo: cached (old) link action of the row's link
+    double *pv = sm + 3 * SWEEP_BCAP;                                                 // potential at the new rows, only when POT != 0
+    double *pend = (POT == PIMC_POT_ZERO) ? sm + 3 * SWEEP_BCAP : sm + 4 * SWEEP_BCAP;
+    int *t_m = (int *)pend;                    // [THREADS] links of the batch's tasks
+    int *t_off = t_m + SWEEP_THREADS;          // [THREADS] first staged row
+    unsigned char *map = (unsigned char *)(t_off + SWEEP_THREADS);   // [BCAP] row -> task of the batch
     unsigned char *flag = map + SWEEP_BCAP;    // [N] outcome per slot
     double *s_alpha = (double *)(flag + ((S.N + 15) & ~15));  // [M+1] staging table alpha_k
     __shared__ int s_scan[SWEEP_THREADS / 32];
+    __shared__ int s_first;
     __shared__ unsigned long long s_bead;
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
-    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const int pick = d_pick_update(P, di);
-    if (P.kind[pick] != PIMC_UPD_RESHAPE_LINEAR) return;
     const UpdDev &U = T->upd[P.upd_id[pick]];
     const int var = (int)U.var[c], vmax = (int)P.vmax[pick];
     double *s_logtab = s_alpha + (M + 1);     // [2*128]
     for (int i = tid; i < 2 * PIMC_LOGTAB_N; i += SWEEP_THREADS) s_logtab[i] = S.logtab[i];
     const int j0 = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
-    const int nx_stride = N; (void)nx_stride;
     const int *nextc = S.next + (size_t)c * N;
+    double *rc = S.r + (size_t)c * N * dim * M;   // this chain's positions / link cache: 32-bit indexing below
+    double *vc = S.Vl + (size_t)c * N * M;
+    const int first = j0 - 1, nfirst = M - first;   // a strand's rows 0..nfirst-1 lie on its own particle, the rest on the next one
     if (tid == 0) s_bead = 0;
     for (int i = tid; i <= M; i += SWEEP_THREADS) s_alpha[i] = S.tab_alpha[i];
     unsigned long long my_beads = 0;
+#ifdef EXP_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(), tstart = tlast; int nbatch = 0;
+#endif
 
-    for (int t0 = 0; t0 < N;) {
-        // ---- batch selection: tasks t0.. as long as their rows (m + 1 each) fit the staging buffer ----
-        int slot = t0 + tid, m = 0, cnt = 0;
-        if (slot < N) {
-            pimc_u4 dt = pimc_draw_rk(st, &P.rk, (uint32_t)slot, PIMC_K_TASK, 0, 0);
+    // super-batch: SWEEP_THREADS tasks, one per thread; their segment length and endpoints are fetched once (one Philox draw,
+    // one round of global loads) and stay in registers until the task's batch comes up
+    for (int sb0 = 0; sb0 < N; sb0 += SWEEP_THREADS) {
+        const int n = sb0 + tid;
+        int m = 0, cnt = 0, nx = 0;
+        double bx = 0.0, by = 0.0, ex = 0.0, ey = 0.0;
+        if (n < N) {
+            pimc_u4 dt = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 0);
             int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
             m = vmax < mm ? vmax : mm;
             cnt = m + 1;
+            nx = nextc[n];
+            // endpoints (reshape.jl:56-58) with the boundary shift of levy! (helper.jl:120-125)
+            const int pe = m < nfirst ? n : nx, je = m < nfirst ? first + m : m - nfirst;
+            bx = rc[(n * dim) * M + first]; ex = rc[(pe * dim) * M + je];
+            if (fabs(bx - ex) > L) ex += d_sign(bx) * twoL;
+            if (dim > 1) {
+                by = rc[(n * dim + 1) * M + first]; ey = rc[(pe * dim + 1) * M + je];
+                if (fabs(by - ey) > L) ey += d_sign(by) * twoL;
+            }
+            my_beads += (unsigned long long)(m - 1);
         }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncthreads();                       // previous super-batch done with s_scan / staging
         if (lane == 31) s_scan[warp] = incl;
         __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_scan[w];
-        incl += wbase;
-        const int excl = incl - cnt;
-        const bool fits = slot < N && incl <= SWEEP_BCAP && tid < SWEEP_TBMAX;
-        const int TB = __syncthreads_count(fits);      // prefix property: the fitting tasks are exactly the first TB
-        if (fits) { t_m[tid] = m; t_off[tid] = excl; }
-        __syncthreads();
-        const int B = t_off[TB - 1] + t_m[TB - 1] + 1;
-        if (tid < TB) {
-            // endpoints (reshape.jl:56-58) with the boundary shift of levy! (helper.jl:120-125); map rows -> task
-            const int n = slot, jm = j0 + m;
-            const int pe = jm <= M ? n : nextc[n], je = (jm <= M ? jm : jm - M) - 1;
-            double bx = S.r[RIDX(S, c, n, 0, j0 - 1)], ex = S.r[RIDX(S, c, pe, 0, je)];
-            if (fabs(bx - ex) > L) ex += d_sign(bx) * twoL;
-            xs[excl] = bx; xs[excl + m] = ex;
-            if (dim > 1) {
-                double by = S.r[RIDX(S, c, n, 1, j0 - 1)], ey = S.r[RIDX(S, c, pe, 1, je)];
-                if (fabs(by - ey) > L) ey += d_sign(by) * twoL;
-                ys[excl] = by; ys[excl + m] = ey;
+        for (int w = 0; w < warp; ++w) incl += s_scan[w];
+        const int nsb = N - sb0 < SWEEP_THREADS ? N - sb0 : SWEEP_THREADS;
+
+        for (int b0 = 0; b0 < nsb;) {          // batches: consecutive tasks whose rows (m + 1 each) fit the staging buffer
+            TICK(7);
+            if (tid == b0) s_first = incl - cnt;
+            __syncthreads();
+            const int basep = s_first;
+            const bool fits = tid >= b0 && tid < nsb && incl - basep <= SWEEP_BCAP;
+            const int TB = __syncthreads_count(fits);      // prefix property: the fitting tasks are b0 .. b0+TB-1
+            const int q_me = tid - b0, excl = incl - cnt - basep;
+            if (fits) {
+                t_m[q_me] = m; t_off[q_me] = excl;
+                xs[excl] = bx; xs[excl + m] = ex;
+                if (dim > 1) { ys[excl] = by; ys[excl + m] = ey; }
+                for (int r = 0; r <= m; ++r) map[excl + r] = (unsigned char)q_me;
             }
-            for (int r = 0; r <= m; ++r) map[excl + r] = (unsigned char)tid;
-            my_beads += (unsigned long long)(m - 1);
-        }
-        __syncthreads();
-        // ---- phase A: Gaussians of every interior row, lanes = rows ----
-        for (int s = tid; s < B; s += SWEEP_THREADS) {
-            const int q = map[s], row = s - t_off[q], mq = t_m[q];
-            if (row >= 1 && row < mq) {
-                double g0, g1;
-                pimc_gauss_pair_t(pimc_draw_rk(st, &P.rk, (uint32_t)(t0 + q), PIMC_K_BRIDGE, 0, (uint32_t)row), s_logtab, &g0, &g1);
-                const double sig = S.tab_sig[mq + 1 - row];
-                xs[s] = g0 * sig;
-                if (dim > 1) ys[s] = g1 * sig;
+            __syncthreads();
+            const int B = t_off[TB - 1] + t_m[TB - 1] + 1;
+            TICK(0);
+            // ---- phase A: Gaussians of every interior row, lanes = rows; the old link action of the row's link is fetched alongside ----
+#ifndef EXP_SKIP_A
+            for (int s = tid; s < B; s += SWEEP_THREADS) {
+                const int q = map[s], row = s - t_off[q], mq = t_m[q];
+                double vold = 0.0;              // issued first, consumed last: the load's latency hides behind the Gaussian arithmetic
+                if (row < mq) {                 // link `row` of the strand: slice first+row of its particle, or wrapped on the next particle
+                    const int nq = sb0 + b0 + q;
+                    vold = row < nfirst ? vc[nq * M + first + row] : vc[nextc[nq] * M + row - nfirst];
+                }
+                if (row >= 1 && row < mq) {
+                    double g0, g1;
+                    pimc_gauss_pair_t(pimc_draw_rk(st, &P.rk, (uint32_t)(sb0 + b0 + q), PIMC_K_BRIDGE, 0, (uint32_t)row), s_logtab, &g0, &g1);
+                    const double sig = S.tab_sig[mq + 1 - row];
+                    xs[s] = g0 * sig;
+                    if (dim > 1) ys[s] = g1 * sig;
+                }
+                if (row < mq) vo[s] = vold;
             }
-        }
-        __syncthreads();
-        // ---- phase B: serial recurrence r[j+1] = (alpha r[j] + (1-alpha) r[end]) + xi sigma, lanes = (task, dim) ----
-        for (int w = tid; w < TB * dim; w += SWEEP_THREADS) {
-            const int q = dim > 1 ? (w >> 1) : w, k = dim > 1 ? (w & 1) : 0;
-            double *arr = k ? ys : xs;
-            const int base = t_off[q], mq = t_m[q];
-            double prev = arr[base];
-            const double e = arr[base + mq];
-            const double *al = s_alpha + mq + 1;  // alpha of row `row` is al[-row]
-            double *ar = arr + base;
+#endif
+            __syncthreads();
+            TICK(1);
+            // ---- phase B: serial recurrence r[j+1] = (alpha r[j] + (1-alpha) r[end]) + xi sigma, lanes = (task, dim) ----
+#ifndef EXP_SKIP_B
+            for (int w = tid; w < TB * dim; w += SWEEP_THREADS) {
+                const int q = dim > 1 ? (w >> 1) : w, k = dim > 1 ? (w & 1) : 0;
+                double *arr = k ? ys : xs;
+                const int base = t_off[q], mq = t_m[q];
+                double prev = arr[base];
+                const double e = arr[base + mq];
+                const double *al = s_alpha + mq + 1;  // alpha of row `row` is al[-row]
+                double *ar = arr + base;
 #pragma unroll 4
-            for (int row = 1; row < mq; ++row) {
-                const double a = al[-row];
-                prev = a * prev + (1 - a) * e + ar[row];
-                ar[row] = prev;
+                for (int row = 1; row < mq; ++row) {
+                    const double a = al[-row];
+                    prev = a * prev + (1 - a) * e + ar[row];
+                    ar[row] = prev;
+                }
             }
-        }
-        __syncthreads();
-        // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
-        for (int s = tid; s < B; s += SWEEP_THREADS) {
-            double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
-            xs[s] = x;
-            if (dim > 1) { y = d_teleport_fast(ys[s], L, twoL, inv2L); ys[s] = y; }
-            if (POT != PIMC_POT_ZERO) pv[s] = d_pot_t<POT>(S.pot, x, y, dim);
-        }
-        __syncthreads();
-        // ---- phase D: Delta-U, Metropolis, commit -- one warp per task ----
-        {
-            double *rc = S.r + (size_t)c * N * dim * M;   // this chain's positions / link cache: 32-bit indexing below
-            double *vc = S.Vl + (size_t)c * N * M;
+#endif
+            __syncthreads();
+            TICK(2);
+            // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
+            for (int s = tid; s < B; s += SWEEP_THREADS) {
+                double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
+                xs[s] = x;
+                if (dim > 1) { y = d_teleport_fast(ys[s], L, twoL, inv2L); ys[s] = y; }
+                if (POT != PIMC_POT_ZERO) pv[s] = d_pot_t<POT>(S.pot, x, y, dim);
+            }
+            __syncthreads();
+            TICK(3);
+            // ---- phase D: Delta-U from shared memory, Metropolis, coalesced commit -- one warp per task ----
             for (int q = warp; q < TB; q += SWEEP_THREADS / 32) {
-                const int n = t0 + q, mq = t_m[q], base = t_off[q], nx = nextc[n];
-                // link jp (1-based) starts at slice j0-1+jp-1 of n, or wrapped on the next particle of the cycle
-                const int first = j0 - 1, nfirst = M - first;           // rows 0..nfirst-1 stay on particle n
+                const int nq = sb0 + b0 + q, mq = t_m[q], base = t_off[q], nxq = nextc[nq];
                 double wi = 0.0, wu = 0.0;
                 for (int jp = lane; jp < mq; jp += 32) {
-                    const int p = jp < nfirst ? n : nx, sl = jp < nfirst ? first + jp : jp - nfirst;
-                    wi += vc[p * M + sl];
+                    wi += vo[base + jp];
                     wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
                 }
                 wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
@@ -219,27 +307,43 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1024 / SWEEP_THREADS) k_reshape
                     else {
                         const double delta = pimc_exp(dw);
                         if (delta >= 1.0) acc = 1;
-                        else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                        else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)nq, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
                     }
-                    flag[n] = (unsigned char)acc;
+                    flag[nq] = (unsigned char)acc;
                 }
                 acc = __shfl_sync(0xffffffffu, acc, 0);
                 if (acc) {
-                    for (int jp = lane; jp < mq; jp += 32) {
-                        const int p = jp < nfirst ? n : nx, sl = jp < nfirst ? first + jp : jp - nfirst;
-                        rc[(p * dim) * M + sl] = xs[base + jp];
-                        if (dim > 1) rc[(p * dim + 1) * M + sl] = ys[base + jp];
-                        vc[p * M + sl] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                    const int n1 = mq < nfirst ? mq : nfirst;                 // rows 0..n1-1 on particle nq, the rest wrapped on nxq
+                    double *x1 = rc + (nq * dim) * M + first, *x2 = rc + (nxq * dim) * M - nfirst;
+                    double *w1 = vc + nq * M + first, *w2 = vc + nxq * M - nfirst;
+                    for (int jp = lane; jp < n1; jp += 32) {
+                        x1[jp] = xs[base + jp];
+                        if (dim > 1) x1[M + jp] = ys[base + jp];
+                        w1[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                    }
+                    for (int jp = nfirst + lane; jp < mq; jp += 32) {
+                        x2[jp] = xs[base + jp];
+                        if (dim > 1) x2[M + jp] = ys[base + jp];
+                        w2[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
                     }
                 }
             }
+            __syncthreads();
+            TICK(4);
+#ifdef EXP_TIMING
+            nbatch++;
+#endif
+            b0 += TB;
         }
-        __syncthreads();
-        t0 += TB;
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
-    if (tid == 0) d_bookkeep_sweep(U, c, flag, N, s_bead, P.stats);
+    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats);
+#ifdef EXP_TIMING
+    TICK(5);
+    if (threadIdx.x == 0 && (blockIdx.x % 512) == 7 && (P.iter % 64) == 3)
+        printf("blk %d iter %llu batches %d cycles: setup %lld A %lld B %lld C %lld D %lld book %lld total %lld\n", blockIdx.x, P.iter, nbatch, tacc[0] + tacc[7], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], clock64() - tstart);
+#endif
 }
 
 // generic centre-of-mass proposal for a permutation cycle of several worldlines (rare in a sweep): kept out of line so that it
@@ -254,17 +358,14 @@ __device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, 
 
 // KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
 template <int POT, int KM>
-__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_com_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTables *__restrict__ T, const SweepParams &P, const pimc_stream &st,
+                                                 const int pick)
 {
     extern __shared__ double sm[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = SWEEP_THREADS / 32;
     const int M = S.M, N = S.N, dim = S.dim;
     unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
-    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const int pick = d_pick_update(P, di);
-    if (P.kind[pick] != PIMC_UPD_SINGLE_COM && P.kind[pick] != PIMC_UPD_POLYMER_COM) return;
     const UpdDev &U = T->upd[P.upd_id[pick]];
     const bool polymer = P.kind[pick] == PIMC_UPD_POLYMER_COM;
     const double maxd = U.var[c];
@@ -356,7 +457,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
-    if (tid == 0) d_bookkeep_sweep(U, c, flag, N, s_bead, P.stats);
+    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats);
+}
+
+// One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
+template <int POT, int KM>
+__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+{
+    const int c = blockIdx.x;
+    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    const int kind = P.kind[pick];
+    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, T, P, st, di, pick);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, T, P, st, pick);
 }
 
 // the swap move stays one proposal per chain and iteration (reshape.jl:123-283), thread 0 of a one-warp CTA
