@@ -11,8 +11,8 @@
 #pragma once
 #include "pimc_moves.cuh"
 
-#define SWEEP_THREADS 128
-#define SWEEP_BCAP 1024   // staged rows per batch (xs, ys, pv: 24 B each)
+#define SWEEP_THREADS 256
+#define SWEEP_BCAP 2048   // staged rows per batch (xs, ys, pv: 24 B each)
 #define SWEEP_TBMAX 256   // tasks per batch
 #ifdef EXP_TIMING
 #define TICK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
@@ -114,17 +114,27 @@ __device__ __forceinline__ void d_ring_write_seg(unsigned *ring, int pos, int n,
     ring[w] = (ring[w] & ~(unsigned)m) | (unsigned)v;
     if (o + n > 32) ring[w + 1] = (ring[w + 1] & ~(unsigned)(m >> 32)) | (unsigned)(v >> 32);
 }
+// per-chain counters of one update object, fetched at the START of a sweep kernel (thread 0) so that the global-memory
+// latency is hidden behind the moves instead of sitting on the CTA's tail
+struct BookPre { int head, len, sum; long long tries, tr, ac; double var; long long range, adj; };
+__device__ __forceinline__ BookPre d_book_prefetch(const UpdDev &U, int c)
+{
+    BookPre b; b.head = U.ring_head[c]; b.len = U.ring_len[c]; b.sum = U.ring_sum[c]; b.tries = U.tries_var[c];
+    b.tr = U.tries[c]; b.ac = U.accepted[c]; b.var = U.var[c]; b.range = U.range; b.adj = U.adj;
+    return b;
+}
 __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, const unsigned char *flag, int ntask, unsigned long long beads,
-                                                      unsigned long long *stats)
+                                                      unsigned long long *stats, const BookPre &pre)
 {
     const int lane = threadIdx.x & 31;
-    if (U.range < 64) { if (lane == 0) d_bookkeep_sweep(U, c, flag, ntask, beads, stats); return; }
+    const long long range_ll = pre.range;
+    if (range_ll < 64) { if (lane == 0) d_bookkeep_sweep(U, c, flag, ntask, beads, stats); return; }
     unsigned *ring = U.ring + (size_t)c * U.ring_words;
-    const int cap = (int)U.range + 1, range = (int)U.range;
-    int head = U.ring_head[c], len = U.ring_len[c], sum = U.ring_sum[c];
-    long long tries = U.tries_var[c];
+    const int cap = (int)range_ll + 1, range = (int)range_ll;
+    int head = pre.head, len = pre.len, sum = pre.sum;
+    long long tries = pre.tries;
     const long long tries0 = tries;
-    long long tr = U.tries[c], ac = U.accepted[c];
+    long long tr = pre.tr, ac = pre.ac;
     int cnt = 0;
     for (int base = 0; base < ntask; base += 32) {
         const int f = base + lane < ntask ? flag[base + lane] : 2;
@@ -149,11 +159,16 @@ __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, co
         }
     }
     if (lane != 0) return;
-    RingReg R; R.head = head; R.len = len; R.sum = sum; R.tries = tries;
-    bool adj = cnt > 0 && (tries / U.adj) != (tries0 / U.adj);
+    bool adj = cnt > 0 && (tries / pre.adj) != (tries0 / pre.adj);
     U.ring_head[c] = head; U.ring_len[c] = len; U.ring_sum[c] = sum; U.tries_var[c] = tries;
-    U.tries[c] = tr; U.accepted[c] = ac; U.bead_moves[c] += (long long)beads;
-    if (adj) d_adjust(U, c, R);
+    U.tries[c] = tr; U.accepted[c] = ac; atomicAdd((unsigned long long *)&U.bead_moves[c], beads);
+    if (adj) { // adjust! (helper.jl:22-52) on the prefetched variable
+        double acc = (double)sum / (double)len, v = pre.var;
+        if (U.kind == PIMC_UPD_RESHAPE_LINEAR || U.kind == PIMC_UPD_RESHAPE_SWAP) { if (acc < U.minacc) v -= 1; else if (acc > U.maxacc) v += 1; }
+        else { if (acc < U.minacc) v *= 0.9; else if (acc > U.maxacc) v *= 1.1; }
+        v = U.vmin > v ? U.vmin : v; v = U.vmax < v ? U.vmax : v;
+        U.var[c] = v;
+    }
     if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
 }
 
@@ -177,6 +192,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
     const UpdDev &U = T->upd[P.upd_id[pick]];
+    __shared__ BookPre s_pre; if (tid == 0) s_pre = d_book_prefetch(U, c);   // parked in shared memory: no registers held across the sweep
     const int var = (int)U.var[c], vmax = (int)P.vmax[pick];
     double *s_logtab = s_alpha + (M + 1);     // [2*128]
     for (int i = tid; i < 2 * PIMC_LOGTAB_N; i += SWEEP_THREADS) s_logtab[i] = S.logtab[i];
@@ -272,11 +288,15 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
                 const double e = arr[base + mq];
                 const double *al = s_alpha + mq + 1;  // alpha of row `row` is al[-row]
                 double *ar = arr + base;
-#pragma unroll 4
+                // software pipelined by hand: next step's alpha and xi*sigma are fetched before this step's store, so that only
+                // DMUL -> DADD -> DADD sits on the serial path (the compiler cannot hoist the loads over the aliasing store)
+                double a = al[-1], g = ar[1];
                 for (int row = 1; row < mq; ++row) {
-                    const double a = al[-row];
-                    prev = a * prev + (1 - a) * e + ar[row];
+                    const double a_n = al[-(row + 1)], g_n = ar[row + 1];   // row + 1 <= mq: the end row / alpha_1 slots exist
+                    const double t = (1 - a) * e;
+                    prev = a * prev + t + g;
                     ar[row] = prev;
+                    a = a_n; g = g_n;
                 }
             }
 #endif
@@ -338,7 +358,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
-    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats);
+    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 #ifdef EXP_TIMING
     TICK(5);
     if (threadIdx.x == 0 && (blockIdx.x % 512) == 7 && (P.iter % 64) == 3)
@@ -367,6 +387,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTable
     unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
     const UpdDev &U = T->upd[P.upd_id[pick]];
+    __shared__ BookPre s_pre; if (tid == 0) s_pre = d_book_prefetch(U, c);
     const bool polymer = P.kind[pick] == PIMC_UPD_POLYMER_COM;
     const double maxd = U.var[c];
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
@@ -457,7 +478,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTable
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
-    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats);
+    if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 }
 
 // One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
