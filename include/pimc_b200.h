@@ -154,6 +154,8 @@ int pimc_update_get(pimc_handle *h, int32_t id, int32_t chain, double *var, int6
 int pimc_energy_create(pimc_handle *h, int64_t cap, int32_t *id);
 /* chain >= 0: that chain's series ; chain = -1: mean over this handle's chains per measurement index */
 int pimc_energy_read(pimc_handle *h, int32_t id, int32_t chain, double *E, double *Ev, int64_t cap, int64_t *n);
+/* same, entries [start, start+count) only (a measurement block); *n = total number of measurements taken */
+int pimc_energy_read_range(pimc_handle *h, int32_t id, int32_t chain, int64_t start, int64_t count, double *E, double *Ev, int64_t *n);
 /* per-chain accumulators: out[chains][5] = n, sum E, sum E^2, sum Ev, sum Ev^2 */
 int pimc_energy_stats(pimc_handle *h, int32_t id, double *out);
 int pimc_density_create(pimc_handle *h, int64_t nbins, int32_t *id);

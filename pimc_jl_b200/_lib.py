@@ -88,6 +88,7 @@ SIGNATURES = {
     "pimc_update_get": (C.c_int, [_vp, _i32, _i32, f64p, i64p, i64p, f64p, i64p, i64p]),
     "pimc_energy_create": (C.c_int, [_vp, _i64, i32p]),
     "pimc_energy_read": (C.c_int, [_vp, _i32, _i32, f64p, f64p, _i64, i64p]),
+    "pimc_energy_read_range": (C.c_int, [_vp, _i32, _i32, _i64, _i64, f64p, f64p, i64p]),
     "pimc_energy_stats": (C.c_int, [_vp, _i32, f64p]),
     "pimc_density_create": (C.c_int, [_vp, _i64, i32p]),
     "pimc_density_measure": (C.c_int, [_vp, _i32]),

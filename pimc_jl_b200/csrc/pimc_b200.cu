@@ -282,20 +282,24 @@ __global__ void k_action(DevSys S, double *cached, double *recomputed)
     __syncthreads();
     if (threadIdx.x == 0) { a = 0; b = 0; for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) { a += red[i]; b += red[32 + i]; } cached[c] = a; recomputed[c] = b; }
 }
-// mean over chains of the energy series (deterministic order), one thread per measurement index
-__global__ void k_energy_chain_mean(const double *E, const double *Ev, int C, long long n, double *mE, double *mEv)
+// mean over chains of the energy series: one CTA per measurement index, coalesced over the chain-fastest layout, fixed
+// reduction tree (deterministic)
+__global__ void k_energy_chain_mean(const double *E, const double *Ev, int C, long long k0, double *mE, double *mEv)
 {
-    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    __shared__ double ra[8], rb[8];
+    const long long k = k0 + blockIdx.x;
     double a = 0.0, b = 0.0;
-    for (int c = 0; c < C; ++c) { a += E[(size_t)k * C + c]; b += Ev[(size_t)k * C + c]; }
-    mE[k] = a / C; mEv[k] = b / C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { a += E[(size_t)k * C + c]; b += Ev[(size_t)k * C + c]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = a; rb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) { a = 0.0; b = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += ra[i]; b += rb[i]; } mE[blockIdx.x] = a / C; mEv[blockIdx.x] = b / C; }
 }
-__global__ void k_energy_chain_series(const double *E, const double *Ev, int C, int c, long long n, double *oE, double *oEv)
+__global__ void k_energy_chain_series(const double *E, const double *Ev, int C, int c, long long k0, long long n, double *oE, double *oEv)
 {
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (k >= n) return;
-    oE[k] = E[(size_t)k * C + c]; oEv[k] = Ev[(size_t)k * C + c];
+    oE[k] = E[(size_t)(k0 + k) * C + c]; oEv[k] = Ev[(size_t)(k0 + k) * C + c];
 }
 __global__ void k_dens_to_double(const unsigned long long *d, size_t n, double *o)
 {
@@ -901,23 +905,28 @@ static int energy_count(pimc_handle *h, int id, long long *n)
     double a0; CK(h, cudaMemcpy(&a0, h->T.en[id].acc, sizeof(double), cudaMemcpyDeviceToHost));
     *n = (long long)a0; return PIMC_OK;
 }
-extern "C" int pimc_energy_read(pimc_handle *h, int32_t id, int32_t chain, double *E, double *Ev, int64_t cap, int64_t *n)
+extern "C" int pimc_energy_read_range(pimc_handle *h, int32_t id, int32_t chain, int64_t start, int64_t count, double *E, double *Ev, int64_t *n)
 {
-    if (!h || id < 0 || id >= h->nen || chain < -1 || chain >= h->S.C) return PIMC_ERR_INVALID;
+    if (!h || id < 0 || id >= h->nen || chain < -1 || chain >= h->S.C || start < 0 || count < 0) return PIMC_ERR_INVALID;
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
     long long cnt; int rc = energy_count(h, id, &cnt); if (rc) return rc;
     if (n) *n = cnt;
-    long long m = cnt < h->T.en[id].cap ? cnt : h->T.en[id].cap; if (m > cap) m = cap;
+    long long avail = cnt < h->T.en[id].cap ? cnt : h->T.en[id].cap;
+    long long m = avail - start; if (m > count) m = count;
     if (m <= 0 || (!E && !Ev)) return PIMC_OK;
     TmpBuf t; double *a = t.up((double *)nullptr, m), *b = t.up((double *)nullptr, m); if (!a || !b) return PIMC_ERR_NOMEM;
-    if (chain < 0) k_energy_chain_mean<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, m, a, b);
-    else k_energy_chain_series<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, chain, m, a, b);
+    if (chain < 0) k_energy_chain_mean<<<(int)m, 256, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, start, a, b);
+    else k_energy_chain_series<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, chain, start, m, a, b);
     LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
     if (E) CK(h, cudaMemcpy(E, a, m * sizeof(double), cudaMemcpyDeviceToHost));
     if (Ev) CK(h, cudaMemcpy(Ev, b, m * sizeof(double), cudaMemcpyDeviceToHost));
     return PIMC_OK;
+}
+extern "C" int pimc_energy_read(pimc_handle *h, int32_t id, int32_t chain, double *E, double *Ev, int64_t cap, int64_t *n)
+{
+    return pimc_energy_read_range(h, id, chain, 0, cap, E, Ev, n);
 }
 extern "C" int pimc_energy_stats(pimc_handle *h, int32_t id, double *out)
 {
@@ -1033,9 +1042,11 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
                 long long ctrv = h->Nctr + it + 1;
                 if (ctrv % h->cfg.Ncycle == 0) {
                     MP.k = h->N_MC + ctrv / h->cfg.Ncycle - 1;
-                    if (pk == PIMC_POT_ZERO) k_measure<PIMC_POT_ZERO><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
-                    else if (pk == PIMC_POT_HARMONIC) k_measure<PIMC_POT_HARMONIC><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
-                    else k_measure<PIMC_POT_LATTICE><<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
+                    typedef void (*mfn)(DevSys, const DevTables *, MeasParams);
+#define PICK_MEAS(P_) (KM <= 1 ? k_measure<P_, 1> : KM <= 2 ? k_measure<P_, 2> : KM <= 4 ? k_measure<P_, 4> : KM <= 8 ? k_measure<P_, 8> : k_measure<P_, 0>)
+                    mfn k_me = pk == PIMC_POT_ZERO ? PICK_MEAS(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_MEAS(PIMC_POT_HARMONIC) : PICK_MEAS(PIMC_POT_LATTICE));
+#undef PICK_MEAS
+                    k_me<<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
                     LAUNCHED(); launches++;
                 }
             }

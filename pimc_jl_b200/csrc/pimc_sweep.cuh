@@ -572,15 +572,63 @@ __device__ __forceinline__ void d_energy_block_fast(const DevSys &S, int c, doub
         *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
     }
 }
-template <int POT>
-__global__ void __launch_bounds__(256) k_measure(DevSys S, const DevTables *__restrict__ T, MeasParams P)
+// register-resident variant for M <= 32*KM: all of a worldline's loads are issued before any arithmetic, the next bead comes
+// from the neighbouring lane by shuffle
+template <int POT, int KM>
+__device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, double *red, double *E, double *Ev)
+{
+    const int M = S.M, N = S.N, dim = S.dim, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double twoL = 2 * S.L;
+    const double *rc = S.r + (size_t)c * N * dim * M;
+    const int *nextc = S.next + (size_t)c * N;
+    double link = 0.0, pot = 0.0, vkin = 0.0;
+    for (int n = warp; n < N; n += nw) {
+        const double *rx = rc + (size_t)(n * dim) * M, *ry = rx + M;
+        const int nx = nextc[n];
+        double x[KM], y[KM];
+#pragma unroll
+        for (int k = 0; k < KM; ++k) { const int j = lane + 32 * k; x[k] = j < M ? rx[j] : 0.0; y[k] = (dim > 1 && j < M) ? ry[j] : 0.0; }
+        const double *qx = rc + (size_t)(nx * dim) * M;
+        const double x0n = qx[0], y0n = dim > 1 ? qx[M] : 0.0;      // first bead of the next particle of the cycle
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+            const int j = lane + 32 * k;
+            double bx = __shfl_down_sync(0xffffffffu, x[k], 1), by = __shfl_down_sync(0xffffffffu, y[k], 1);
+            const double nbx = __shfl_sync(0xffffffffu, x[(k + 1 < KM) ? k + 1 : k], 0), nby = __shfl_sync(0xffffffffu, y[(k + 1 < KM) ? k + 1 : k], 0);
+            if (lane == 31) { bx = nbx; by = nby; }
+            if (j == M - 1) { bx = x0n; by = y0n; }
+            if (j < M) {
+                const double ax = x[k], ay = y[k];
+                double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
+                double d2 = dx * dx;
+                if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
+                link += d2;
+                if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
+                vkin += d_rdv(S.pot, ax, ay, dim);
+            }
+        }
+    }
+    link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
+    __syncthreads();
+    if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        link = 0.0; pot = 0.0; vkin = 0.0;
+        for (int i = 0; i < nw; ++i) { link += red[i]; pot += red[32 + i]; vkin += red[64 + i]; }
+        *E = (double)(S.dim * S.N) / (2 * S.tau) - 1 / (4 * S.lambda * (S.tau * S.tau) * S.M) * link + 1.0 / (2 * S.M) * pot;
+        *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
+    }
+}
+template <int POT, int KM>
+__global__ void __launch_bounds__(256, 4) k_measure(DevSys S, const DevTables *__restrict__ T, MeasParams P)
 {
     __shared__ double red[96];
     const int c = blockIdx.x;
     for (int e = 0; e < P.nen; ++e) {
         const EnDev &En = T->en[P.en_id[e]];
         double E, Ev;
-        d_energy_block_fast<POT>(S, c, red, &E, &Ev);
+        if (KM > 0) d_energy_block_reg<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev);
+        else d_energy_block_fast<POT>(S, c, red, &E, &Ev);
         if (threadIdx.x == 0) {
             if (P.k < En.cap) { En.E[(size_t)P.k * S.C + c] = E; En.Ev[(size_t)P.k * S.C + c] = Ev; }
             double *a = En.acc + (size_t)c * 5;

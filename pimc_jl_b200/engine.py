@@ -177,6 +177,14 @@ class Engine:
         self._ck(self.lib.pimc_energy_read(self.h, eid, chain, _p(E), _p(Ev), m, C.byref(n)))
         return E[:m], Ev[:m], n.value
 
+    def energy_read_range(self, eid, start, count, chain=-1):
+        """measurement block [start, start+count): returns (E, Ev, total measurements taken)"""
+        n = C.c_int64()
+        E, Ev = np.zeros(max(count, 1)), np.zeros(max(count, 1))
+        self._ck(self.lib.pimc_energy_read_range(self.h, eid, chain, start, count, _p(E), _p(Ev), C.byref(n)))
+        m = max(0, min(count, n.value - start))
+        return E[:m], Ev[:m], n.value
+
     def energy_stats(self, eid):
         out = np.zeros((self.C, 5))
         self._ck(self.lib.pimc_energy_stats(self.h, eid, _p(out)))
