@@ -320,3 +320,43 @@ def test_interacting_faithful_cell_list(oracle, compat):
     assert any(not np.array_equal(nxt[c], np.arange(1, cfg["N"] + 1)) for c in range(2)) or True
     with pytest.raises(pj.PimcError):
         e.run(10, ge, sched=L.SCHED_SWEEP)
+
+
+@pytest.mark.parametrize("impl", [1, 2], ids=["sweep-persistent", "sweep-batched"])
+@pytest.mark.parametrize("cfg,rng_,n_it", [
+    (dict(pot="zero", dim=2, M=33, N=300, L=5.0, T=1.0, lam=1.0, Ncycle=3), 10000, 14),      # two super-batches, ragged M (KM = 2)
+    (dict(pot="harmonic", dim=2, M=200, N=5, L=6.0, T=0.25, lam=0.5, Ncycle=2), 10000, 30),   # KM = 8 register tiles
+    (dict(pot="harmonic", dim=2, M=12, N=9, L=4.0, T=1.0, lam=0.5, Ncycle=2), 70, 120),       # acceptance window wraps / evicts (ballot path)
+    (dict(pot="harmonic", dim=2, M=12, N=9, L=4.0, T=1.0, lam=0.5, Ncycle=2), 33, 60),        # tiny window: serial fallback
+    (dict(pot="sin2", dim=1, M=64, N=40, L=4.0, T=1.0, lam=1.0, Ncycle=5), 200, 40),          # 1-D, window wrap
+], ids=["N300-M33", "N5-M200", "window70", "window33", "1d-window200"])
+def test_sweep_edge_cases_bit_exact(oracle, cfg, rng_, n_it, impl):
+    """ragged sizes, several super-batches, register-tile variants and acceptance-window wrap-around, both sweep implementations"""
+    ob = oracle
+    e, os_ = make_pair(ob, cfg, chains=2, seed=99)
+    e.set_option(L.OPT_SWEEP_IMPL, impl)
+    spec = [(1, L.UPD_SINGLE_COM, 0.8), (1, L.UPD_RESHAPE_LINEAR, 7), (4, L.UPD_POLYMER_COM, 0.4)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    for (_, uid), k in zip(ge, range(len(spec))):
+        lim = (2, cfg["M"] - 2, 0.6, 0.8) if spec[k][1] == L.UPD_RESHAPE_LINEAR else (0.1, cfg["L"] / 2, 0.4, 0.6)
+        e.update_configure(uid, *lim, adj=10, rng=rng_)
+        for c in range(2):
+            oo[c][k][1].configure(*lim, adj=10, rng=rng_)
+    en_id = e.energy_create(200)
+    oen = [ob.Energy(200) for _ in os_]
+    e.run(n_it, ge, energies=[en_id], sched=L.SCHED_SWEEP)
+    for s, ups, en in zip(os_, oo, oen):
+        s.run(n_it, ups, energies=[en], sched=L.SCHED_SWEEP)
+    _sync_paths(e, os_, cfg["pot"] in ("zero", "harmonic"))
+    for (_, uid), k in zip(ge, range(len(spec))):
+        for c in range(2):
+            g, o = e.update_get(uid, c), oo[c][k][1].get()
+            assert (g["tries"], g["tries_var"], g["accepted"], g["bead_moves"], g["var"]) == (o["tries"], o["tries_var"], o["accepted"], o["bead_moves"], o["var"]), (k, c, g, o)
+            assert (np.isnan(g["acc_window"]) and np.isnan(o["acc_window"])) or g["acc_window"] == o["acc_window"], (k, c, g, o)
+    scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+    for c in range(2):
+        E, Ev, n = e.energy_read(en_id, c)
+        Eo, Evo = oen[c].read()
+        assert n == len(Eo) and np.all(np.abs(E - Eo) <= 1e-12 * scale)
+    Eb, Evb, n = e.energy_read_range(en_id, 1, 2)
+    assert len(Eb) == min(2, max(0, n - 1)) and np.array_equal(Eb, e.energy_read(en_id, -1)[0][1:3])
