@@ -522,10 +522,6 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     S.ncell = cfg->dim == 2 ? S.nbins * S.nbins : S.nbins;
     S.cellw = 2 * cfg->L / S.nbins;
     S.need_cells = (S.a > 0.0 || cfg->interactions) ? 1 : 0;
-    if (cfg->interactions && !(cfg->compat & PIMC_COMPAT_PAIR_BYVALUE)) {
-        snprintf(g_err, sizeof g_err, "intended-mode pair action inside ReshapeLinear / centre-of-mass moves is not built yet: keep PIMC_COMPAT_PAIR_BYVALUE set");
-        pimc_destroy(h); return PIMC_ERR_UNSUPPORTED;
-    }
     size_t nb = (size_t)S.C * S.N * S.M;
     RCC(dalloc(h, &S.r, nb * S.dim)); RCC(dalloc(h, &S.Vl, nb)); RCC(dalloc(h, &S.next, (size_t)S.C * S.N));
     RCC(dalloc(h, &S.prop, nb * S.dim)); RCC(dalloc(h, &S.propV, nb)); RCC(dalloc(h, &S.wtab, (size_t)S.C * S.N));

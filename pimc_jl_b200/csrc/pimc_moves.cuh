@@ -9,51 +9,8 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// ---- ReshapeLinear body (reshape.jl:56-87), one thread.  n 0-based, j0 1-based, scratch slot `slot`.
-// returns 1 accepted, 0 rejected, -1 bridge failed
-__device__ __forceinline__ int d_reshape_linear(const DevSys &S, int c, int n, int j0, int m, const GSrc &g, double u, int commit,
-                                                int slot, double *wi_out, double *wu_out)
-{
-    const int M = S.M, dim = S.dim;
-    const int jm = j0 + m, rows = m + 1;
-    const int nx = S.next[(size_t)c * S.N + n];
-    // pcycle (helper.jl:113-115) for j0 <= j <= jm < 2M: slices beyond M belong to the next particle of the cycle
-    const int pe = jm <= M ? n : nx, je = (jm <= M ? jm : jm - M) - 1;
-    double bx = S.r[RIDX(S, c, n, 0, j0 - 1)], by = dim > 1 ? S.r[RIDX(S, c, n, 1, j0 - 1)] : 0.0;
-    double ex = S.r[RIDX(S, c, pe, 0, je)], ey = dim > 1 ? S.r[RIDX(S, c, pe, 1, je)] : 0.0;
-    double *px = S.prop + RIDX(S, c, slot, 0, 0), *py = px + M, *pv = S.propV + VIDX(S, c, slot, 0);
-    double w_initial = 0.0, w_updated = 0.0;
-    int ret = -1;
-    if (d_bridge(S, c, bx, by, ex, ey, rows, j0, n, g, px, py, pv)) {
-        const double mht = -0.5 * S.tau;
-        double sv = 0.0;
-        for (int jp = 1; jp <= m; ++jp) {
-            int j = j0 + jp - 1;
-            int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
-            w_initial += S.Vl[VIDX(S, c, p, sl)];
-            double vl = mht * (pv[jp - 1] + pv[jp]); // lnV (propagator.jl:26-28)
-            pv[jp - 1] = vl;
-            sv = jp == 1 ? vl : sv + vl;
-        }
-        w_updated += sv;
-        ret = d_metropolis(pimc_exp(w_updated - w_initial), u) ? 1 : 0;
-        if (ret == 1 && commit) {
-            for (int jp = 1; jp <= m; ++jp) {
-                int j = j0 + jp - 1;
-                int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
-                S.r[RIDX(S, c, p, 0, sl)] = px[jp - 1];
-                if (dim > 1) S.r[RIDX(S, c, p, 1, sl)] = py[jp - 1];
-                S.Vl[VIDX(S, c, p, sl)] = pv[jp - 1];
-                d_cell_update(S, c, sl, p, px[jp - 1], dim > 1 ? py[jp - 1] : 0.0);
-            }
-        }
-    }
-    if (wi_out) *wi_out = w_initial;
-    if (wu_out) *wu_out = w_updated;
-    return ret;
-}
-
-// pair-action pieces of ReshapeSwapLinear (reshape.jl:166-199 old configuration, :209-240 new configuration)
+// pair action: interaction_action! (helper.jl:306-366) and the inlined copies of ReshapeSwapLinear (reshape.jl:166-199 old
+// configuration, :209-240 new configuration)
 __device__ __forceinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl)
 {
     // find_nns(s, p, sl, exceptions=[p]) with the STORED bin of p, then lnU of (bead, next bead) distances
@@ -96,6 +53,54 @@ __device__ __forceinline__ double d_pairs_new(const DevSys &S, int c, double x, 
             for (int rep = S.mult[VIDX(S, c, o, sl)]; rep > 0; --rep) w += lu;
         }
     return w;
+}
+
+// ---- ReshapeLinear body (reshape.jl:56-87), one thread.  n 0-based, j0 1-based, scratch slot `slot`.
+// returns 1 accepted, 0 rejected, -1 bridge failed
+__device__ __forceinline__ int d_reshape_linear(const DevSys &S, int c, int n, int j0, int m, const GSrc &g, double u, int commit,
+                                                int slot, double *wi_out, double *wu_out)
+{
+    const int M = S.M, dim = S.dim;
+    const int jm = j0 + m, rows = m + 1;
+    const int nx = S.next[(size_t)c * S.N + n];
+    // pcycle (helper.jl:113-115) for j0 <= j <= jm < 2M: slices beyond M belong to the next particle of the cycle
+    const int pe = jm <= M ? n : nx, je = (jm <= M ? jm : jm - M) - 1;
+    double bx = S.r[RIDX(S, c, n, 0, j0 - 1)], by = dim > 1 ? S.r[RIDX(S, c, n, 1, j0 - 1)] : 0.0;
+    double ex = S.r[RIDX(S, c, pe, 0, je)], ey = dim > 1 ? S.r[RIDX(S, c, pe, 1, je)] : 0.0;
+    double *px = S.prop + RIDX(S, c, slot, 0, 0), *py = px + M, *pv = S.propV + VIDX(S, c, slot, 0);
+    double w_initial = 0.0, w_updated = 0.0;
+    int ret = -1;
+    if (d_bridge(S, c, bx, by, ex, ey, rows, j0, n, g, px, py, pv)) {
+        const double mht = -0.5 * S.tau;
+        double sv = 0.0;
+        for (int jp = 1; jp <= m; ++jp) {
+            int j = j0 + jp - 1;
+            int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
+            w_initial += S.Vl[VIDX(S, c, p, sl)];
+            if (S.interactions && !(S.compat & PIMC_COMPAT_PAIR_BYVALUE)) { // intended mode: interaction_action! does count (reshape.jl:72,75)
+                w_initial += d_pairs_old(S, c, p, sl);
+                w_updated += d_pairs_new(S, c, px[jp - 1], dim > 1 ? py[jp - 1] : 0.0, px[jp], dim > 1 ? py[jp] : 0.0, sl, p, -1, true);
+            }
+            double vl = mht * (pv[jp - 1] + pv[jp]); // lnV (propagator.jl:26-28)
+            pv[jp - 1] = vl;
+            sv = jp == 1 ? vl : sv + vl;
+        }
+        w_updated += sv;
+        ret = d_metropolis(pimc_exp(w_updated - w_initial), u) ? 1 : 0;
+        if (ret == 1 && commit) {
+            for (int jp = 1; jp <= m; ++jp) {
+                int j = j0 + jp - 1;
+                int p = j <= M ? n : nx, sl = (j <= M ? j : j - M) - 1;
+                S.r[RIDX(S, c, p, 0, sl)] = px[jp - 1];
+                if (dim > 1) S.r[RIDX(S, c, p, 1, sl)] = py[jp - 1];
+                S.Vl[VIDX(S, c, p, sl)] = pv[jp - 1];
+                d_cell_update(S, c, sl, p, px[jp - 1], dim > 1 ? py[jp - 1] : 0.0);
+            }
+        }
+    }
+    if (wi_out) *wi_out = w_initial;
+    if (wu_out) *wu_out = w_updated;
+    return ret;
 }
 
 // sampleparticles weight table (helper.jl:230-260), one thread, w[N]
@@ -228,7 +233,10 @@ __device__ __forceinline__ int d_com_warp(const DevSys &S, int c, int n, double 
     // w_initial: cached links of every member of the cycle
     double w_initial = 0.0; int npol = 0;
     { int p = n; do { double part = 0.0;
-            for (int j = lane; j < M; j += 32) part += S.Vl[VIDX(S, c, p, j)];
+            for (int j = lane; j < M; j += 32) {
+                part += S.Vl[VIDX(S, c, p, j)];
+                if (S.interactions && !(S.compat & PIMC_COMPAT_PAIR_BYVALUE)) part += d_pairs_old(S, c, p, j); // com.jl:54,173 (intended)
+            }
             w_initial += warp_sum(part); npol += 1; p = nextc[p]; } while (p != n && npol <= N); }
     double dx = 0.0, dy = 0.0; bool ok = false;
     for (long long ctr = 1; ctr <= S.ctr; ++ctr) {
@@ -260,6 +268,7 @@ __device__ __forceinline__ int d_com_warp(const DevSys &S, int c, int n, double 
                 double x = d_teleport(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? d_teleport(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
                 double xn = d_teleport(S.r[RIDX(S, c, q, 0, jn)] + dx, S.L), yn = dim > 1 ? d_teleport(S.r[RIDX(S, c, q, 1, jn)] + dy, S.L) : 0.0;
                 part += mht * (d_pot(S.pot, x, y, dim) + d_pot(S.pot, xn, yn, dim));
+                if (S.interactions && !(S.compat & PIMC_COMPAT_PAIR_BYVALUE)) part += d_pairs_new(S, c, x, y, xn, yn, j, p, -1, false); // com.jl:79,198
             }
             p = pn; cnt++; } while (p != n && cnt <= N);
         w_updated += warp_sum(part);

@@ -287,7 +287,7 @@ def synthetic_table(n=64, hi=12.0):
     return -0.004 * np.exp(-0.5 * (X + Y)) * (1 + 0.3 * np.cos(X - Y)), 1e-3, hi
 
 
-@pytest.mark.parametrize("compat", [L.COMPAT_ALL, L.COMPAT_PAIR_BYVALUE | L.COMPAT_DENSITY_SHIFT])
+@pytest.mark.parametrize("compat", [L.COMPAT_ALL, L.COMPAT_PAIR_BYVALUE | L.COMPAT_DENSITY_SHIFT, 0], ids=["as-shipped", "swap-fixes", "intended"])
 def test_interacting_faithful_cell_list(oracle, compat):
     """Hard core a > 0, pair action through the lnU table, cell list queries: faithful schedule against the oracle."""
     ob = oracle
@@ -317,7 +317,15 @@ def test_interacting_faithful_cell_list(oracle, compat):
     for c, s in enumerate(os_):
         ro, Vo, bo, no = s.paths()
         assert np.array_equal(nxt[c], no) and np.array_equal(r[c], ro) and np.array_equal(V[c], Vo) and np.array_equal(bins[c], bo)
-    assert any(not np.array_equal(nxt[c], np.arange(1, cfg["N"] + 1)) for c in range(2)) or True
+    # explicit Delta-U hooks on the interacting configuration (pair sums through the cell list vs the oracle's lists)
+    for t in range(12):
+        c = t % 2
+        n = int(rng.integers(1, cfg["N"] + 1)); j0 = int(rng.integers(1, cfg["M"] + 1)); m = int(rng.integers(2, cfg["M"] - 1)); u = float(rng.uniform())
+        xi = 0.05 * rng.standard_normal((m - 1, 2))
+        wi, wu = C.c_double(), C.c_double()
+        acc_o = ob.lib().ora_reshape_linear_explicit(os_[c].h, n, j0, m, ob._p(xi), u, 0, C.byref(wi), C.byref(wu), None)
+        acc, gwi, gwu, _ = e.reshape_linear_explicit(c, n, j0, m, xi, u, commit=False)
+        assert acc == acc_o and close(gwi, wi.value, 1e-11, 1e-12) and close(gwu, wu.value, 1e-11, 1e-12), (t, gwi, wi.value, gwu, wu.value)
     with pytest.raises(pj.PimcError):
         e.run(10, ge, sched=L.SCHED_SWEEP)
 
