@@ -1021,7 +1021,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         SweepParams SP; memset(&SP, 0, sizeof SP);
-        SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS;
+        SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS; const char *padenv = getenv("PIMC_EXP_SMEM_PAD"); const size_t smem_pad = padenv ? (size_t)atol(padenv) : 0;
         pimc_roundkeys_make(S.seed, &SP.rk);
         for (int i = 0; i < nupd; ++i) { SP.kind[i] = h->T.upd[update_ids[i]].kind; SP.vmax[i] = h->T.upd[update_ids[i]].vmax; }
         CK(h, cudaMemcpyAsync(h->dS, &S, sizeof(DevSys), cudaMemcpyHostToDevice, h->stream));
@@ -1032,7 +1032,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, smem_rs > smem_cs ? smem_rs : smem_cs, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;

@@ -116,20 +116,64 @@ __device__ __forceinline__ void d_ring_write_seg(unsigned *ring, int pos, int n,
 }
 // per-chain counters of one update object, fetched at the START of a sweep kernel (thread 0) so that the global-memory
 // latency is hidden behind the moves instead of sitting on the CTA's tail
-struct BookPre { int head, len, sum; long long tries, tr, ac; double var; long long range, adj; };
+#define BOOK_PW 6
+struct BookPre { int head, len, sum; long long tries, tr, ac; double var; long long range, adj; int tw0, hw0; unsigned tw[BOOK_PW], hw[BOOK_PW]; };
 __device__ __forceinline__ BookPre d_book_prefetch(const UpdDev &U, int c)
 {
     BookPre b; b.head = U.ring_head[c]; b.len = U.ring_len[c]; b.sum = U.ring_sum[c]; b.tries = U.tries_var[c];
     b.tr = U.tries[c]; b.ac = U.accepted[c]; b.var = U.var[c]; b.range = U.range; b.adj = U.adj;
+    // the ring words this sweep can touch: BOOK_PW words from the tail (appends) and from the head (evictions)
+    const unsigned *ring = U.ring + (size_t)c * U.ring_words;
+    const int cap = (int)b.range + 1;
+    int tail = b.head + b.len; if (tail >= cap) tail -= cap;
+    b.tw0 = tail >> 5; b.hw0 = b.head >> 5;
+    for (int i = 0; i < BOOK_PW; ++i) {
+        int wt = b.tw0 + i; if (wt >= U.ring_words) wt -= U.ring_words;
+        int wh = b.hw0 + i; if (wh >= U.ring_words) wh -= U.ring_words;
+        b.tw[i] = ring[wt]; b.hw[i] = ring[wh];
+    }
     return b;
 }
+// ring word `w` through the prefetched windows (tail window wins: it holds this sweep's own appends)
+struct RingCache {
+    unsigned *ring; int words; BookPre *pre;
+    __device__ __forceinline__ int slot(int w, int w0) const { int d = w - w0; if (d < 0) d += words; return d; }
+    __device__ __forceinline__ unsigned get(int w) const {
+        int d = slot(w, pre->tw0); if (d < BOOK_PW) return pre->tw[d];
+        d = slot(w, pre->hw0); if (d < BOOK_PW) return pre->hw[d];
+        return ring[w];
+    }
+    __device__ __forceinline__ void put(int w, unsigned v) {
+        int d = slot(w, pre->tw0); if (d < BOOK_PW) pre->tw[d] = v;
+        d = slot(w, pre->hw0); if (d < BOOK_PW) pre->hw[d] = v;
+        ring[w] = v;
+    }
+};
+__device__ __forceinline__ unsigned d_ringc_read_bits(const RingCache &rc, int cap, int pos, int n)
+{
+    const int n1 = n < cap - pos ? n : cap - pos;
+    const int w = pos >> 5, o = pos & 31;
+    unsigned long long two = (unsigned long long)rc.get(w);
+    if (o + n1 > 32) two |= (unsigned long long)rc.get(w + 1) << 32;
+    unsigned out = (unsigned)((two >> o) & ((n1 >= 32) ? 0xFFFFFFFFull : ((1ull << n1) - 1ull)));
+    if (n1 < n) out |= (rc.get(0) & ((1u << (n - n1)) - 1u)) << n1;
+    return out;
+}
+__device__ __forceinline__ void d_ringc_write_seg(RingCache &rc, int pos, int n, unsigned bits)
+{
+    const int w = pos >> 5, o = pos & 31;
+    const unsigned long long m = ((n >= 32) ? 0xFFFFFFFFull : ((1ull << n) - 1ull)) << o;
+    const unsigned long long v = ((unsigned long long)bits << o) & m;
+    rc.put(w, (rc.get(w) & ~(unsigned)m) | (unsigned)v);
+    if (o + n > 32) rc.put(w + 1, (rc.get(w + 1) & ~(unsigned)(m >> 32)) | (unsigned)(v >> 32));
+}
 __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, const unsigned char *flag, int ntask, unsigned long long beads,
-                                                      unsigned long long *stats, const BookPre &pre)
+                                                      unsigned long long *stats, BookPre &pre)
 {
     const int lane = threadIdx.x & 31;
     const long long range_ll = pre.range;
     if (range_ll < 64) { if (lane == 0) d_bookkeep_sweep(U, c, flag, ntask, beads, stats); return; }
-    unsigned *ring = U.ring + (size_t)c * U.ring_words;
+    RingCache rcache; rcache.ring = U.ring + (size_t)c * U.ring_words; rcache.words = U.ring_words; rcache.pre = &pre;
     const int cap = (int)range_ll + 1, range = (int)range_ll;
     int head = pre.head, len = pre.len, sum = pre.sum;
     long long tries = pre.tries;
@@ -150,11 +194,11 @@ __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, co
             const unsigned bits = (accb >> lo) & ((k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u));
             todo &= (k + lo >= 32) ? 0u : ~((1u << (k + lo)) - 1u);
             const int e = len + k - range;
-            if (e > 0) { sum -= __popc(d_ring_read_bits(ring, cap, head, e)); head += e; if (head >= cap) head -= cap; len -= e; }
+            if (e > 0) { sum -= __popc(d_ringc_read_bits(rcache, cap, head, e)); head += e; if (head >= cap) head -= cap; len -= e; }
             int tail = head + len; if (tail >= cap) tail -= cap;
             const int k1 = k < cap - tail ? k : cap - tail;
-            d_ring_write_seg(ring, tail, k1, bits);
-            if (k1 < k) d_ring_write_seg(ring, 0, k - k1, bits >> k1);
+            d_ringc_write_seg(rcache, tail, k1, bits);
+            if (k1 < k) d_ringc_write_seg(rcache, 0, k - k1, bits >> k1);
             len += k; sum += __popc(bits); tries += k; ac += __popc(bits);
         }
     }
@@ -312,39 +356,48 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
             __syncthreads();
             TICK(3);
             // ---- phase D: Delta-U from shared memory, Metropolis, coalesced commit -- one warp per task ----
-            for (int q = warp; q < TB; q += SWEEP_THREADS / 32) {
-                const int nq = sb0 + b0 + q, mq = t_m[q], base = t_off[q], nxq = nextc[nq];
-                double wi = 0.0, wu = 0.0;
-                for (int jp = lane; jp < mq; jp += 32) {
-                    wi += vo[base + jp];
-                    wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
-                }
-                wi = 0.0 + warp_sum(wi); wu = 0.0 + warp_sum(wu);
-                int acc = 0;
-                if (lane == 0) {
-                    const double dw = wu - wi;     // exp(dw) >= 1 for dw >= 0: accepted without the exponential or the uniform
-                    if (dw >= 0.0) acc = 1;
-                    else {
-                        const double delta = pimc_exp(dw);
-                        if (delta >= 1.0) acc = 1;
-                        else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)nq, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+            {   // half a warp per task: twice as many tasks in flight per phase, 4-step shuffle reductions
+                const int hl = lane & 15, hq = tid >> 4;
+                const unsigned hmask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+                for (int q = hq; q < ((TB + 1) & ~1); q += SWEEP_THREADS / 16) {   // both halves of a warp iterate together
+                    const bool live = q < TB;
+                    const int qq = live ? q : TB - 1;
+                    const int nq = sb0 + b0 + qq, mq = live ? t_m[qq] : 0, base = t_off[qq], nxq = nextc[nq];
+                    double wi = 0.0, wu = 0.0;
+                    for (int jp = hl; jp < mq; jp += 16) {
+                        wi += vo[base + jp];
+                        wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
                     }
-                    flag[nq] = (unsigned char)acc;
-                }
-                acc = __shfl_sync(0xffffffffu, acc, 0);
-                if (acc) {
-                    const int n1 = mq < nfirst ? mq : nfirst;                 // rows 0..n1-1 on particle nq, the rest wrapped on nxq
-                    double *x1 = rc + (nq * dim) * M + first, *x2 = rc + (nxq * dim) * M - nfirst;
-                    double *w1 = vc + nq * M + first, *w2 = vc + nxq * M - nfirst;
-                    for (int jp = lane; jp < n1; jp += 32) {
-                        x1[jp] = xs[base + jp];
-                        if (dim > 1) x1[M + jp] = ys[base + jp];
-                        w1[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) { wi += __shfl_xor_sync(0xffffffffu, wi, o); wu += __shfl_xor_sync(0xffffffffu, wu, o); }
+                    wi = 0.0 + wi; wu = 0.0 + wu;
+                    int acc = 0;
+                    if (hl == 0 && live) {
+                        const double dw = wu - wi;     // exp(dw) >= 1 for dw >= 0: accepted without the exponential or the uniform
+                        if (dw >= 0.0) acc = 1;
+                        else {
+                            const double delta = pimc_exp(dw);
+                            if (delta >= 1.0) acc = 1;
+                            else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)nq, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+                        }
+                        flag[nq] = (unsigned char)acc;
                     }
-                    for (int jp = nfirst + lane; jp < mq; jp += 32) {
-                        x2[jp] = xs[base + jp];
-                        if (dim > 1) x2[M + jp] = ys[base + jp];
-                        w2[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                    acc = __shfl_sync(0xffffffffu, acc, lane & 16);
+                    (void)hmask;
+                    if (acc) {
+                        const int n1 = mq < nfirst ? mq : nfirst;                 // rows 0..n1-1 on particle nq, the rest wrapped on nxq
+                        double *x1 = rc + (nq * dim) * M + first, *x2 = rc + (nxq * dim) * M - nfirst;
+                        double *w1 = vc + nq * M + first, *w2 = vc + nxq * M - nfirst;
+                        for (int jp = hl; jp < n1; jp += 16) {
+                            x1[jp] = xs[base + jp];
+                            if (dim > 1) x1[M + jp] = ys[base + jp];
+                            w1[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                        }
+                        for (int jp = nfirst + hl; jp < mq; jp += 16) {
+                            x2[jp] = xs[base + jp];
+                            if (dim > 1) x2[M + jp] = ys[base + jp];
+                            w2[jp] = (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
+                        }
                     }
                 }
             }
