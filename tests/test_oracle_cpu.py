@@ -303,3 +303,103 @@ def test_sweep_equals_sequential_definition(oracle):
     with pytest.raises(RuntimeError):
         s2 = ob.System(ob.make_potential("zero"), dim=2, M=8, N=3, L=4.0, interactions=True, g=1.5, r_a=1.0)
         s2.run(1, [(1, ob.Update(s2, ob.UPD_RESHAPE_LINEAR, 3))], sched=ob.SCHED_SWEEP)
+
+
+# ---------- second opinions for the move functors (numpy, written from src/updates/*.jl) ----------
+def _lnV_py(a, b, tau, V):
+    return -0.5 * tau * (V(a) + V(b))
+
+
+def _harm(r):
+    return 0.5 * float(np.sum(np.asarray(r) ** 2))
+
+
+def test_reshape_linear_delta_u_against_numpy(oracle):
+    """ReshapeLinear (src/updates/reshape.jl:56-87): proposal = levy bridge between the fixed beads, w_initial = cached links,
+    w_updated = lnV of the proposed links, commit writes rows 1..m and the m link-cache entries (incl. wrap to the next particle)."""
+    ob = oracle
+    rng = np.random.default_rng(11)
+    M, N, L, lam = 9, 3, 3.0, 0.5
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=L, T=0.7, lam=lam, seed=21)
+    r0 = rng.uniform(-L, L, (N, 2, M))
+    s.set_paths(r0, np.array([2, 3, 1], dtype=np.int64))       # one 3-cycle: segments may wrap onto the next particle
+    nxt = [2, 3, 1]
+    for trial in range(60):
+        r, V, _, _ = s.paths()
+        n, j0, m = int(rng.integers(1, N + 1)), int(rng.integers(1, M + 1)), int(rng.integers(2, M - 1))
+        xi = rng.standard_normal((m - 1, 2))
+        u = float(rng.uniform())
+        own = lambda j: (n if j <= M else nxt[n - 1], (j - 1) % M)            # (particle, 0-based slice) of unwrapped slice j
+        rp = np.zeros((m + 1, 2))
+        rp[0] = r[n - 1, :, j0 - 1]
+        pe, je = own(j0 + m)
+        rp[-1] = r[pe - 1, :, je]
+        bridge = levy_py(rp, s.tau, L, lam, xi)
+        w_i = sum(V[own(j)[0] - 1, own(j)[1]] for j in range(j0, j0 + m))
+        Vp = [_lnV_py(bridge[k], bridge[k + 1], s.tau, _harm) for k in range(m)]
+        w_u = sum(Vp)
+        acc_py = (math.exp(w_u - w_i) >= 1.0) or (math.exp(w_u - w_i) > u)
+        wi, wu = C.c_double(), C.c_double()
+        rpo = np.zeros((2, m + 1))
+        acc = ob.lib().ora_reshape_linear_explicit(s.h, n, j0, m, ob._p(xi), u, 1, C.byref(wi), C.byref(wu), ob._p(rpo))
+        assert np.array_equal(rpo.T, bridge)
+        assert abs(wi.value - w_i) <= 1e-12 * max(1, abs(w_i)) and abs(wu.value - w_u) <= 1e-12 * max(1, abs(w_u))
+        assert bool(acc) == acc_py
+        r2, V2, _, _ = s.paths()
+        exp_r, exp_V = r.copy(), V.copy()
+        if acc:
+            for k in range(m):
+                p, sl = own(j0 + k)
+                exp_r[p - 1, :, sl] = bridge[k]
+                exp_V[p - 1, sl] = Vp[k]
+        assert np.array_equal(r2, exp_r) and np.allclose(V2, exp_V, rtol=1e-14, atol=0)
+
+
+def test_com_delta_u_against_numpy(oracle):
+    """Single/PolymerCenterOfMass (src/updates/com.jl:47-100,168-220): every bead of the cycle shifted by d and wrapped."""
+    ob = oracle
+    rng = np.random.default_rng(12)
+    M, N, L = 7, 4, 3.0
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=L, T=1.0, lam=0.5, seed=3)
+    s.set_paths(rng.uniform(-L, L, (N, 2, M)), np.array([2, 1, 3, 4], dtype=np.int64))
+    cycles = {1: [1, 2], 2: [2, 1], 3: [3], 4: [4]}
+    nxt = [2, 1, 3, 4]
+    for trial in range(40):
+        r, V, _, _ = s.paths()
+        n = int(rng.integers(1, N + 1))
+        d = rng.uniform(-1.5, 1.5, 2)
+        u = float(rng.uniform())
+        pol = cycles[n]
+        newr = {p: np.array([[teleport_py(r[p - 1, k, j] + d[k], L) for k in range(2)] for j in range(M)]) for p in pol}
+        w_i = sum(V[p - 1].sum() for p in pol)
+        Vp = {p: [_lnV_py(newr[p][j], newr[p][j + 1] if j < M - 1 else newr[nxt[p - 1]][0], s.tau, _harm) for j in range(M)] for p in pol}
+        w_u = sum(sum(Vp[p]) for p in pol)
+        wi, wu = C.c_double(), C.c_double()
+        acc = ob.lib().ora_com_explicit(s.h, n, 1, ob._p(d.copy()), u, 1, C.byref(wi), C.byref(wu))
+        assert abs(wi.value - w_i) <= 1e-12 * max(1, abs(w_i)) and abs(wu.value - w_u) <= 1e-12 * max(1, abs(w_u))
+        assert bool(acc) == ((math.exp(w_u - w_i) >= 1.0) or (math.exp(w_u - w_i) > u))
+        r2, V2, _, _ = s.paths()
+        if acc:
+            for p in pol:
+                assert np.array_equal(r2[p - 1].T, newr[p]) and np.allclose(V2[p - 1], Vp[p], rtol=1e-14, atol=0)
+        else:
+            assert np.array_equal(r2, r)
+
+
+def test_swap_weights_against_numpy(oracle):
+    """sampleparticles (src/updates/helper.jl:224-267): table exp(lnK(n1 -> end_i) + lnK(i -> end_n1)) over all i."""
+    ob = oracle
+    rng = np.random.default_rng(13)
+    M, N, L, lam = 8, 5, 3.0, 0.7
+    s = ob.System(ob.make_potential("zero"), dim=2, M=M, N=N, L=L, T=0.9, lam=lam, seed=8)
+    r = rng.uniform(-L, L, (N, 2, M))
+    nxt = np.array([2, 3, 1, 5, 4], dtype=np.int64)
+    s.set_paths(r, nxt)
+    for n1, j0, m in [(1, 2, 3), (4, 7, 4), (3, 8, 2), (5, 5, 6)]:
+        w = np.zeros(N)
+        ob.lib().ora_swap_weights(s.h, n1, j0, m, ob._p(w))
+        jm = (j0 + m - 1) % M
+        endp = lambda i: (nxt[i - 1] if j0 + m > M else i)
+        lnk = lambda a, b: -sum(distance_py(a[k], b[k], L) ** 2 for k in range(2)) / (4 * (m * s.tau) * lam)
+        ref = [math.exp(lnk(r[n1 - 1, :, j0 - 1], r[endp(i) - 1, :, jm]) + lnk(r[i - 1, :, j0 - 1], r[endp(n1) - 1, :, jm])) for i in range(1, N + 1)]
+        assert np.allclose(w, ref, rtol=1e-13, atol=0)
