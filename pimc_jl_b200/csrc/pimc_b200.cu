@@ -1004,8 +1004,11 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
     const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 3 : 4) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 16;
-    const size_t smem_cs = (size_t)S.N + 16;
-    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 48 * 1024;
+    // COM half: flags, then (TMA path, even M) two mbarriers per warp and two stages of (dim + 1) rows per warp
+    const size_t com_flag = (((size_t)S.N + 127) & ~(size_t)127);
+    const bool com_tma = (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr;
+    const size_t smem_cs = com_flag + (com_tma ? 128 + (size_t)(SWEEP_THREADS / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
+    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
     if (h->opt_sweep_impl == 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
@@ -1023,6 +1026,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         SweepParams SP; memset(&SP, 0, sizeof SP);
         SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS; const char *padenv = getenv("PIMC_EXP_SMEM_PAD"); const size_t smem_pad = padenv ? (size_t)atol(padenv) : 0;
         pimc_roundkeys_make(S.seed, &SP.rk);
+        SP.com_stage_off = com_tma ? (int)com_flag : 0;
         for (int i = 0; i < nupd; ++i) { SP.kind[i] = h->T.upd[update_ids[i]].kind; SP.vmax[i] = h->T.upd[update_ids[i]].vmax; }
         CK(h, cudaMemcpyAsync(h->dS, &S, sizeof(DevSys), cudaMemcpyHostToDevice, h->stream));
         for (int i = 0; i < nupd; ++i) { SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; }

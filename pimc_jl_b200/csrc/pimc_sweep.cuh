@@ -27,6 +27,7 @@ struct SweepParams {
     int kind[PIMC_MAXU]; double vmax[PIMC_MAXU];   // copies of the update descriptors' constants (no global load on the prologue path)
     unsigned long long *stats;
     pimc_roundkeys rk;  // Philox round keys of the seed (constant-bank operands)
+    int com_stage_off;  // byte offset of the COM half's TMA staging area in dynamic shared memory (0: register path with plain loads)
 };
 
 // teleport (propagator.jl:30-32) without the IEEE division on the fast path: q = x * (1/2L) differs from x / 2L by
@@ -419,6 +420,19 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
 #endif
 }
 
+// ---- 1-D bulk async copies (TMA, cp.async.bulk + mbarrier complete_tx): HBM -> shared memory without register staging ----
+__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void d_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void d_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void d_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // generic centre-of-mass proposal for a permutation cycle of several worldlines (rare in a sweep): kept out of line so that it
 // does not cost the fast path registers
 __device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, double maxd, pimc_stream st, int *npol)
@@ -447,7 +461,27 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTable
     const int *nextc = S.next + (size_t)c * N;
     if (tid == 0) s_bead = 0;
     for (int i = tid; i < N; i += SWEEP_THREADS) flag[i] = 2;
+    // TMA pipeline of this warp: two stages of (x row, y row, link-action row); the next proposal's worldline is in flight
+    // (cp.async.bulk -> shared memory, completion on an mbarrier) while the current one is being processed
+    const bool use_tma = P.com_stage_off > 0;
+    const int rows = dim + 1;
+    const uint32_t row_bytes = (uint32_t)M * 8u;
+    unsigned long long *mbar = (unsigned long long *)((char *)sm + P.com_stage_off) + warp * 2;
+    double *stage0 = (double *)((char *)sm + P.com_stage_off + 128) + (size_t)warp * 2 * rows * M;
+    const uint32_t bar_u = d_smem_u32(mbar), stage_u = d_smem_u32(stage0);
+    const double *rc0 = S.r + (size_t)c * N * dim * M, *vc0 = S.Vl + (size_t)c * N * M;
+    auto issue = [&](int n_, int stg) {
+        if (lane == 0) {
+            const uint32_t b = bar_u + 8u * stg, d0 = stage_u + (uint32_t)stg * rows * row_bytes;
+            d_mbar_expect_tx(b, rows * row_bytes);
+            d_bulk_g2s(d0, rc0 + (size_t)(n_ * dim) * M, (uint32_t)dim * row_bytes, b);      // x row (and y row: contiguous)
+            d_bulk_g2s(d0 + (uint32_t)dim * row_bytes, vc0 + (size_t)n_ * M, row_bytes, b);  // cached link actions
+        }
+    };
+    if (use_tma && lane == 0) { d_mbar_init(bar_u, 1); d_mbar_init(bar_u + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
+    int it = 0;
+    if (use_tma && warp < N) issue(warp, 0);
     unsigned long long my_beads = 0;
     // groups of 32 proposals per warp: lane l draws the displacement of the l-th proposal of the group (one Philox per lane
     // instead of one per warp and proposal); the proposals themselves run one after the other, lanes striding the slices
@@ -463,6 +497,12 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTable
             const int n = g0 + t * NW;
             if (n >= N) break;
             const double dx = __shfl_sync(0xffffffffu, dxl, t), dy = __shfl_sync(0xffffffffu, dyl, t);
+            const int stg = it & 1; const uint32_t par = (uint32_t)(it >> 1) & 1u; ++it;
+            if (use_tma) {
+                __syncwarp();                              // every lane is done with the other stage (read two proposals ago)
+                if (n + NW < N) issue(n + NW, stg ^ 1);
+                d_mbar_wait(bar_u + 8u * stg, par);        // this proposal's rows have landed
+            }
             const int nx = nextc[n];
             const bool single = nx == n;
             bool run_it = single;
@@ -479,9 +519,16 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTable
 #pragma unroll
             for (int k = 0; k < KM; ++k) {
                 const int j = lane + 32 * k;
-                x[k] = j < M ? rx[j] : 0.0;
-                y[k] = (dim > 1 && j < M) ? ry[j] : 0.0;
-                v[k] = j < M ? vl[j] : 0.0;
+                if (use_tma) {
+                    const double *sx = stage0 + (size_t)stg * rows * M;
+                    x[k] = j < M ? sx[j] : 0.0;
+                    y[k] = (dim > 1 && j < M) ? sx[M + j] : 0.0;
+                    v[k] = j < M ? sx[dim * M + j] : 0.0;
+                } else {
+                    x[k] = j < M ? rx[j] : 0.0;
+                    y[k] = (dim > 1 && j < M) ? ry[j] : 0.0;
+                    v[k] = j < M ? vl[j] : 0.0;
+                }
             }
 #pragma unroll
             for (int k = 0; k < KM; ++k) {
