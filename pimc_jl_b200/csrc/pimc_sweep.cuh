@@ -410,7 +410,10 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
             b0 += TB;
         }
     }
-    if (my_beads) atomicAdd(&s_bead, my_beads);
+    {   // one shared-memory atomic per warp (a 64-bit ATOMS on one address from every thread costs ~8k cycles)
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned)my_beads);
+        if (lane == 0 && wsum) atomicAdd(&s_bead, (unsigned long long)wsum);
+    }
     __syncthreads();
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 #ifdef EXP_TIMING
