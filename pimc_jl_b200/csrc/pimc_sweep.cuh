@@ -129,8 +129,7 @@ __device__ __forceinline__ BookPre d_book_prefetch(const UpdDev &U, int c)
     int tail = b.head + b.len; if (tail >= cap) tail -= cap;
     b.tw0 = tail >> 5; b.hw0 = b.head >> 5;
     for (int i = 0; i < BOOK_PW; ++i) {
-        int wt = b.tw0 + i; if (wt >= U.ring_words) wt -= U.ring_words;
-        int wh = b.hw0 + i; if (wh >= U.ring_words) wh -= U.ring_words;
+        const int wt = (b.tw0 + i) % U.ring_words, wh = (b.hw0 + i) % U.ring_words;   // small windows wrap more than once
         b.tw[i] = ring[wt]; b.hw[i] = ring[wh];
     }
     return b;
