@@ -26,15 +26,49 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 B_ALG = 48.0   # algorithmic bytes per bead-move: read+write of position (2x8 B) and cached link action (8 B)
-F_ALG = 47.0   # algorithmic flops per bead-move, V = 0
+# algorithmic flops per bead-move: 47 (V = 0), 51 (harmonic), ~149 (12-beam lattice) -- per workload below
+L25 = [2.214297435588181, 0.9272952180016122, -0.6435011087932844, 0.6435011087932844, -2.498091544796509, 3.141592653589793,
+       2.498091544796509, 0, 1.5707963267948966, -2.2142974355881813, -1.5707963267948968, -0.9272952180016123]
+_LAT = dict(kind="lattice", dv="zero", depth=6.0, scale=1.0, sgn=-1.0, angles=L25)   # examples/density_SRL_lattice.jl:16, potentialtools.jl:28-29
+# SURVEY.md 8d configurations.  pot: keyword arguments of make_potential; measure: "energy" | "density"; sched: "sweep" | "faithful"
 WORKLOADS = {
-    "c2": dict(name="C2 2D free Bose gas N=64 M=128", pot="zero", dv="identity", dim=2, N=64, M=128, L=16.0, T=1.0, lam=1.0, Ncycle=2,
-               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 20)]),
-    "c5": dict(name="C5 2D trapped gas N=1024 M=64", pot="harmonic", dv="identity", dim=2, N=1024, M=64, L=100.0, T=1.0, lam=0.5, Ncycle=10,
-               chains=512, updates=[("com", 1, 1.0), ("reshape", 1, 2)]),
-    "c1": dict(name="C1 2D trap N=1 M=5 (as shipped)", pot="harmonic", dv="identity", dim=2, N=1, M=5, L=100.0, T=1.0, lam=0.5, Ncycle=10,
-               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 2)]),
+    "c1": dict(name="C1 2D trap N=1 M=5 (as shipped)", pot=dict(kind="harmonic", dv="identity"), dim=2, N=1, M=5, L=100.0, T=1.0, lam=0.5, Ncycle=10,
+               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 2)], measure="energy", sched="sweep", F_alg=51.0),
+    "c2": dict(name="C2 2D free Bose gas N=64 M=128", pot=dict(kind="zero", dv="identity"), dim=2, N=64, M=128, L=16.0, T=1.0, lam=1.0, Ncycle=2,
+               chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 20)], measure="energy", sched="sweep", F_alg=47.0),
+    "c2s": dict(name="C2 + ReshapeSwapLinear(20):1", pot=dict(kind="zero", dv="identity"), dim=2, N=64, M=128, L=16.0, T=1.0, lam=1.0, Ncycle=2,
+                chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 20), ("swap", 1, 20)], measure="energy", sched="sweep", F_alg=47.0),
+    "c2f": dict(name="C2, reference schedule (one particle per iteration)", pot=dict(kind="zero", dv="identity"), dim=2, N=64, M=128, L=16.0, T=1.0,
+                lam=1.0, Ncycle=2, chains=4096, updates=[("com", 1, 1.0), ("reshape", 1, 20)], measure="energy", sched="faithful", F_alg=47.0),
+    "c3": dict(name="C3 2D trap density N=256 M=100 L=16, non-interacting as shipped", pot=dict(kind="harmonic", dv="identity"), dim=2, N=256, M=100,
+               L=16.0, T=0.5, lam=0.5, Ncycle=5, chains=1024, updates=[("pcom", 1, 1.0), ("reshape", 1, 20), ("swap", 1, 20)], measure="density",
+               nbins=500, sched="sweep", F_alg=51.0),
+    "c3i": dict(name="C3 with hard core a=0.05, r_a=1.0, lnU table, cell list (32x32 cells per slice)", pot=dict(kind="harmonic", dv="identity"),
+                dim=2, N=256, M=100, L=16.0, T=0.5, lam=0.5, Ncycle=5, chains=1024, updates=[("pcom", 1, 1.0), ("reshape", 1, 20), ("swap", 1, 20)],
+                measure="density", nbins=500, sched="faithful", interactions=True, a=0.05, r_a=1.0, F_alg=51.0),
+    "c4": dict(name="C4 lattice density N=128 M=256 L=8 V0=6 l25, non-interacting", pot=_LAT, dim=2, N=128, M=256, L=8.0, T=0.2,
+               lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024, updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)], measure="density",
+               nbins=500, sched="sweep", F_alg=149.0),
+    "c4i": dict(name="C4 with interactions as the script (g=2, a=exp(-pi), lnU table, r_a from the propagator)", pot=_LAT, dim=2, N=128, M=256, L=8.0,
+                T=0.2, lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024, updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)],
+                measure="density", nbins=500, sched="faithful", interactions=True, g=2.0, r_a=0.0, F_alg=149.0),
+    "c5": dict(name="C5 2D trapped gas N=1024 M=64", pot=dict(kind="harmonic", dv="identity"), dim=2, N=1024, M=64, L=100.0, T=1.0, lam=0.5, Ncycle=10,
+               chains=512, updates=[("com", 1, 1.0), ("reshape", 1, 2)], measure="energy", sched="sweep", F_alg=51.0),
 }
+UPD_NAMES = {"com": "SingleCenterOfMass", "pcom": "PolymerCenterOfMass", "reshape": "ReshapeLinear", "swap": "ReshapeSwapLinear"}
+
+
+def interaction_args(wl):
+    """g, r_a and the pair-propagator term table of an interacting workload (host-side build, pimc_jl_b200/propint.py)"""
+    if not wl.get("interactions"):
+        return {}
+    import math
+    from pimc_jl_b200 import propint
+    g = wl.get("g") or -2 * math.pi / math.log(wl["a"])          # a = exp(-2 pi / g), src/system.jl:151
+    tau = (1.0 / wl["T"]) / wl["M"]
+    p = propint.build_prop_int(math.ceil(math.sqrt(2) * wl["L"]), g, tau)   # examples/density_SRL_lattice.jl:17
+    r_a = wl["r_a"] or propint.determine_nnrange(p, tau, 1e-20, wl["L"])
+    return dict(interactions=True, g=g, r_a=r_a, tab=p["tab"], tab_lo=p["lo"], tab_hi=p["hi"])
 
 
 def peaks():
@@ -83,16 +117,19 @@ def oracle_arm(wl, threads, iters, seed=1, therm=60):
     ob.build()
     kind = {"com": ob.UPD_SINGLE_COM, "reshape": ob.UPD_RESHAPE_LINEAR, "swap": ob.UPD_RESHAPE_SWAP, "pcom": ob.UPD_POLYMER_COM}
     systems = []
+    ia = interaction_args(wl)
+    sched = ob.SCHED_SWEEP if wl["sched"] == "sweep" else ob.SCHED_FAITHFUL
     for t in range(threads):
-        s = ob.System(ob.make_potential(wl["pot"], wl["dv"]), dim=wl["dim"], M=wl["M"], N=wl["N"], L=wl["L"], T=wl["T"], lam=wl["lam"],
-                      Ncycle=wl["Ncycle"], seed=seed, chain=t)
+        s = ob.System(ob.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], L=wl["L"], T=wl["T"], lam=wl["lam"],
+                      Ncycle=wl["Ncycle"], seed=seed, chain=t, **ia)
         ups = [(every, ob.Update(s, kind[k], v0)) for k, every, v0 in wl["updates"]]
-        en = ob.Energy(max(16, (therm + iters) // wl["Ncycle"] + 16))
+        en = ob.Energy(max(16, (therm + iters) // wl["Ncycle"] + 16)) if wl["measure"] == "energy" else ob.Density(s, wl["nbins"])
         systems.append((s, ups, en))
 
     def work(i, n, measure):
         s, ups, en = systems[i]
-        s.run(n, ups, energies=[en] if measure else [], sched=ob.SCHED_SWEEP)
+        kw = {} if not measure else (dict(energies=[en]) if wl["measure"] == "energy" else dict(densities=[en]))
+        s.run(n, ups, sched=sched, **kw)
 
     def par(n, measure):
         th = [threading.Thread(target=work, args=(i, n, measure)) for i in range(threads)]
@@ -115,27 +152,36 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--iters", type=int, default=400, help="run! iterations per step")
-    ap.add_argument("--therm", type=int, default=300, help="untimed thermalisation iterations before the warm-up")
+    ap.add_argument("--iters", type=int, default=0, help="run! iterations per step (default 400; 40000 for the reference schedule)")
+    ap.add_argument("--therm", type=int, default=-1, help="untimed thermalisation iterations before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=0)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.chains:
         wl["chains"] = args.chains
+    faithful = wl["sched"] == "faithful"
+    if not args.iters:
+        args.iters = 40000 if faithful else 400
+    if args.therm < 0:
+        args.therm = 20000 if faithful else 300
+    F_ALG = wl["F_alg"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncpu = os.cpu_count() or 1
     config = {"workload": wl["name"], "chains_per_gpu": wl["chains"], "N": wl["N"], "M": wl["M"], "dim": wl["dim"],
-              "updates": "SingleCenterOfMass(1.0):1 + ReshapeLinear:1", "schedule": "sweep", "iters_per_step": args.iters,
-              "measure": f"Energy every {wl['Ncycle']} iterations", "l2": "state (chains x 192 KiB) larger than L2"}
+              "updates": " + ".join(f"{UPD_NAMES[k]}({v0}):{every}" for k, every, v0 in wl["updates"]),
+              "schedule": "sweep (every worldline of a chain proposes per iteration)" if not faithful else "reference (one proposal per chain and iteration)",
+              "iters_per_step": args.iters, "measure": f"{wl['measure'].capitalize()} every {wl['Ncycle']} iterations",
+              "interactions": bool(wl.get("interactions")),
+              "l2": f"state ({wl['chains']} chains x {wl['N'] * wl['M'] * 24 // 1024} KiB) larger than L2"}
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path: Julia is absent from this image, so the oracle port is timed
         if rank != 0:
             return
-        per_step = args.cpu_iters or max(8, 2000 // max(1, (args.steps + args.warmup)))
+        per_step = args.cpu_iters or (max(8, 2000 // max(1, (args.steps + args.warmup))) if not faithful else 20000)
         threads = ncpu
         tot_bm, tot_t = 0, 0.0
         for step in range(args.warmup + args.steps):
@@ -144,7 +190,7 @@ def main():
                 tot_bm += bm
                 tot_t += dt
         val = tot_bm / tot_t
-        sample = f"{threads} chains (one per host thread) x {per_step} sweep iterations per step, oracle port (C, -O2), not Julia"
+        sample = f"{threads} chains (one per host thread) x {per_step} run! iterations per step, oracle port (C, -O2), not Julia"
         line = {"metric": "bead-moves/sec", "value": val, "unit": "bead-moves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "impl": "reference",
@@ -166,18 +212,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = L.load()
     Cc = wl["chains"]
-    e = pj.Engine(pj.make_potential(wl["pot"], wl["dv"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
-                  T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank)
+    e = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
+                  T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
+    SCHED = L.SCHED_FAITHFUL if faithful else L.SCHED_SWEEP
+    use_density = wl["measure"] == "density"
     kind = {"com": L.UPD_SINGLE_COM, "reshape": L.UPD_RESHAPE_LINEAR, "swap": L.UPD_RESHAPE_SWAP, "pcom": L.UPD_POLYMER_COM}
     ups = [(every, e.update_create(kind[k], v0)) for k, every, v0 in wl["updates"]]
     nmeas_total = (args.therm + (args.warmup + args.steps) * args.iters * 2) // wl["Ncycle"] + 64
-    en = e.energy_create(nmeas_total)
+    en = e.density_create(wl["nbins"]) if use_density else e.energy_create(nmeas_total)
+    mkw = dict(densities=[en]) if use_density else dict(energies=[en])
     stream = torch.cuda.current_stream()
     e.set_stream(stream.cuda_stream)
-    e.run(args.therm, ups, sched=L.SCHED_SWEEP)  # thermalisation: adaptive slice count / step settle
+    e.run(args.therm, ups, sched=SCHED)  # thermalisation: adaptive slice count / step settle
 
     def block_allreduce(n_before):
         """per-block all-reduce of the estimator accumulators: chain-mean E, Ev of this step's measurements (NCCL)"""
+        if use_density:   # density counters are summed over the GPUs at read-out
+            dens, nd, _ = e.density_read(en, wl["nbins"])
+            blk = torch.from_numpy(dens).cuda()
+            if dist is not None:
+                dist.all_reduce(blk)
+            return blk, nd
         E, Ev, n = e.energy_read_range(en, n_before, 1 << 20)
         blk = torch.from_numpy(np.stack([E, Ev])).cuda()
         if dist is not None:
@@ -191,9 +246,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm: `value` ----
-    n_seen = e.energy_read(en, -1, cap=0)[2]
+    n_seen = 0 if use_density else e.energy_read(en, -1, cap=0)[2]
     for _ in range(args.warmup):
-        e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        e.run(args.iters, ups, sched=SCHED, **mkw)
         _, n_seen = block_allreduce(n_seen)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -204,7 +259,7 @@ def main():
     bead_moves, kern_ms = 0, 0.0
     ev0.record(stream)
     for _ in range(args.steps):
-        st = e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        st = e.run(args.iters, ups, sched=SCHED, **mkw)
         bead_moves += st["bead_moves"]
         kern_ms += st["kernel_ms"]
         blk, n_seen = block_allreduce(n_seen)
@@ -232,7 +287,7 @@ def main():
     e2e_bm = 0
     for _ in range(args.steps):
         e.set_paths(host_r)                                    # H2D: this step's worldlines (pinned host memory)
-        st = e.run(args.iters, ups, energies=[en], sched=L.SCHED_SWEEP)
+        st = e.run(args.iters, ups, sched=SCHED, **mkw)
         e2e_bm += st["bead_moves"]
         blk, n_seen = block_allreduce(n_seen)                  # estimator block (all-reduced over GPUs)
         e.get_r_into(host_r)                                   # D2H: updated worldlines
@@ -246,7 +301,7 @@ def main():
         dist.all_reduce(be)
     e2e_val = float(be[0]) / float(te[0])
     h2d = per * Cc * 8
-    d2h = per * Cc * 8 + 2 * 8 * (args.iters // wl["Ncycle"])
+    d2h = per * Cc * 8 + (8 * wl["nbins"] ** wl["dim"] if use_density else 2 * 8 * (args.iters // wl["Ncycle"]))
 
     if rank != 0:
         if dist is not None:
@@ -256,7 +311,7 @@ def main():
     # dominant kernel: k_sweep (one launch per iteration: staging-bridge + centre-of-mass sweeps of every chain).  Its own launch time
     # is measured live on a moves-only leg (no estimator launches in between): achieved = algorithmic bytes per launch / avg launch time.
     l1 = lib.pimc_launch_count()
-    st_mv = e.run(args.iters, ups, sched=L.SCHED_SWEEP)
+    st_mv = e.run(args.iters, ups, sched=SCHED)
     n_launch = max(1, lib.pimc_launch_count() - l1)
     sweep_ms = st_mv["kernel_ms"] / n_launch
     sweep_bytes = st_mv["bead_moves"] * B_ALG / n_launch
@@ -271,24 +326,28 @@ def main():
         if tj.get("workload") == args.workload and tj.get("chains") == Cc:
             traffic = tj.get("k_sweep_dram_bytes_per_launch")
     whole = total_bm / world / (kern_ms * 1e-3)            # moves + estimator kernels, per GPU
-    roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": "k_run" if st_mv["launches"] == 1 else "k_sweep", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json ({how})", "alg_bytes_per_bead_move": B_ALG,
                 "alg_bytes_per_launch": sweep_bytes, "launch_ms": sweep_ms,
                 "step_including_estimator": {"achieved": whole * B_ALG / 1e9, "frac": whole * B_ALG / 1e9 / hbm},
                 "fp64": {"achieved_tflops": achieved * 1e9 / B_ALG * F_ALG / 1e12, "peak_tflops_measured_dfma": fp64.value,
                          "frac": (achieved * 1e9 / B_ALG * F_ALG / 1e12 / fp64.value) if fp64.value else None, "alg_flops_per_bead_move": F_ALG}}
-    Em = float(blk_host[0].mean()) if blk_host.numel() else None
+    if use_density:   # sum(dens)/ndata vs N (test/testmeasurements.jl:24-29), chain-summed
+        check = {"density_sum_over_ndata": float(blk_host.sum()) / (n_seen * world) if n_seen else None, "expected": float(wl["N"])}
+    else:
+        Em = float(blk_host[0].mean()) if blk_host.numel() else None
+        check = {"E_mean_last_block": Em, "E_expected_boltzmannon": wl["dim"] * wl["N"] / 2.0 * wl["T"] if wl["pot"]["kind"] == "zero" else None}
     line = {"metric": "bead-moves/sec", "value": value, "unit": "bead-moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_val, "unit": "bead-moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "kernel_ms_per_step": kern_ms / args.steps,
-            "check": {"E_mean_last_block": Em, "E_expected_boltzmannon": wl["dim"] * wl["N"] / 2.0 * wl["T"] if wl["pot"] == "zero" else None}}
+            "check": check}
     if not args.no_cpu_baseline:
-        it = args.cpu_iters or 150
+        it = args.cpu_iters or (150 if not faithful else 20000)
         bm, dt = oracle_arm(wl, ncpu, it)
         line["cpu_baseline"] = {"value": bm / dt, "unit": "bead-moves/s", "cores": ncpu, "kind": "port",
-                                "sample": f"{ncpu} chains (one per host thread) x {it} sweep iterations after 60 thermalisation iterations; "
+                                "sample": f"{ncpu} chains (one per host thread) x {it} run! iterations after 60 thermalisation iterations; "
                                           f"oracle port of the reference (C, -O2), not Julia"}
     print(json.dumps(line))
     if dist is not None:

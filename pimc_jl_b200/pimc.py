@@ -16,6 +16,8 @@ import numpy as np
 from . import _lib as _L
 from . import engine as _eng
 from .engine import Engine
+from . import propint as _propint
+from .propint import build_prop_int, determine_nnrange  # noqa: F401  (src/propagator.jl:79-89, src/system.jl:10-15)
 
 L25 = [2.214297435588181, 0.9272952180016122, -0.6435011087932844, 0.6435011087932844, -2.498091544796509, 3.141592653589793,
        2.498091544796509, 0, 1.5707963267948966, -2.2142974355881813, -1.5707963267948968, -0.9272952180016123]
@@ -255,6 +257,8 @@ class System:                       # src/system.jl:93-168
             if propint is None or not isinstance(propint, dict):
                 raise TypeError("interactions=True needs propint = dict(tab=..., lo=..., hi=...) (the sampled term table of build_prop_int)")
             tab, tab_lo, tab_hi = propint["tab"], propint["lo"], propint["hi"]
+            if r_a == 0.0:   # init_int (src/system.jl:29-31): the cut-off comes from the propagator itself
+                r_a = _propint.determine_nnrange(propint, (1.0 / T) / M, 1e-20, L)
         self.engine = Engine(_L.make_potential(**spec), dim=dim, M=M, N=N, chains=cnt, chain_offset=off, mu=mu, L_=L, T=T, lam=lam,
                              interactions=interactions, g=g, r_a=r_a, Ncycle=length_measurement_cycle, compat=compat, seed=seed,
                              tab=tab, tab_lo=tab_lo or 0.0, tab_hi=tab_hi or 1.0, device=device)
