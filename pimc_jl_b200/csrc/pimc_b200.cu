@@ -3,6 +3,7 @@
 #include <cstdio>
 #include "pimc_moves.cuh"
 #include "pimc_sweep.cuh"
+#include "pimc_sweep2.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -567,7 +568,7 @@ extern "C" int pimc_set_stream(pimc_handle *h, void *s) { if (!h) return PIMC_ER
 extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
 {
     if (!h) return PIMC_ERR_INVALID;
-    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 3) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
     SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
 }
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
@@ -1009,8 +1010,8 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     const bool com_tma = (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr;
     const size_t smem_cs = com_flag + (com_tma ? 128 + (size_t)(SWEEP_THREADS / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
     const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
-    bool batched = batched_ok && (h->opt_sweep_impl == 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
-    if (h->opt_sweep_impl == 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
+    bool batched = batched_ok && (h->opt_sweep_impl >= 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
+    if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
     if (n > 0 && !batched) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
     if (n > 0 && batched) {
@@ -1034,9 +1035,33 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         MP.nen = nen; MP.nde = nde;
         for (int i = 0; i < nen; ++i) MP.en_id[i] = P.en_id[i];
         for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
+        // second-generation staging sweep (pimc_sweep2.cuh): 512-thread CTAs, the whole chain staged as one rank-sorted batch.
+        // Used for register tiles KM <= 4 and enough worldlines to fill the CTA; PIMC_OPT_SWEEP_IMPL = 2 keeps generation one.
+        typedef void (*kfn2)(const DevSys, const DevTables *, const Sweep2Params);
+        kfn2 k_sw2 = nullptr; int cap2 = 0; size_t smem2 = 0;
+        if (KM <= 4 && S.N >= 32 && h->opt_sweep_impl != 2) {
+#define PICK_SWEEP2(P_) (KM <= 1 ? k_sweep2<P_, 1> : KM <= 2 ? k_sweep2<P_, 2> : k_sweep2<P_, 4>)
+            k_sw2 = pk == PIMC_POT_ZERO ? PICK_SWEEP2(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP2(PIMC_POT_HARMONIC) : PICK_SWEEP2(PIMC_POT_LATTICE));
+#undef PICK_SWEEP2
+            const size_t budget = 112000;   // two CTAs per SM
+            const size_t fixed = sw2_smem_bytes(pk, 0, S.N, S.M);
+            const size_t per_slot = (pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
+            const size_t com2 = com_flag + (com_tma ? (SW2_THREADS / 32) * 16 + (size_t)(SW2_THREADS / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
+            cap2 = fixed < budget ? (int)(((budget - fixed) / per_slot) & ~(size_t)15) : 0;
+            if (cap2 < 1024 || com2 > budget) k_sw2 = nullptr;
+            else {
+                smem2 = sw2_smem_bytes(pk, cap2, S.N, S.M); if (com2 > smem2) smem2 = com2;
+                cudaFuncSetAttribute(k_sw2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+                cudaFuncSetAttribute(k_sw2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
+        }
+        Sweep2Params SP2; memset(&SP2, 0, sizeof SP2); SP2.cap = cap2;
+        for (int i = 0; i < nupd; ++i) SP2.upd[i] = h->T.upd[update_ids[i]];
+        if (h->opt_sweep_impl == 3 && !k_sw2) { SETERR(h, "second-generation sweep kernel needs M <= 128, N >= 32"); return PIMC_ERR_UNSUPPORTED; }
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if ((has_com || has_rs) && k_sw2) { SP2.sp = SP; k_sw2<<<S.C, SW2_THREADS, smem2, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
+            else if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;

@@ -446,30 +446,29 @@ __device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, 
 }
 
 // KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
-template <int POT, int KM>
-__device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const DevTables *__restrict__ T, const SweepParams &P, const pimc_stream &st,
+template <int POT, int KM, int TH = SWEEP_THREADS>
+__device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &U, const SweepParams &P, const pimc_stream &st,
                                                  const int pick)
 {
     extern __shared__ double sm[];
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = SWEEP_THREADS / 32;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TH / 32;
     const int M = S.M, N = S.N, dim = S.dim;
     unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
-    const UpdDev &U = T->upd[P.upd_id[pick]];
     __shared__ BookPre s_pre; if (tid == 0) s_pre = d_book_prefetch(U, c);
     const bool polymer = P.kind[pick] == PIMC_UPD_POLYMER_COM;
     const double maxd = U.var[c];
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
     const int *nextc = S.next + (size_t)c * N;
     if (tid == 0) s_bead = 0;
-    for (int i = tid; i < N; i += SWEEP_THREADS) flag[i] = 2;
+    for (int i = tid; i < N; i += TH) flag[i] = 2;
     // TMA pipeline of this warp: two stages of (x row, y row, link-action row); the next proposal's worldline is in flight
     // (cp.async.bulk -> shared memory, completion on an mbarrier) while the current one is being processed
     const bool use_tma = P.com_stage_off > 0;
     const int rows = dim + 1;
     const uint32_t row_bytes = (uint32_t)M * 8u;
     unsigned long long *mbar = (unsigned long long *)((char *)sm + P.com_stage_off) + warp * 2;
-    double *stage0 = (double *)((char *)sm + P.com_stage_off + 128) + (size_t)warp * 2 * rows * M;
+    double *stage0 = (double *)((char *)sm + P.com_stage_off + NW * 16) + (size_t)warp * 2 * rows * M;   // after the 2 * NW mbarriers
     const uint32_t bar_u = d_smem_u32(mbar), stage_u = d_smem_u32(stage0);
     const double *rc0 = S.r + (size_t)c * N * dim * M, *vc0 = S.Vl + (size_t)c * N * M;
     auto issue = [&](int n_, int stg) {
@@ -593,7 +592,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
     const int pick = d_pick_update(P, di);
     const int kind = P.kind[pick];
     if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, T, P, st, di, pick);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, T, P, st, pick);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, T->upd[P.upd_id[pick]], P, st, pick);
 }
 
 // the swap move stays one proposal per chain and iteration (reshape.jl:123-283), thread 0 of a one-warp CTA

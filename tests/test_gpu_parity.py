@@ -340,6 +340,23 @@ def test_interacting_faithful_cell_list(oracle, compat):
 ], ids=["N300-M33", "N5-M200", "window70", "window33", "1d-window200"])
 def test_sweep_edge_cases_bit_exact(oracle, cfg, rng_, n_it, impl):
     """ragged sizes, several super-batches, register-tile variants and acceptance-window wrap-around, both sweep implementations"""
+    _run_sweep_case(oracle, cfg, rng_, n_it, impl)
+
+
+@pytest.mark.parametrize("cfg,rng_,n_it", [
+    (dict(pot="zero", dim=2, M=33, N=300, L=5.0, T=1.0, lam=1.0, Ncycle=3), 10000, 14),       # ragged M (KM = 2), one super-batch
+    (dict(pot="zero", dim=2, M=128, N=64, L=16.0, T=1.0, lam=1.0, Ncycle=2), 10000, 24),      # the C2 shape: segments up to 126 links
+    (dict(pot="harmonic", dim=2, M=128, N=64, L=6.0, T=0.5, lam=0.5, Ncycle=2), 10000, 24),   # C2 shape in a trap: rejections, wrapped windows
+    (dict(pot="harmonic", dim=2, M=64, N=600, L=8.0, T=1.0, lam=0.5, Ncycle=4), 10000, 10),   # two super-batches, several batches per sweep
+    (dict(pot="lattice", dim=2, M=40, N=33, L=8.0, T=0.5, lam=1.0 / np.pi ** 2, Ncycle=3), 500, 30),   # 12-beam lattice, window wrap
+    (dict(pot="sin2", dim=1, M=64, N=40, L=4.0, T=1.0, lam=1.0, Ncycle=5), 200, 40),          # 1-D
+], ids=["N300-M33", "C2-free", "C2-trap", "N600-M64", "lattice-N33", "1d-N40"])
+def test_sweep_gen2_bit_exact(oracle, cfg, rng_, n_it):
+    """second-generation staging sweep (pimc_sweep2.cuh: 512-thread CTAs, rank-sorted single batch) against the oracle"""
+    _run_sweep_case(oracle, cfg, rng_, n_it, 3)
+
+
+def _run_sweep_case(oracle, cfg, rng_, n_it, impl):
     ob = oracle
     e, os_ = make_pair(ob, cfg, chains=2, seed=99)
     e.set_option(L.OPT_SWEEP_IMPL, impl)
@@ -368,3 +385,35 @@ def test_sweep_edge_cases_bit_exact(oracle, cfg, rng_, n_it, impl):
         assert n == len(Eo) and np.all(np.abs(E - Eo) <= 1e-12 * scale)
     Eb, Evb, n = e.energy_read_range(en_id, 1, 2)
     assert len(Eb) == min(2, max(0, n - 1)) and np.array_equal(Eb, e.energy_read(en_id, -1)[0][1:3])
+
+
+def test_golden_vectors():
+    """The CUDA path against the committed golden vectors (tests/golden/pimc_golden.npz: pure-Python restatements of levy!, teleport,
+    distance, Energy, Density and the lattice potential, written from the Julia source) -- no oracle involved."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pimc_golden.npz"))
+    for row, l in enumerate(gold["tp_L"]):
+        assert np.array_equal(eng.teleport(gold["tp_x"][row], l), gold["tp_teleport"][row])
+        assert np.array_equal(eng.distance(gold["tp_x"][row], gold["tp_y"][row], l), gold["tp_distance"][row])
+    for i, (rows, dim, l, lam, tau) in enumerate(gold["levy_cases"]):
+        out = eng.levy_bridge(np.ascontiguousarray(gold[f"levy{i}_r"].T)[None], tau, l, lam, gold[f"levy{i}_xi"][None])
+        assert np.array_equal(out[0].T, gold[f"levy{i}_out"]), i          # bit for bit given the same Gaussian draws
+    l, T, lam = gold["en_par"]
+    r, nxt = gold["en_r"], gold["en_next"]
+    N, dim, M = r.shape
+    lat = dict(kind="lattice", dv="zero", depth=6.0, scale=1.0, sgn=-1.0, angles=list(gold["lat_angles"]))
+    for pot, key in ((dict(kind="harmonic", dv="identity"), "en_harmonic"), (lat, "en_lattice")):
+        e = pj.Engine(pj.make_potential(**pot), dim=dim, M=M, N=N, chains=2, L_=l, T=T, lam=lam, seed=3)
+        e.set_paths(np.stack([r, r]), np.stack([nxt, nxt]))
+        E, Ev, _ = e.energy_now()
+        scale = dim * N / (2 * e.tau)
+        assert np.all(np.abs(E - gold[key][0]) <= 1e-12 * scale) and np.all(np.abs(Ev - gold[key][1]) <= 1e-12 * max(1.0, abs(gold[key][1])))
+    for compat, key in ((L.COMPAT_ALL, "dens_shift"), (0, "dens_fixed")):
+        e = pj.Engine(pj.make_potential("harmonic", "identity"), dim=dim, M=M, N=N, chains=1, L_=l, T=T, lam=lam, seed=3, compat=compat)
+        e.set_paths(r[None], nxt[None])
+        d = e.density_create(10)
+        e.density_measure(d)
+        dens, nd, _ = e.density_read(d, 10)
+        assert np.array_equal(dens, gold[key]) and nd == M
+    V, _ = eng.potential_eval(gold["lat_pts"], pj.make_potential(**lat))
+    assert close(V, gold["lat_V"], 1e-12, 1e-13)
