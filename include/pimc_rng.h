@@ -27,6 +27,34 @@
 #define PIMC_HD static inline
 #endif
 
+/* ---- polynomial coefficients of the Gaussian transform.  On the device they live in the constant bank and reach the fp64
+ * pipe as c[bank][offset] operands: as literals every coefficient costs two extra instructions (an fp64 immediate is moved
+ * into a register pair half by half) in front of each DFMA of the hot loop.  Host and device read the same values. */
+#define PIMC_KLIST(X) \
+    X(PIMC_KI_LN2HI, 6.93147180369123816490e-01) X(PIMC_KI_LN2LO, 1.90821492927058770002e-10) \
+    X(PIMC_KI_L7, 1.0 / 7.0) X(PIMC_KI_L6, -1.0 / 6.0) X(PIMC_KI_L5, 0.2) X(PIMC_KI_L3, 1.0 / 3.0) \
+    X(PIMC_KI_TWOPI, 6.283185307179586476925) \
+    X(PIMC_KI_S0, 1.58969099521155010221e-10) X(PIMC_KI_S1, -2.50507602534068634195e-08) X(PIMC_KI_S2, 2.75573137070700676789e-06) \
+    X(PIMC_KI_S3, -1.98412698298579493134e-04) X(PIMC_KI_S4, 8.33333333332248946124e-03) X(PIMC_KI_S5, -1.66666666666666324348e-01) \
+    X(PIMC_KI_C0, -1.13596475577881948265e-11) X(PIMC_KI_C1, 2.08757232129817482790e-09) X(PIMC_KI_C2, -2.75573143513906633035e-07) \
+    X(PIMC_KI_C3, 2.48015872894767294178e-05) X(PIMC_KI_C4, -1.38888888888741095749e-03) X(PIMC_KI_C5, 4.16666666666666019037e-02)
+#define PIMC_KENUM(name, value) name,
+enum { PIMC_KLIST(PIMC_KENUM) PIMC_KI_COUNT };
+#undef PIMC_KENUM
+#if defined(__CUDACC__)
+#define PIMC_KVAL(name, value) value,
+static __constant__ double pimc_kc_dev[PIMC_KI_COUNT] = { PIMC_KLIST(PIMC_KVAL) };
+#undef PIMC_KVAL
+#endif
+#define PIMC_KHOST(name, value) value,
+static const double pimc_kc_host[PIMC_KI_COUNT] = { PIMC_KLIST(PIMC_KHOST) };
+#undef PIMC_KHOST
+#if defined(__CUDA_ARCH__)
+#define PIMC_K(name) pimc_kc_dev[name]
+#else
+#define PIMC_K(name) pimc_kc_host[name]
+#endif
+
 /* ---- draw kinds (bits 28..31 of counter word 0) ------------------------------------ */
 #define PIMC_K_ITER     0u  /* per-iteration, per-chain: update pick, sweep window j0    */
 #define PIMC_K_TASK     1u  /* per-move choices: n, j0, m ; bead=1: Metropolis uniform   */
@@ -221,15 +249,15 @@ PIMC_HD double pimc_log_tab(double x, const double *tab)
     double invc = tab[2 * i], lc = tab[2 * i + 1];
     k += (i >= 53);                        /* c_53 = 1.41796875 is the first centre >= sqrt 2 */
     double e = fma(z, invc, -1.0);
-    double p = 1.0 / 7.0;
-    p = fma(p, e, -1.0 / 6.0);
-    p = fma(p, e, 0.2);
+    double p = PIMC_K(PIMC_KI_L7);
+    p = fma(p, e, PIMC_K(PIMC_KI_L6));
+    p = fma(p, e, PIMC_K(PIMC_KI_L5));
     p = fma(p, e, -0.25);
-    p = fma(p, e, 1.0 / 3.0);
+    p = fma(p, e, PIMC_K(PIMC_KI_L3));
     p = fma(p, e, -0.5);
     p = fma(p, e, 1.0);
     double dk = (double)k;
-    return fma(dk, 6.93147180369123816490e-01, lc) + fma(p, e, dk * 1.90821492927058770002e-10);
+    return fma(dk, PIMC_K(PIMC_KI_LN2HI), lc) + fma(p, e, dk * PIMC_K(PIMC_KI_LN2LO));
 }
 
 /* sin and cos of 2*pi*u for u in [0,1): exact quadrant reduction in u, minimax kernels. */
@@ -237,21 +265,21 @@ PIMC_HD void pimc_sincos2pi(double u, double *sn, double *cs)
 {
     double q = floor(4.0 * u + 0.5);          /* 0..4, exact                    */
     double t = u - 0.25 * q;                  /* exact, |t| <= 1/8              */
-    double x = t * 6.283185307179586476925;   /* |x| <= pi/4                    */
+    double x = t * PIMC_K(PIMC_KI_TWOPI);     /* |x| <= pi/4                    */
     double z = x * x;
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = PIMC_K(PIMC_KI_S0);
+    ps = fma(ps, z, PIMC_K(PIMC_KI_S1));
+    ps = fma(ps, z, PIMC_K(PIMC_KI_S2));
+    ps = fma(ps, z, PIMC_K(PIMC_KI_S3));
+    ps = fma(ps, z, PIMC_K(PIMC_KI_S4));
+    ps = fma(ps, z, PIMC_K(PIMC_KI_S5));
     double s0 = fma(x * z, ps, x);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double pc = PIMC_K(PIMC_KI_C0);
+    pc = fma(pc, z, PIMC_K(PIMC_KI_C1));
+    pc = fma(pc, z, PIMC_K(PIMC_KI_C2));
+    pc = fma(pc, z, PIMC_K(PIMC_KI_C3));
+    pc = fma(pc, z, PIMC_K(PIMC_KI_C4));
+    pc = fma(pc, z, PIMC_K(PIMC_KI_C5));
     double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
     int iq = (int)q & 3;
     double s1 = (iq & 1) ? c0 : s0;

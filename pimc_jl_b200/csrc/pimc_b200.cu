@@ -1004,7 +1004,12 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
-    const size_t smem_rs = (size_t)(pk == PIMC_POT_ZERO ? 3 : 4) * SWEEP_BCAP * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + SWEEP_BCAP + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 16;
+    // generation-one staging half: xs, ys, (pv) and the row map take BCAP rows; BCAP fills what four CTAs per SM leave of the shared memory
+    const size_t rs_fixed = (size_t)SWEEP_THREADS * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 32;
+    const size_t rs_row = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
+    const size_t rs_budget = ((S.M + 31) / 32 <= 4 ? 56000 : 74000);   // launch bounds: four (KM <= 4) or three CTAs per SM
+    const int bcap = rs_fixed + 512 * rs_row < rs_budget ? (int)(((rs_budget - rs_fixed) / rs_row) & ~(size_t)15) : 512;
+    const size_t smem_rs = rs_fixed + (size_t)bcap * rs_row;
     // COM half: flags, then (TMA path, even M) two mbarriers per warp and two stages of (dim + 1) rows per warp
     const size_t com_flag = (((size_t)S.N + 127) & ~(size_t)127);
     const bool com_tma = (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr;
@@ -1018,7 +1023,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         bool has_rs = false, has_com = false, has_swap = false;
         for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
         const int KM = (S.M + 31) / 32;
-        typedef void (*kfn)(DevSys, const DevTables *, SweepParams);
+        typedef void (*kfn)(const DevSys, const DevTables *, const Sweep2Params);
 #define PICK_SWEEP(P_) (KM <= 1 ? k_sweep<P_, 1> : KM <= 2 ? k_sweep<P_, 2> : KM <= 4 ? k_sweep<P_, 4> : k_sweep<P_, 8>)
         kfn k_sw = pk == PIMC_POT_ZERO ? PICK_SWEEP(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP(PIMC_POT_HARMONIC) : PICK_SWEEP(PIMC_POT_LATTICE));
 #undef PICK_SWEEP
@@ -1039,14 +1044,17 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         // Used for register tiles KM <= 4 and enough worldlines to fill the CTA; PIMC_OPT_SWEEP_IMPL = 2 keeps generation one.
         typedef void (*kfn2)(const DevSys, const DevTables *, const Sweep2Params);
         kfn2 k_sw2 = nullptr; int cap2 = 0; size_t smem2 = 0;
-        if (KM <= 4 && S.N >= 32 && h->opt_sweep_impl != 2) {
-#define PICK_SWEEP2(P_) (KM <= 1 ? k_sweep2<P_, 1> : KM <= 2 ? k_sweep2<P_, 2> : k_sweep2<P_, 4>)
+        const char *th2env = getenv("PIMC_SW2_TH");
+        const int th2 = th2env ? atoi(th2env) : 512;          // 512 threads, two CTAs per SM (256 / four CTAs: experiment)
+        if (KM <= 4 && h->opt_sweep_impl == 3 && S.N >= 32 && (th2 == 512 || th2 == 256)) {   // measured slower than generation one: opt-in only
+#define PICK_SWEEP2(P_) (th2 == 512 ? (KM <= 1 ? k_sweep2<P_, 1, 512> : KM <= 2 ? k_sweep2<P_, 2, 512> : k_sweep2<P_, 4, 512>) \
+                                    : (KM <= 1 ? k_sweep2<P_, 1, 256> : KM <= 2 ? k_sweep2<P_, 2, 256> : k_sweep2<P_, 4, 256>))
             k_sw2 = pk == PIMC_POT_ZERO ? PICK_SWEEP2(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP2(PIMC_POT_HARMONIC) : PICK_SWEEP2(PIMC_POT_LATTICE));
 #undef PICK_SWEEP2
-            const size_t budget = 112000;   // two CTAs per SM
+            const size_t budget = th2 == 512 ? 112000 : 55500;   // two / four CTAs per SM
             const size_t fixed = sw2_smem_bytes(pk, 0, S.N, S.M);
             const size_t per_slot = (pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
-            const size_t com2 = com_flag + (com_tma ? (SW2_THREADS / 32) * 16 + (size_t)(SW2_THREADS / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
+            const size_t com2 = com_flag + (com_tma ? (th2 / 32) * 16 + (size_t)(th2 / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
             cap2 = fixed < budget ? (int)(((budget - fixed) / per_slot) & ~(size_t)15) : 0;
             if (cap2 < 1024 || com2 > budget) k_sw2 = nullptr;
             else {
@@ -1055,13 +1063,13 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
                 cudaFuncSetAttribute(k_sw2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             }
         }
-        Sweep2Params SP2; memset(&SP2, 0, sizeof SP2); SP2.cap = cap2;
+        Sweep2Params SP2; memset(&SP2, 0, sizeof SP2); SP2.cap = k_sw2 ? cap2 : bcap;
         for (int i = 0; i < nupd; ++i) SP2.upd[i] = h->T.upd[update_ids[i]];
         if (h->opt_sweep_impl == 3 && !k_sw2) { SETERR(h, "second-generation sweep kernel needs M <= 128, N >= 32"); return PIMC_ERR_UNSUPPORTED; }
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if ((has_com || has_rs) && k_sw2) { SP2.sp = SP; k_sw2<<<S.C, SW2_THREADS, smem2, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
-            else if (has_com || has_rs) { k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if ((has_com || has_rs) && k_sw2) { SP2.sp = SP; k_sw2<<<S.C, th2, smem2, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
+            else if (has_com || has_rs) { SP2.sp = SP; k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
             if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;

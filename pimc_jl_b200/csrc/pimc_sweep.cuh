@@ -12,7 +12,7 @@
 #include "pimc_moves.cuh"
 
 #define SWEEP_THREADS 256
-#define SWEEP_BCAP 2048   // staged rows per batch (xs, ys, pv: 24 B each)
+// staged rows per batch: runtime (Sweep2Params::cap), sized by the host from the shared-memory budget
 #define SWEEP_TBMAX 256   // tasks per batch
 #ifdef EXP_TIMING
 #define TICK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
@@ -29,6 +29,10 @@ struct SweepParams {
     pimc_roundkeys rk;  // Philox round keys of the seed (constant-bank operands)
     int com_stage_off;  // byte offset of the COM half's TMA staging area in dynamic shared memory (0: register path with plain loads)
 };
+
+// The update descriptors travel by value in the kernel parameters (constant bank): no dependent global loads of T->upd[...]
+// on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).
+struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; };
 
 // teleport (propagator.jl:30-32) without the IEEE division on the fast path: q = x * (1/2L) differs from x / 2L by
 // <= 1 ulp, so floor(q + 0.5) can differ only when q + 0.5 sits within a few ulp of an integer; that case takes the exact path.
@@ -216,18 +220,32 @@ __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, co
     if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
 }
 
+// cached action of the links of one strand, summed by half a warp in the order of the first-generation kernel
+__device__ __forceinline__ double d_wi_halfwarp(const double *w1, const double *w2, int n1, int mq, int hl)
+{
+    double v[8], wi = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int jp = hl + 16 * i; v[i] = jp < mq ? (jp < n1 ? w1[jp] : w2[jp]) : 0.0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wi += v[i];
+    for (int jp = hl + 128; jp < mq; jp += 16) wi += jp < n1 ? w1[jp] : w2[jp];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
+    return wi;
+}
+
 template <int POT>
-__device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevTables *__restrict__ T, const SweepParams &P, const pimc_stream &st,
-                                                     const pimc_u4 &di, const int pick)
+__device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdDev &U, const SweepParams &P, const pimc_stream &st,
+                                                     const pimc_u4 &di, const int pick, const int BCAP)
 {
     extern __shared__ double sm[];
-    double *xs = sm, *ys = sm + SWEEP_BCAP, *vo = sm + 2 * SWEEP_BCAP;               // vo: cached (old) link action of the row's link
-    double *pv = sm + 3 * SWEEP_BCAP;                                                 // potential at the new rows, only when POT != 0
-    double *pend = (POT == PIMC_POT_ZERO) ? sm + 3 * SWEEP_BCAP : sm + 4 * SWEEP_BCAP;
-    int *t_m = (int *)pend;                    // [THREADS] links of the batch's tasks
+    double *xs = sm, *ys = sm + BCAP;          // BCAP staged rows per batch (a multiple of 16, sized by the host from the shared-memory budget)
+    double *pv = sm + 2 * BCAP;                                                       // potential at the new rows, only when POT != 0
+    double *s_wi = (POT == PIMC_POT_ZERO) ? sm + 2 * BCAP : sm + 3 * BCAP;            // [THREADS] cached action of a task's links (w_initial)
+    int *t_m = (int *)(s_wi + SWEEP_THREADS);  // [THREADS] links of the batch's tasks
     int *t_off = t_m + SWEEP_THREADS;          // [THREADS] first staged row
     unsigned char *map = (unsigned char *)(t_off + SWEEP_THREADS);   // [BCAP] row -> task of the batch
-    unsigned char *flag = map + SWEEP_BCAP;    // [N] outcome per slot
+    unsigned char *flag = map + BCAP;          // [N] outcome per slot
     double *s_alpha = (double *)(flag + ((S.N + 15) & ~15));  // [M+1] staging table alpha_k
     __shared__ int s_scan[SWEEP_THREADS / 32];
     __shared__ int s_first;
@@ -235,7 +253,6 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
-    const UpdDev &U = T->upd[P.upd_id[pick]];
     __shared__ BookPre s_pre; if (tid == 0) s_pre = d_book_prefetch(U, c);   // parked in shared memory: no registers held across the sweep
     const int var = (int)U.var[c], vmax = (int)P.vmax[pick];
     double *s_logtab = s_alpha + (M + 1);     // [2*128]
@@ -289,7 +306,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
             if (tid == b0) s_first = incl - cnt;
             __syncthreads();
             const int basep = s_first;
-            const bool fits = tid >= b0 && tid < nsb && incl - basep <= SWEEP_BCAP;
+            const bool fits = tid >= b0 && tid < nsb && incl - basep <= BCAP;
             const int TB = __syncthreads_count(fits);      // prefix property: the fitting tasks are b0 .. b0+TB-1
             const int q_me = tid - b0, excl = incl - cnt - basep;
             if (fits) {
@@ -301,15 +318,10 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
             __syncthreads();
             const int B = t_off[TB - 1] + t_m[TB - 1] + 1;
             TICK(0);
-            // ---- phase A: Gaussians of every interior row, lanes = rows; the old link action of the row's link is fetched alongside ----
+            // ---- phase A: Gaussians of every interior row, lanes = rows ----
 #ifndef EXP_SKIP_A
             for (int s = tid; s < B; s += SWEEP_THREADS) {
                 const int q = map[s], row = s - t_off[q], mq = t_m[q];
-                double vold = 0.0;              // issued first, consumed last: the load's latency hides behind the Gaussian arithmetic
-                if (row < mq) {                 // link `row` of the strand: slice first+row of its particle, or wrapped on the next particle
-                    const int nq = sb0 + b0 + q;
-                    vold = row < nfirst ? vc[nq * M + first + row] : vc[nextc[nq] * M + row - nfirst];
-                }
                 if (row >= 1 && row < mq) {
                     double g0, g1;
                     pimc_gauss_pair_t(pimc_draw_rk(st, &P.rk, (uint32_t)(sb0 + b0 + q), PIMC_K_BRIDGE, 0, (uint32_t)row), s_logtab, &g0, &g1);
@@ -317,12 +329,23 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
                     xs[s] = g0 * sig;
                     if (dim > 1) ys[s] = g1 * sig;
                 }
-                if (row < mq) vo[s] = vold;
             }
 #endif
             __syncthreads();
             TICK(1);
-            // ---- phase B: serial recurrence r[j+1] = (alpha r[j] + (1-alpha) r[end]) + xi sigma, lanes = (task, dim) ----
+            // ---- phase B: serial recurrence r[j+1] = (alpha r[j] + (1-alpha) r[end]) + xi sigma, lanes = (task, dim);
+            //      the warps it leaves idle sum the cached link actions of the tasks meanwhile (global loads hidden behind B) ----
+            const int nBw = (TB * dim + 31) >> 5;
+            const bool helpers = SWEEP_THREADS / 32 - nBw >= 2;
+            if (helpers && warp >= nBw) {
+                const int hl = lane & 15, nH = (SWEEP_THREADS / 32 - nBw) * 2;
+                for (int q = (warp - nBw) * 2 + (lane >> 4); q < ((TB + 1) & ~1); q += nH) {
+                    const int qq = q < TB ? q : TB - 1;
+                    const int nq = sb0 + b0 + qq, mq = t_m[qq], nxq = nextc[nq];
+                    const double wi = d_wi_halfwarp(vc + nq * M + first, vc + nxq * M - nfirst, mq < nfirst ? mq : nfirst, mq, hl);
+                    if (hl == 0 && q < TB) s_wi[qq] = wi;
+                }
+            }
 #ifndef EXP_SKIP_B
             for (int w = tid; w < TB * dim; w += SWEEP_THREADS) {
                 const int q = dim > 1 ? (w >> 1) : w, k = dim > 1 ? (w & 1) : 0;
@@ -363,13 +386,12 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const DevT
                     const bool live = q < TB;
                     const int qq = live ? q : TB - 1;
                     const int nq = sb0 + b0 + qq, mq = live ? t_m[qq] : 0, base = t_off[qq], nxq = nextc[nq];
-                    double wi = 0.0, wu = 0.0;
-                    for (int jp = hl; jp < mq; jp += 16) {
-                        wi += vo[base + jp];
+                    double wi = helpers ? s_wi[qq] : d_wi_halfwarp(vc + nq * M + first, vc + nxq * M - nfirst, mq < nfirst ? mq : nfirst, mq, hl);
+                    double wu = 0.0;
+                    for (int jp = hl; jp < mq; jp += 16)
                         wu += (POT == PIMC_POT_ZERO) ? mht * (0.0 + 0.0) : mht * (pv[base + jp] + pv[base + jp + 1]);
-                    }
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) { wi += __shfl_xor_sync(0xffffffffu, wi, o); wu += __shfl_xor_sync(0xffffffffu, wu, o); }
+                    for (int o = 8; o > 0; o >>= 1) wu += __shfl_xor_sync(0xffffffffu, wu, o);
                     wi = 0.0 + wi; wu = 0.0 + wu;
                     int acc = 0;
                     if (hl == 0 && live) {
@@ -584,15 +606,17 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
 
 // One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
 template <int POT, int KM>
-__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(const __grid_constant__ DevSys S, const DevTables *__restrict__ T,
+                                                                                                   const __grid_constant__ Sweep2Params P2)
 {
     const int c = blockIdx.x;
+    const SweepParams &P = P2.sp;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
     pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
     const int pick = d_pick_update(P, di);
     const int kind = P.kind[pick];
-    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, T, P, st, di, pick);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, T->upd[P.upd_id[pick]], P, st, pick);
+    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, P2.upd[pick], P, st, pick);
 }
 
 // the swap move stays one proposal per chain and iteration (reshape.jl:123-283), thread 0 of a one-warp CTA

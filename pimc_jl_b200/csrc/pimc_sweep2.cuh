@@ -15,13 +15,10 @@
 #pragma once
 #include "pimc_sweep.cuh"
 
-#define SW2_THREADS 512
+#define SW2_THREADS 512       // largest CTA of this generation (array sizes); the kernel is templated on the actual count
 #define SW2_MAXR 256          // rows of a segment: m + 1 <= M - 1 <= 255 (the batched path needs M <= 256)
 #define SW2_KR 4              // rows per lane staged in registers by phase D (chunks of 16 * SW2_KR rows)
 
-// The update descriptors travel by value in the kernel parameters (constant bank): no dependent global loads of T->upd[...]
-// on the prologue or the bookkeeping tail of a CTA.
-struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; };
 
 // smem carve-up shared by host (size) and device (pointers); cap = staged slots, a multiple of 16
 __host__ __device__ inline int sw2_mp(int M) { return (M + 2) & ~1; }   // table stride: even, so that 16-byte async copies stay aligned
@@ -62,25 +59,11 @@ __device__ __forceinline__ void d_book_prefetch_async2(const UpdDev &U, int c, B
     }
 }
 
-// cached action of the links of one strand, summed by half a warp in the order of the first-generation kernel
-__device__ __forceinline__ double d_wi_halfwarp(const double *w1, const double *w2, int n1, int mq, int hl)
-{
-    double v[8], wi = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const int jp = hl + 16 * i; v[i] = jp < mq ? (jp < n1 ? w1[jp] : w2[jp]) : 0.0; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wi += v[i];
-    for (int jp = hl + 128; jp < mq; jp += 16) wi += jp < n1 ? w1[jp] : w2[jp];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
-    return wi;
-}
-
-template <int POT>
+template <int POT, int TH>
 __device__ __forceinline__ void d_reshape_sweep2_body(const DevSys &S, const Sweep2Params &P2, const pimc_stream &st, const pimc_u4 &di, const int pick)
 {
     extern __shared__ double sm[];
-    constexpr int TH = SW2_THREADS, NW = TH / 32;
+    constexpr int NW = TH / 32;
     const SweepParams &P = P2.sp;
     const UpdDev &U = P2.upd[pick];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,7 +91,8 @@ __device__ __forceinline__ void d_reshape_sweep2_body(const DevSys &S, const Swe
 
     // ---- prologue: nothing here waits for global memory ----
     for (int i = tid; i < SW2_MAXR + 2; i += TH) alive[i] = 0;
-    if (tid == 0) { s_bead = 0; s_rows = 0; d_book_prefetch_async1(U, c, &s_pre); }
+    if (tid == 0) { s_bead = 0; s_rows = 0; }
+    if (tid == 32) d_book_prefetch_async1(U, c, &s_pre);   // the thread that issues a cp.async is the one that waits for it
     for (int i = tid; i < PIMC_LOGTAB_N; i += TH) d_cp_async16(s_logtab + 2 * i, S.logtab + 2 * i);
     for (int i = tid; i < (M + 1) / 2; i += TH) { d_cp_async16(s_alpha + 2 * i, S.tab_alpha + 2 * i); d_cp_async16(s_sig + 2 * i, S.tab_sig + 2 * i); }
     if (tid == TH - 1 && ((M + 1) & 1)) { d_cp_async8(s_alpha + M, S.tab_alpha + M); d_cp_async8(s_sig + M, S.tab_sig + M); }
@@ -361,14 +345,14 @@ __device__ __forceinline__ void d_reshape_sweep2_body(const DevSys &S, const Swe
 }
 
 // One launch per iteration, one 512-thread CTA per chain: the CTA picks its update (simulation.jl:33-37) and runs that family's sweep.
-template <int POT, int KM>
-__global__ void __launch_bounds__(SW2_THREADS, 2) k_sweep2(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
+template <int POT, int KM, int TH>
+__global__ void __launch_bounds__(TH, 1024 / TH) k_sweep2(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
 {
     const int c = blockIdx.x;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P2.sp.iter);
     pimc_u4 di = pimc_draw_rk(st, &P2.sp.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
     const int pick = d_pick_update(P2.sp, di);
     const int kind = P2.sp.kind[pick];
-    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep2_body<POT>(S, P2, st, di, pick);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, SW2_THREADS>(S, P2.upd[pick], P2.sp, st, pick);
+    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep2_body<POT, TH>(S, P2, st, di, pick);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, TH>(S, P2.upd[pick], P2.sp, st, pick);
 }
