@@ -1013,7 +1013,13 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     // COM half: flags, then (TMA path, even M) two mbarriers per warp and two stages of (dim + 1) rows per warp
     const size_t com_flag = (((size_t)S.N + 127) & ~(size_t)127);
     const bool com_tma = (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr;
-    const size_t smem_cs = com_flag + (com_tma ? 128 + (size_t)(SWEEP_THREADS / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
+    bool has_pcom = false;
+    for (int i = 0; i < nupd; ++i) has_pcom |= h->T.upd[update_ids[i]].kind == PIMC_UPD_POLYMER_COM;
+    auto com_bytes = [&](int threads) {   // flags | mbarriers | max(TMA stages of every warp, scratch of the exchange-cycle moves)
+        const size_t stage = com_tma ? (size_t)(threads / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 0, cyc = has_pcom ? pcom_smem_bytes(S.N) : 0;
+        return com_flag + (size_t)(threads / 32) * 16 + (stage > cyc ? stage : cyc) + 16;
+    };
+    const size_t smem_cs = com_bytes(SWEEP_THREADS);
     const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl >= 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
     if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
@@ -1054,7 +1060,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
             const size_t budget = th2 == 512 ? 112000 : 55500;   // two / four CTAs per SM
             const size_t fixed = sw2_smem_bytes(pk, 0, S.N, S.M);
             const size_t per_slot = (pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
-            const size_t com2 = com_flag + (com_tma ? (th2 / 32) * 16 + (size_t)(th2 / 32) * 2 * (S.dim + 1) * S.M * sizeof(double) : 16);
+            const size_t com2 = com_bytes(th2);
             cap2 = fixed < budget ? (int)(((budget - fixed) / per_slot) & ~(size_t)15) : 0;
             if (cap2 < 1024 || com2 > budget) k_sw2 = nullptr;
             else {
@@ -1070,7 +1076,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
             SP.iter = h->iter + (unsigned long long)it;
             if ((has_com || has_rs) && k_sw2) { SP2.sp = SP; k_sw2<<<S.C, th2, smem2, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
             else if (has_com || has_rs) { SP2.sp = SP; k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
-            if (has_swap) { k_swap_iter<<<S.C, 32, 0, h->stream>>>(S, h->dT, SP); LAUNCHED(); launches++; }
+            if (has_swap) { SP2.sp = SP; k_swap_iter<<<S.C, 32, swap_smem_bytes(S.N, S.M), h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
             if (nen + nde > 0) {
                 long long ctrv = h->Nctr + it + 1;
                 if (ctrv % h->cfg.Ncycle == 0) {

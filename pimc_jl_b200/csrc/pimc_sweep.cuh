@@ -457,14 +457,112 @@ __device__ __forceinline__ void d_mbar_wait(uint32_t bar, uint32_t parity)
     asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// generic centre-of-mass proposal for a permutation cycle of several worldlines (rare in a sweep): kept out of line so that it
-// does not cost the fast path registers
-__device__ __noinline__ int d_com_cycle_generic(const DevSys *Sg, int c, int n, double maxd, pimc_stream st, int *npol)
+// One member worldline of a permutation cycle under the displacement (dx, dy) (com.jl:47-100, move_polymer! helper.jl:368-395):
+// loads its rows into registers, returns the lane-partial sums of the cached (wi) and new (wu) link actions; on return x, y hold
+// the shifted, wrapped positions and v the new link actions.  (fx, fy): first bead of the NEXT member of the cycle (unshifted).
+template <int POT, int KM>
+__device__ __forceinline__ void d_com_member(const DevSys &S, const double *rx, const double *ry, const double *vl, double dx, double dy, double fx, double fy,
+                                             double *x, double *y, double *v, double &wi, double &wu)
 {
-    const DevSys &S = *Sg;
-    pimc_u4 dm = pimc_draw(st, (uint32_t)n, PIMC_K_TASK, 0, 1);
-    DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)n;
-    return d_com_warp(S, c, n, maxd, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, npol);
+    const int lane = threadIdx.x & 31, M = S.M, dim = S.dim;
+    const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+        const int j = lane + 32 * k;
+        x[k] = j < M ? rx[j] : 0.0; y[k] = (dim > 1 && j < M) ? ry[j] : 0.0; v[k] = j < M ? vl[j] : 0.0;
+    }
+    wi = 0.0; wu = 0.0;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+        wi += (lane + 32 * k < M) ? v[k] : 0.0;
+        x[k] = d_teleport_fast(x[k] + dx, L, twoL, inv2L);
+        if (dim > 1) y[k] = d_teleport_fast(y[k] + dy, L, twoL, inv2L);
+        v[k] = (POT == PIMC_POT_ZERO) ? 0.0 : d_pot_t<POT>(S.pot, x[k], y[k], dim);
+    }
+    const double vnext = (POT == PIMC_POT_ZERO) ? 0.0
+        : d_pot_t<POT>(S.pot, d_teleport_fast(fx + dx, L, twoL, inv2L), dim > 1 ? d_teleport_fast(fy + dy, L, twoL, inv2L) : 0.0, dim);
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+        const int j = lane + 32 * k;
+        double up = 0.0;
+        if (POT != PIMC_POT_ZERO) {
+            up = __shfl_down_sync(0xffffffffu, v[k], 1);
+            const double nextreg = __shfl_sync(0xffffffffu, (k + 1 < KM) ? v[(k + 1 < KM) ? k + 1 : k] : 0.0, 0);
+            if (lane == 31) up = nextreg;
+            if (j == M - 1) up = vnext;         // the link out of the last slice ends on the next member of the cycle
+        }
+        const double lk = mht * (v[k] + up);
+        v[k] = lk;
+        if (j < M) wu += lk;
+    }
+}
+
+// PolymerCenterOfMass for the exchange cycles of a chain (com.jl:31-104 read as "whole cycle"), all warps of the CTA together:
+// leaders (smallest index of a cycle) by pointer jumping in shared memory, one warp per MEMBER for the link-action sums, one thread
+// per cycle for the sums in cycle order + Metropolis, one warp per member again for the commit.  Same draws as the one-warp-per-cycle
+// implementation d_com_warp (slot = leader); the reduction order differs (per-member warp sums, then cycle order).
+__host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
+template <int POT, int KM, int TH>
+__device__ __forceinline__ void d_pcom_cycles(const DevSys &S, const SweepParams &P, const pimc_stream &st, const int c, const double maxd,
+                                              unsigned char *flag, char *scratch, unsigned long long &my_beads)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TH / 32, M = S.M, N = S.N, dim = S.dim;
+    double *s_wi = (double *)scratch, *s_wu = s_wi + N, *s_fx = s_wu + N, *s_fy = s_fx + N;
+    int *s_nx = (int *)(s_fy + N), *nA = s_nx + N, *nB = nA + N, *mA = nB + N, *mB = mA + N;
+    unsigned char *s_acc = (unsigned char *)(mB + N);
+    const int *nextc = S.next + (size_t)c * N;
+    int any = 0;
+    for (int i = tid; i < N; i += TH) { const int nx = nextc[i]; s_nx[i] = nx; nA[i] = nx; mA[i] = i; s_acc[i] = 0; any |= nx != i; }
+    if (!__syncthreads_or(any)) return;                       // no exchange cycle in this chain
+    int *ns = nA, *nd = nB, *ms = mA, *md = mB;
+    for (int span = 1; span < N; span <<= 1) {                // after k rounds ms[i] = min over the 2^k successors of i
+        for (int i = tid; i < N; i += TH) { const int j = ns[i]; md[i] = ms[i] < ms[j] ? ms[i] : ms[j]; nd[i] = ns[j]; }
+        __syncthreads();
+        int *t = ns; ns = nd; nd = t; t = ms; ms = md; md = t;
+    }
+    const double *rc = S.r + (size_t)c * N * dim * M, *vc = S.Vl + (size_t)c * N * M;
+    for (int p = warp; p < N; p += NW) {                      // pass 1: link-action sums of every member
+        const int pn = s_nx[p];
+        if (pn == p) continue;
+        const pimc_u4 w = pimc_draw_rk(st, &P.rk, (uint32_t)ms[p], PIMC_K_COM, 0, 0);
+        const double dx = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5), dy = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
+        const double fx = rc[(size_t)(pn * dim) * M], fy = dim > 1 ? rc[(size_t)(pn * dim + 1) * M] : 0.0;
+        double x[KM], y[KM], v[KM], wi, wu;
+        d_com_member<POT, KM>(S, rc + (size_t)(p * dim) * M, rc + (size_t)(p * dim + 1) * M, vc + (size_t)p * M, dx, dy, fx, fy, x, y, v, wi, wu);
+        wi = warp_sum(wi); wu = warp_sum(wu);
+        if (lane == 0) { s_wi[p] = wi; s_wu[p] = wu; s_fx[p] = fx; s_fy[p] = fy; }
+    }
+    __syncthreads();
+    for (int n = tid; n < N; n += TH)                         // one thread per cycle: sums in cycle order, Metropolis (helper.jl:3-5)
+        if (ms[n] == n && s_nx[n] != n) {
+            double wi = 0.0, wu = 0.0; int p = n, npol = 0;
+            do { wi += s_wi[p]; wu += s_wu[p]; p = s_nx[p]; npol++; } while (p != n && npol <= N);
+            const double dw = (0.0 + wu) - (0.0 + wi);
+            int acc = 0;
+            if (dw >= 0.0) acc = 1;
+            else {
+                const double delta = pimc_exp(dw);
+                if (delta >= 1.0) acc = 1;
+                else { pimc_u4 dm = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 1); acc = delta > pimc_u01_co(dm.w[0], dm.w[1]); }
+            }
+            s_acc[n] = (unsigned char)acc; flag[n] = (unsigned char)acc;
+            my_beads += (unsigned long long)M * npol;
+        }
+    __syncthreads();
+    double *rw = S.r + (size_t)c * N * dim * M, *vw = S.Vl + (size_t)c * N * M;
+    for (int p = warp; p < N; p += NW) {                      // pass 2: commit the members of the accepted cycles
+        if (s_nx[p] == p || !s_acc[ms[p]]) continue;
+        const pimc_u4 w = pimc_draw_rk(st, &P.rk, (uint32_t)ms[p], PIMC_K_COM, 0, 0);
+        const double dx = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5), dy = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
+        double x[KM], y[KM], v[KM], wi, wu;
+        double *rx = rw + (size_t)(p * dim) * M, *ry = rw + (size_t)(p * dim + 1) * M, *vl = vw + (size_t)p * M;
+        d_com_member<POT, KM>(S, rx, ry, vl, dx, dy, s_fx[p], s_fy[p], x, y, v, wi, wu);
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+            const int j = lane + 32 * k;
+            if (j < M) { rx[j] = x[k]; if (dim > 1) ry[j] = y[k]; vl[j] = v[k]; }
+        }
+    }
 }
 
 // KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
@@ -528,15 +626,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
             }
             const int nx = nextc[n];
             const bool single = nx == n;
-            bool run_it = single;
-            if (polymer && !single) { run_it = true; int p = nx, cnt = 0; while (p != n && cnt <= N) { if (p < n) run_it = false; p = nextc[p]; cnt++; } }
-            if (!run_it) continue;
-            if (!single) {
-                int npol = 1;
-                int r = d_com_cycle_generic(P.Sg, c, n, maxd, st, &npol);
-                if (lane == 0) { flag[n] = r == 1 ? 1 : 0; my_beads += (unsigned long long)M * npol; }
-                continue;
-            }
+            if (!single) continue;              // members of exchange cycles: PolymerCOM moves them below, SingleCOM never (com.jl:139-141)
             double *rx = S.r + RIDX(S, c, n, 0, 0), *ry = rx + M, *vl = S.Vl + VIDX(S, c, n, 0);
             double x[KM], y[KM], v[KM], wi = 0.0, wu = 0.0;
 #pragma unroll
@@ -599,6 +689,10 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
             }
         }
     }
+    if (polymer) {                              // whole-cycle moves of the exchange cycles, all warps together (staging area reused)
+        __syncthreads();
+        d_pcom_cycles<POT, KM, TH>(S, P, st, c, maxd, flag, (char *)sm + (((size_t)N + 127) & ~(size_t)127) + NW * 16, my_beads);
+    }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
@@ -619,36 +713,153 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
     else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, P2.upd[pick], P, st, pick);
 }
 
-// the swap move stays one proposal per chain and iteration (reshape.jl:123-283), thread 0 of a one-warp CTA
-__global__ void k_swap_iter(DevSys S, const DevTables *__restrict__ T, SweepParams P)
+// The swap move stays one proposal per chain and iteration (reshape.jl:123-283): one warp per chain.  Everything that touches
+// memory or a transcendental runs across the lanes (weight table of sampleparticles, Gaussians of the two bridges, potentials, commit,
+// tail exchange); the two staging recurrences run on four lanes (bridge x dim); every SUM keeps the sequential order of the
+// one-thread reference implementation d_reshape_swap / d_swap_weights on lane 0, so results are bit-identical to it and to the oracle.
+// Shared memory (dynamic): w[N] | 2 bridges x { x[M+1], y[M+1], v[M+1], link[M+1], vold[M+1] }.
+__host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }
+__global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
 {
-    const int c = blockIdx.x, N = S.N, M = S.M;
-    if (threadIdx.x != 0) return;
+    extern __shared__ double sm[];
+    const SweepParams &P = P2.sp;
+    const int c = blockIdx.x, N = S.N, M = S.M, dim = S.dim, lane = threadIdx.x;
     pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const UpdDev &U = T->upd[P.upd_id[d_pick_update(P, di)]];
-    if (U.kind != PIMC_UPD_RESHAPE_SWAP) return;
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    if (P.kind[pick] != PIMC_UPD_RESHAPE_SWAP) return;
+    const UpdDev &U = P2.upd[pick];
+    double *w = sm, *br = sm + N;                              // br: bridge b at br + b * 5 * (M + 1)
+    const int R1 = M + 1;
     unsigned char f = 3; unsigned long long beads = 0;
     if (N > 1) {
         const int var = (int)U.var[c];
-        pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-        pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
-        pimc_u4 dsw = pimc_draw(st, 0, PIMC_K_SWAP, 0, 0);
-        int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
-        int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
-        int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-        int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
-        double *w = S.wtab + (size_t)c * N;
-        d_swap_weights(S, c, n1, j0, m, w);
-        double norm = w[0]; for (int i = 1; i < N; ++i) norm = norm + w[i];
-        for (int i = 0; i < N; ++i) w[i] = w[i] / norm;
-        int n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
+        const pimc_u4 dt = pimc_draw_rk(st, &P.rk, 0, PIMC_K_TASK, 0, 0);
+        const pimc_u4 dm = pimc_draw_rk(st, &P.rk, 0, PIMC_K_TASK, 0, 1);
+        const pimc_u4 dsw = pimc_draw_rk(st, &P.rk, 0, PIMC_K_SWAP, 0, 0);
+        const int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+        const int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
+        const int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+        const int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
+        int *nextc = S.next + (size_t)c * N;
+        double *rc = S.r + (size_t)c * N * dim * M, *vc = S.Vl + (size_t)c * N * M;
+        // ---- sampleparticles (helper.jl:224-267): weight table across the lanes, sums on lane 0 ----
+        {
+            const int jmw = (j0 + m - 1) % M;                 // mod1(j0 + m, M) - 1
+            const bool wrapw = j0 + m > M;
+            const int n1next = wrapw ? nextc[n1] : n1;
+            const double mt = m * S.tau;
+            const double ax = rc[(n1 * dim) * M + j0 - 1], ay = dim > 1 ? rc[(n1 * dim + 1) * M + j0 - 1] : 0.0;
+            const double cx = rc[(n1next * dim) * M + jmw], cy = dim > 1 ? rc[(n1next * dim + 1) * M + jmw] : 0.0;
+            for (int i = lane; i < N; i += 32) {
+                const int inext = wrapw ? nextc[i] : i;
+                const double t = d_lnK2(ax, ay, rc[(inext * dim) * M + jmw], dim > 1 ? rc[(inext * dim + 1) * M + jmw] : 0.0, dim, S.lambda, mt, S.L);
+                const double y = d_lnK2(rc[(i * dim) * M + j0 - 1], dim > 1 ? rc[(i * dim + 1) * M + j0 - 1] : 0.0, cx, cy, dim, S.lambda, mt, S.L);
+                w[i] = pimc_exp(t + y);
+            }
+            __syncwarp();
+            double norm = 0.0;
+            if (lane == 0) { norm = w[0]; for (int i = 1; i < N; ++i) norm = norm + w[i]; }
+            norm = __shfl_sync(0xffffffffu, norm, 0);
+            for (int i = lane; i < N; i += 32) w[i] = w[i] / norm;
+            __syncwarp();
+        }
+        int n2 = 0;
+        if (lane == 0) n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
+        n2 = __shfl_sync(0xffffffffu, n2, 0);
         if (n1 != n2) {
-            GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
-            int r = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr);
-            f = r == 1 ? 1 : 0; beads = 2ull * (unsigned long long)(m - 1);
+            // ---- ReshapeSwapLinear body (reshape.jl:138-279), independent worldlines (the sweep schedule has no pair action) ----
+            const int jm = j0 + m, rows = m + 1, mb = m - 1;   // mb interior beads per bridge
+            const int x1 = nextc[n1], x2 = nextc[n2];
+            const bool wrap = jm > M;
+            const int je = (wrap ? jm - M : jm) - 1;
+            const int e1 = wrap ? x2 : n2, e2 = wrap ? x1 : n1; // bridge 1 ends on the cycle of n2 and vice versa
+            const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
+            // Gaussians of both bridges across the lanes: xi * sigma_j staged in place of the interior rows
+            for (int idx = lane; idx < 2 * mb; idx += 32) {
+                const int b = idx >= mb ? 1 : 0, j = 1 + idx - b * mb;
+                double g0, g1;
+                pimc_gauss_pair_t(pimc_draw_rk(st, &P.rk, 0, b ? PIMC_K_BRIDGE2 : PIMC_K_BRIDGE, 0, (uint32_t)j), S.logtab, &g0, &g1);
+                const double alpha = (double)(mb + 1 - j) / (double)(mb + 2 - j);
+                const double sig = sqrt(2 * S.lambda * alpha * S.tau);
+                double *bb = br + b * 5 * R1;
+                bb[j] = g0 * sig; if (dim > 1) bb[R1 + j] = g1 * sig;
+            }
+            // cached link actions of the old configuration (w_initial), fetched across the lanes
+            for (int idx = lane; idx < 2 * m; idx += 32) {
+                const int b = idx >= m ? 1 : 0, jp = idx - b * m, j = j0 + jp;
+                const int q = j <= M ? (b ? n2 : n1) : (b ? x2 : x1), sl = (j <= M ? j : j - M) - 1;
+                br[b * 5 * R1 + 4 * R1 + jp] = vc[q * M + sl];
+            }
+            __syncwarp();
+            // the two staging recurrences of levy! (helper.jl:118-139), lanes = (bridge, dim)
+            if (lane < 2 * dim) {
+                const int b = lane / dim, k = lane - b * dim;
+                const int ns = b ? n2 : n1, ne = b ? e2 : e1;
+                double q = rc[(ns * dim + k) * M + j0 - 1], e = rc[(ne * dim + k) * M + je];
+                if (fabs(q - e) > L) e += d_sign(q) * twoL;
+                double *arr = br + b * 5 * R1 + k * R1;
+                arr[0] = d_teleport_fast(q, L, twoL, inv2L);
+                for (int j = 1; j <= mb; ++j) {
+                    const double alpha = (double)(mb + 1 - j) / (double)(mb + 2 - j), om = 1 - alpha;
+                    q = alpha * q + om * e + arr[j];
+                    arr[j] = d_teleport_fast(q, L, twoL, inv2L);
+                }
+                arr[rows - 1] = d_teleport_fast(e, L, twoL, inv2L);
+            }
+            __syncwarp();
+            for (int idx = lane; idx < 2 * rows; idx += 32) {  // potential at every row of both bridges
+                const int b = idx >= rows ? 1 : 0, row = idx - b * rows;
+                double *bb = br + b * 5 * R1;
+                bb[2 * R1 + row] = d_pot(S.pot, bb[row], dim > 1 ? bb[R1 + row] : 0.0, dim);
+            }
+            __syncwarp();
+            for (int idx = lane; idx < 2 * m; idx += 32) {     // lnV of the new links (propagator.jl:26-28)
+                const int b = idx >= m ? 1 : 0, jp = idx - b * m;
+                double *bb = br + b * 5 * R1;
+                bb[3 * R1 + jp] = mht * (bb[2 * R1 + jp] + bb[2 * R1 + jp + 1]);
+            }
+            __syncwarp();
+            int ret = 0;
+            if (lane == 0) {                                   // the sums in the reference order
+                const double *b1 = br, *b2 = br + 5 * R1;
+                double w_initial = 0.0, w_updated = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int jp = 0; jp < m; ++jp) w_initial += b1[4 * R1 + jp] + b2[4 * R1 + jp];
+                for (int jp = 0; jp < m; ++jp) { s1 = jp == 0 ? b1[3 * R1] : s1 + b1[3 * R1 + jp]; s2 = jp == 0 ? b2[3 * R1] : s2 + b2[3 * R1 + jp]; }
+                w_updated += s1 + s2;
+                ret = d_metropolis(pimc_exp(w_updated - w_initial), pimc_u01_co(dm.w[0], dm.w[1])) ? 1 : 0;
+            }
+            ret = __shfl_sync(0xffffffffu, ret, 0);
+            if (ret) {
+                const double *b1 = br, *b2 = br + 5 * R1;
+                if (lane == 0) { nextc[n1] = x2; nextc[n2] = x1; }   // reshape.jl:254
+                for (int jr = 2 + lane; jr <= m + 1; jr += 32) {     // new rows 2..m+1: beyond slice M they land on the NEW next particle
+                    const int j = j0 + jr - 1;
+                    const int q1 = j <= M ? n1 : x2, q2 = j <= M ? n2 : x1, sl = (j <= M ? j : j - M) - 1;
+                    rc[(q1 * dim) * M + sl] = b1[jr - 1]; if (dim > 1) rc[(q1 * dim + 1) * M + sl] = b1[R1 + jr - 1];
+                    rc[(q2 * dim) * M + sl] = b2[jr - 1]; if (dim > 1) rc[(q2 * dim + 1) * M + sl] = b2[R1 + jr - 1];
+                }
+                for (int jp = 1 + lane; jp <= m; jp += 32) {
+                    const int j = j0 + jp - 1;
+                    const int q1 = j <= M ? n1 : x2, q2 = j <= M ? n2 : x1, sl = (j <= M ? j : j - M) - 1;
+                    vc[q1 * M + sl] = b1[3 * R1 + jp - 1];
+                    vc[q2 * M + sl] = b2[3 * R1 + jp - 1];
+                }
+                if (jm < M)                                          // tails jm+1..M change owner (reshape.jl:269-275)
+                    for (int sl = jm + lane; sl < M; sl += 32) {
+                        for (int k = 0; k < dim; ++k) {
+                            const double t = rc[(n1 * dim + k) * M + sl]; rc[(n1 * dim + k) * M + sl] = rc[(n2 * dim + k) * M + sl]; rc[(n2 * dim + k) * M + sl] = t;
+                        }
+                        const double tv = vc[n1 * M + sl]; vc[n1 * M + sl] = vc[n2 * M + sl]; vc[n2 * M + sl] = tv;
+                    }
+                if (lane == 0 && !(S.compat & PIMC_COMPAT_SWAP_STALE_LINK) && jm <= M) {   // intended: the link leaving slice j_m changes owner too
+                    const double tv = vc[n1 * M + jm - 1]; vc[n1 * M + jm - 1] = vc[n2 * M + jm - 1]; vc[n2 * M + jm - 1] = tv;
+                }
+            }
+            f = ret ? 1 : 0; beads = 2ull * (unsigned long long)(m - 1);
         }
     }
+    if (lane != 0) return;
     // faithful-style bookkeeping of a single proposal (apply!, simulation.jl:19-27)
     RingReg R; R.head = U.ring_head[c]; R.len = U.ring_len[c]; R.sum = U.ring_sum[c]; R.tries = U.tries_var[c];
     U.tries[c] += 1;
