@@ -45,7 +45,7 @@ WORKLOADS = {
                nbins=500, sched="sweep", F_alg=51.0),
     "c3i": dict(name="C3 with hard core a=0.05, r_a=1.0, lnU table, cell list (32x32 cells per slice)", pot=dict(kind="harmonic", dv="identity"),
                 dim=2, N=256, M=100, L=16.0, T=0.5, lam=0.5, Ncycle=5, chains=1024, updates=[("pcom", 1, 1.0), ("reshape", 1, 20), ("swap", 1, 20)],
-                measure="density", nbins=500, sched="faithful", interactions=True, a=0.05, r_a=1.0, F_alg=51.0),
+                measure="density", nbins=500, sched="faithful", interactions=True, a=0.05, r_a=1.0, F_alg=51.0, iters=100, therm=50),
     "c4": dict(name="C4 lattice density N=128 M=256 L=8 V0=6 l25, non-interacting", pot=_LAT, dim=2, N=128, M=256, L=8.0, T=0.2,
                lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024, updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)], measure="density",
                nbins=500, sched="sweep", F_alg=149.0),
@@ -162,9 +162,9 @@ def main():
         wl["chains"] = args.chains
     faithful = wl["sched"] == "faithful"
     if not args.iters:
-        args.iters = (4000 if wl.get("interactions") else 40000) if faithful else 400
+        args.iters = wl.get("iters") or ((1000 if wl.get("interactions") else 40000) if faithful else 400)
     if args.therm < 0:
-        args.therm = (2000 if wl.get("interactions") else 20000) if faithful else 300
+        args.therm = wl.get("therm") or ((500 if wl.get("interactions") else 20000) if faithful else 300)
     F_ALG = wl["F_alg"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,7 +181,7 @@ def main():
         # the reference's own CPU implementation of the path: Julia is absent from this image, so the oracle port is timed
         if rank != 0:
             return
-        per_step = args.cpu_iters or (max(8, 2000 // max(1, (args.steps + args.warmup))) if not faithful else (2000 if wl.get("interactions") else 20000))
+        per_step = args.cpu_iters or (max(8, 2000 // max(1, (args.steps + args.warmup))) if not faithful else (wl.get("iters") or (1000 if wl.get("interactions") else 20000)))
         threads = ncpu
         tot_bm, tot_t = 0, 0.0
         for step in range(args.warmup + args.steps):
@@ -344,7 +344,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "kernel_ms_per_step": kern_ms / args.steps,
             "check": check}
     if not args.no_cpu_baseline:
-        it = args.cpu_iters or (150 if not faithful else (2000 if wl.get("interactions") else 20000))
+        it = args.cpu_iters or (150 if not faithful else (wl.get("iters") or (1000 if wl.get("interactions") else 20000)))
         bm, dt = oracle_arm(wl, ncpu, it)
         line["cpu_baseline"] = {"value": bm / dt, "unit": "bead-moves/s", "cores": ncpu, "kind": "port",
                                 "sample": f"{ncpu} chains (one per host thread) x {it} run! iterations after 60 thermalisation iterations; "

@@ -128,3 +128,36 @@ def test_debug_exports():
     e = Energy(s, 3)
     with pytest.raises(Exception):
         run_b(s, 100, [(1, ReshapeLinear(s, 3))], Zmeasurements=[e])  # 10 measurements into a vector of 3: the reference errors too
+
+
+@pytest.mark.gpu
+def test_checkpoint_restore_and_save_tools(tmp_path):
+    """State checkpoint / restore: a restored System continues bit for bit; save_paths / save_density write the
+    reference's CSV layouts (examples/tools/savetools.jl)."""
+    from pimc_jl_b200 import tools
+    import pimc_jl_b200.pimc as P
+    kw = dict(dV="identity", dim=2, M=16, N=6, L=4.0, T=1.0, lam=0.5, length_measurement_cycle=2, chains=3, seed=21, schedule="sweep")
+    s = P.System(P.harmonic(), **kw)
+    ups = [(1, P.SingleCenterOfMass(s, 1.0)), (1, P.ReshapeLinear(s, 6)), (2, P.ReshapeSwapLinear(s, 6))]
+    P.run_b(s, 30, ups)
+    ck = tools.checkpoint(s, str(tmp_path / "ck"), ups)
+    r0, _, _, n0 = s.engine.paths(want=("r", "next"))
+    P.run_b(s, 20, ups)
+    r1, V1, _, n1 = s.engine.paths(want=("r", "V", "next"))
+    assert not np.array_equal(r0, r1)
+    s2 = P.System(P.harmonic(), **kw)
+    var = tools.restore(s2, ck)
+    ups2 = [(1, P.SingleCenterOfMass(s2, 1.0)), (1, P.ReshapeLinear(s2, 6)), (2, P.ReshapeSwapLinear(s2, 6))]
+    assert var.shape == (3, 3)
+    ra, _, _, na = s2.engine.paths(want=("r", "next"))
+    assert np.array_equal(ra, r0) and np.array_equal(na, n0)
+    assert s2.engine.scalars()["iter"] == 30
+    path = tools.save_paths(s, str(tmp_path / "paths.csv"))
+    tab = np.loadtxt(path, delimiter=",", skiprows=1)
+    assert tab.shape == (17, 13) and open(path).readline().startswith("tau,p1 x,p1 y,p2 x")
+    d = P.Density(s, nbins=20)
+    P.run_b(s, 10, ups, Zmeasurements=[d])
+    path = tools.save_density(s, d, 0.0, "test", 1.0, path=str(tmp_path / "dens.csv"))
+    tab = np.loadtxt(path, delimiter=",", skiprows=1)
+    assert tab.shape == (20, 21) and abs(tab[:, 1:].sum() * d.bin - s.N) < 0.5 * s.N
+    assert "Slices" in tools.info_updates(ups) and "particles" in tools.info_system(s)
