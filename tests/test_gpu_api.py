@@ -161,3 +161,50 @@ def test_checkpoint_restore_and_save_tools(tmp_path):
     tab = np.loadtxt(path, delimiter=",", skiprows=1)
     assert tab.shape == (20, 21) and abs(tab[:, 1:].sum() * d.bin - s.N) < 0.5 * s.N
     assert "Slices" in tools.info_updates(ups) and "particles" in tools.info_system(s)
+
+
+@pytest.mark.gpu
+def test_full_size_properties_c2_and_c5():
+    """BASELINE.json's full sizes (C2: 4096 chains x N=64 x M=128; C5: 512 chains x N=1024 x M=64), held through size-independent
+    properties: beads stay in the box (test/testsystem.jl:37-56), `next` stays a permutation, the cached link action equals the
+    recomputed one, a run is reproducible bit for bit, results do not depend on how the chains are sharded (chain_offset: the
+    multi-GPU partition), and <E> of distinguishable free particles is N d / (2 beta) within |z| < 3."""
+    import pimc_jl_b200 as pj
+    from pimc_jl_b200 import _lib as L
+
+    def build(pot, chains, off, N, M, Lbox, lam, ncyc=2):
+        e = pj.Engine(pj.make_potential(pot, "identity"), dim=2, M=M, N=N, chains=chains, chain_offset=off, L_=Lbox, T=1.0, lam=lam, Ncycle=ncyc, seed=42)
+        ups = [(1, e.update_create(L.UPD_SINGLE_COM, 1.0)), (1, e.update_create(L.UPD_RESHAPE_LINEAR, 20))]
+        return e, ups
+
+    # ---- C2 ----
+    e, ups = build("zero", 4096, 0, 64, 128, 16.0, 1.0)
+    en = e.energy_create(400)
+    e.run(200, ups, sched=L.SCHED_SWEEP)
+    e.run(200, ups, energies=[en], sched=L.SCHED_SWEEP)
+    r, V, _, nxt = e.paths(want=("r", "V", "next"))
+    assert np.all(np.abs(r) <= 16.0) and np.all(np.isfinite(r))
+    assert np.array_equal(np.sort(nxt, axis=1), np.broadcast_to(np.arange(1, 65), nxt.shape))
+    a_cached, a_recomputed = e.action()
+    assert np.allclose(a_cached, a_recomputed, rtol=1e-12, atol=1e-12)
+    st = e.energy_stats(en)
+    Emean = st[:, 1] / st[:, 0]
+    assert abs(zscore(Emean, 64.0)) < 3, (Emean.mean(), zscore(Emean, 64.0))
+    # sharding independence + reproducibility: chains [1024, 1536) run alone give the same bits
+    e2, ups2 = build("zero", 512, 1024, 64, 128, 16.0, 1.0)
+    e2.run(200, ups2, sched=L.SCHED_SWEEP)
+    e2.run(200, ups2, sched=L.SCHED_SWEEP)
+    r2, V2, _, n2 = e2.paths(want=("r", "V", "next"))
+    assert np.array_equal(r2, r[1024:1536]) and np.array_equal(V2, V[1024:1536]) and np.array_equal(n2, nxt[1024:1536])
+    e.close(); e2.close()
+    # ---- C5 ----
+    e, ups = build("harmonic", 512, 0, 1024, 64, 100.0, 0.5, ncyc=10)
+    e.run(60, ups, sched=L.SCHED_SWEEP)
+    r, V, _, nxt = e.paths(want=("r", "V", "next"))
+    assert np.all(np.abs(r) <= 100.0) and np.all(np.isfinite(r))
+    a_cached, a_recomputed = e.action()
+    assert np.allclose(a_cached, a_recomputed, rtol=1e-12, atol=1e-9)
+    e3, ups3 = build("harmonic", 64, 448, 1024, 64, 100.0, 0.5, ncyc=10)
+    e3.run(60, ups3, sched=L.SCHED_SWEEP)
+    r3 = e3.paths(want=("r",))[0]
+    assert np.array_equal(r3, r[448:512])
