@@ -1081,7 +1081,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
                 long long ctrv = h->Nctr + it + 1;
                 if (ctrv % h->cfg.Ncycle == 0) {
                     MP.k = h->N_MC + ctrv / h->cfg.Ncycle - 1;
-                    typedef void (*mfn)(DevSys, const DevTables *, MeasParams);
+                    typedef void (*mfn)(const DevSys, const DevTables *, const MeasParams);
 #define PICK_MEAS(P_) (KM <= 1 ? k_measure<P_, 1> : KM <= 2 ? k_measure<P_, 2> : KM <= 4 ? k_measure<P_, 4> : KM <= 8 ? k_measure<P_, 8> : k_measure<P_, 0>)
                     mfn k_me = pk == PIMC_POT_ZERO ? PICK_MEAS(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_MEAS(PIMC_POT_HARMONIC) : PICK_MEAS(PIMC_POT_LATTICE));
 #undef PICK_MEAS

@@ -370,12 +370,14 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
             __syncthreads();
             TICK(2);
             // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
+#ifndef EXP_SKIP_C
             for (int s = tid; s < B; s += SWEEP_THREADS) {
                 double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
                 xs[s] = x;
                 if (dim > 1) { y = d_teleport_fast(ys[s], L, twoL, inv2L); ys[s] = y; }
                 if (POT != PIMC_POT_ZERO) pv[s] = d_pot_t<POT>(S.pot, x, y, dim);
             }
+#endif
             __syncthreads();
             TICK(3);
             // ---- phase D: Delta-U from shared memory, Metropolis, coalesced commit -- one warp per task ----
@@ -917,6 +919,7 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
     const double twoL = 2 * S.L;
     const double *rc = S.r + (size_t)c * N * dim * M;
     const int *nextc = S.next + (size_t)c * N;
+    const int dvk = S.pot.dv_kind;                                  // hoisted: the virial term r . dV(r) is x^2 + y^2 for dV = identity
     double link = 0.0, pot = 0.0, vkin = 0.0;
     for (int n = warp; n < N; n += nw) {
         const double *rx = rc + (size_t)(n * dim) * M, *ry = rx + M;
@@ -940,7 +943,8 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
                 if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
                 link += d2;
                 if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
-                vkin += d_rdv(S.pot, ax, ay, dim);
+                if (dvk == PIMC_DV_IDENTITY) { double s = ax * ax; if (dim > 1) s = s + ay * ay; vkin += s; }   // r . dV(r), measurement.jl:105
+                else if (dvk != PIMC_DV_ZERO) vkin += d_rdv(S.pot, ax, ay, dim);
             }
         }
     }
@@ -956,7 +960,7 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
     }
 }
 template <int POT, int KM>
-__global__ void __launch_bounds__(256, 4) k_measure(DevSys S, const DevTables *__restrict__ T, MeasParams P)
+__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P)
 {
     __shared__ double red[96];
     const int c = blockIdx.x;
