@@ -220,6 +220,33 @@ __device__ __forceinline__ void d_bookkeep_sweep_warp(const UpdDev &U, int c, co
     if (stats) { atomicAdd(stats + 0, (unsigned long long)cnt); atomicAdd(stats + 2, beads); }
 }
 
+__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d_cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void d_cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void d_cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void d_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// apply! counters of (update, chain) fetched asynchronously (cp.async: no registers, no stall) in two steps: the scalars at
+// kernel start, the ring words they point at once the scalars have landed.  Same contents as d_book_prefetch.
+__device__ __forceinline__ void d_book_prefetch_async1(const UpdDev &U, int c, BookPre *b)
+{
+    d_cp_async4(&b->head, U.ring_head + c); d_cp_async4(&b->len, U.ring_len + c); d_cp_async4(&b->sum, U.ring_sum + c);
+    d_cp_async8(&b->tries, U.tries_var + c); d_cp_async8(&b->tr, U.tries + c); d_cp_async8(&b->ac, U.accepted + c);
+    d_cp_async8(&b->var, U.var + c);
+    b->range = U.range; b->adj = U.adj;
+}
+__device__ __forceinline__ void d_book_prefetch_async2(const UpdDev &U, int c, BookPre *b)   // after cp.async.wait_all of step 1
+{
+    const unsigned *ring = U.ring + (size_t)c * U.ring_words;
+    const int cap = (int)b->range + 1;
+    int tail = b->head + b->len; if (tail >= cap) tail -= cap;
+    b->tw0 = tail >> 5; b->hw0 = b->head >> 5;
+    for (int i = 0; i < BOOK_PW; ++i) {
+        d_cp_async4(&b->tw[i], ring + (b->tw0 + i) % U.ring_words);
+        d_cp_async4(&b->hw[i], ring + (b->hw0 + i) % U.ring_words);
+    }
+}
+
 // cached action of the links of one strand, summed by half a warp in the order of the first-generation kernel
 __device__ __forceinline__ double d_wi_halfwarp(const double *w1, const double *w2, int n1, int mq, int hl)
 {
@@ -246,17 +273,22 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
     int *t_off = t_m + SWEEP_THREADS;          // [THREADS] first staged row
     unsigned char *map = (unsigned char *)(t_off + SWEEP_THREADS);   // [BCAP] row -> task of the batch
     unsigned char *flag = map + BCAP;          // [N] outcome per slot
-    double *s_alpha = (double *)(flag + ((S.N + 15) & ~15));  // [M+1] staging table alpha_k
+    double *s_logtab = (double *)(flag + ((S.N + 15) & ~15));  // [2*128] log table of the Gaussian transform (16-byte aligned)
+    double *s_alpha = s_logtab + 2 * PIMC_LOGTAB_N;            // [M+1] staging table alpha_k
     __shared__ int s_scan[SWEEP_THREADS / 32];
     __shared__ int s_first;
     __shared__ unsigned long long s_bead;
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
-    __shared__ BookPre s_pre; if (tid == 0) s_pre = d_book_prefetch(U, c);   // parked in shared memory: no registers held across the sweep
-    const int var = (int)U.var[c], vmax = (int)P.vmax[pick];
-    double *s_logtab = s_alpha + (M + 1);     // [2*128]
-    for (int i = tid; i < 2 * PIMC_LOGTAB_N; i += SWEEP_THREADS) s_logtab[i] = S.logtab[i];
+    const double varf = U.var[c];             // the only global load the segment lengths wait for: issued first
+    // counters of the apply! bookkeeping and the tables arrive by cp.async (no registers, nobody waits): the scalars now, the ring
+    // words they point at after the first barrier; the thread that issues a cp.async is the one that waits for it
+    __shared__ BookPre s_pre; if (tid == 32) d_book_prefetch_async1(U, c, &s_pre);
+    for (int i = tid; i < PIMC_LOGTAB_N; i += SWEEP_THREADS) d_cp_async16(s_logtab + 2 * i, S.logtab + 2 * i);
+    for (int i = tid; i < (M + 1) / 2; i += SWEEP_THREADS) d_cp_async16(s_alpha + 2 * i, S.tab_alpha + 2 * i);
+    if (tid == SWEEP_THREADS - 1 && ((M + 1) & 1)) d_cp_async8(s_alpha + M, S.tab_alpha + M);
+    const int vmax = (int)P.vmax[pick];
     const int j0 = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
     const double L = S.L, twoL = 2 * S.L, inv2L = 1.0 / twoL, mht = -0.5 * S.tau;
     const int *nextc = S.next + (size_t)c * N;
@@ -264,8 +296,8 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
     double *vc = S.Vl + (size_t)c * N * M;
     const int first = j0 - 1, nfirst = M - first;   // a strand's rows 0..nfirst-1 lie on its own particle, the rest on the next one
     if (tid == 0) s_bead = 0;
-    for (int i = tid; i <= M; i += SWEEP_THREADS) s_alpha[i] = S.tab_alpha[i];
     unsigned long long my_beads = 0;
+    bool tables_pending = true;
 #ifdef EXP_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(), tstart = tlast; int nbatch = 0;
 #endif
@@ -277,17 +309,19 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
         int m = 0, cnt = 0, nx = 0;
         double bx = 0.0, by = 0.0, ex = 0.0, ey = 0.0;
         if (n < N) {
+            nx = nextc[n];                          // independent of the adaptive variable: in flight together with it
+            bx = rc[(n * dim) * M + first]; if (dim > 1) by = rc[(n * dim + 1) * M + first];
             pimc_u4 dt = pimc_draw_rk(st, &P.rk, (uint32_t)n, PIMC_K_TASK, 0, 0);
+            const int var = (int)varf;
             int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
             m = vmax < mm ? vmax : mm;
             cnt = m + 1;
-            nx = nextc[n];
             // endpoints (reshape.jl:56-58) with the boundary shift of levy! (helper.jl:120-125)
             const int pe = m < nfirst ? n : nx, je = m < nfirst ? first + m : m - nfirst;
-            bx = rc[(n * dim) * M + first]; ex = rc[(pe * dim) * M + je];
+            ex = rc[(pe * dim) * M + je];
             if (fabs(bx - ex) > L) ex += d_sign(bx) * twoL;
             if (dim > 1) {
-                by = rc[(n * dim + 1) * M + first]; ey = rc[(pe * dim + 1) * M + je];
+                ey = rc[(pe * dim + 1) * M + je];
                 if (fabs(by - ey) > L) ey += d_sign(by) * twoL;
             }
             my_beads += (unsigned long long)(m - 1);
@@ -297,6 +331,11 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         __syncthreads();                       // previous super-batch done with s_scan / staging
         if (lane == 31) s_scan[warp] = incl;
+        if (tables_pending) {                  // first pass: the async copies have had the prologue to land
+            d_cp_async_wait_all();
+            if (tid == 32) { d_book_prefetch_async2(U, c, &s_pre); }
+            tables_pending = false;
+        }
         __syncthreads();
         for (int w = 0; w < warp; ++w) incl += s_scan[w];
         const int nsb = N - sb0 < SWEEP_THREADS ? N - sb0 : SWEEP_THREADS;
@@ -319,7 +358,9 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
             const int B = t_off[TB - 1] + t_m[TB - 1] + 1;
             TICK(0);
             // ---- phase A: Gaussians of every interior row, lanes = rows ----
-#ifndef EXP_SKIP_A
+#ifdef EXP_SKIP_A
+            for (int s = tid; s < B; s += SWEEP_THREADS) { const int q = map[s], row = s - t_off[q], mq = t_m[q]; if (row >= 1 && row < mq) { xs[s] = 0.0; ys[s] = 0.0; } }
+#else
             for (int s = tid; s < B; s += SWEEP_THREADS) {
                 const int q = map[s], row = s - t_off[q], mq = t_m[q];
                 if (row >= 1 && row < mq) {
@@ -408,6 +449,9 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
                     }
                     acc = __shfl_sync(0xffffffffu, acc, lane & 16);
                     (void)hmask;
+#ifdef EXP_SKIP_D
+                    acc = 0;
+#endif
                     if (acc) {
                         const int n1 = mq < nfirst ? mq : nfirst;                 // rows 0..n1-1 on particle nq, the rest wrapped on nxq
                         double *x1 = rc + (nq * dim) * M + first, *x2 = rc + (nxq * dim) * M - nfirst;
@@ -437,6 +481,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
         const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned)my_beads);
         if (lane == 0 && wsum) atomicAdd(&s_bead, (unsigned long long)wsum);
     }
+    if (tid == 32) d_cp_async_wait_all();      // ring words of the counter prefetch
     __syncthreads();
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 #ifdef EXP_TIMING
@@ -447,7 +492,6 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
 }
 
 // ---- 1-D bulk async copies (TMA, cp.async.bulk + mbarrier complete_tx): HBM -> shared memory without register staging ----
-__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void d_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void d_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void d_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)

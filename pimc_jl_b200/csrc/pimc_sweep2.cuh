@@ -33,32 +33,6 @@ __host__ __device__ inline size_t sw2_smem_bytes(int pot_kind, int cap, int N, i
     return b + 64;
 }
 
-__device__ __forceinline__ void d_cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
-__device__ __forceinline__ void d_cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
-__device__ __forceinline__ void d_cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d_smem_u32(dst_smem)), "l"(src) : "memory"); }
-__device__ __forceinline__ void d_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// apply! counters of (update, chain) fetched asynchronously (cp.async: no registers, no stall) in two steps: the scalars at
-// kernel start, the ring words they point at once the scalars have landed.  Same contents as d_book_prefetch.
-__device__ __forceinline__ void d_book_prefetch_async1(const UpdDev &U, int c, BookPre *b)
-{
-    d_cp_async4(&b->head, U.ring_head + c); d_cp_async4(&b->len, U.ring_len + c); d_cp_async4(&b->sum, U.ring_sum + c);
-    d_cp_async8(&b->tries, U.tries_var + c); d_cp_async8(&b->tr, U.tries + c); d_cp_async8(&b->ac, U.accepted + c);
-    d_cp_async8(&b->var, U.var + c);
-    b->range = U.range; b->adj = U.adj;
-}
-__device__ __forceinline__ void d_book_prefetch_async2(const UpdDev &U, int c, BookPre *b)   // after cp.async.wait_all of step 1
-{
-    const unsigned *ring = U.ring + (size_t)c * U.ring_words;
-    const int cap = (int)b->range + 1;
-    int tail = b->head + b->len; if (tail >= cap) tail -= cap;
-    b->tw0 = tail >> 5; b->hw0 = b->head >> 5;
-    for (int i = 0; i < BOOK_PW; ++i) {
-        d_cp_async4(&b->tw[i], ring + (b->tw0 + i) % U.ring_words);
-        d_cp_async4(&b->hw[i], ring + (b->hw0 + i) % U.ring_words);
-    }
-}
-
 template <int POT, int TH>
 __device__ __forceinline__ void d_reshape_sweep2_body(const DevSys &S, const Sweep2Params &P2, const pimc_stream &st, const pimc_u4 &di, const int pick)
 {
