@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--iters", type=int, default=0, help="run! iterations per step (default 400; 40000 for the reference schedule)")
     ap.add_argument("--therm", type=int, default=-1, help="untimed thermalisation iterations before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--faithful-impl", type=int, default=0, help="reference-schedule proposals: 0 warp-cooperative (default), 1 one thread (A/B)")
     ap.add_argument("--cpu-iters", type=int, default=0)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -215,6 +216,8 @@ def main():
     e = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
                   T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
     SCHED = L.SCHED_FAITHFUL if faithful else L.SCHED_SWEEP
+    if args.faithful_impl:
+        e.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
     use_density = wl["measure"] == "density"
     kind = {"com": L.UPD_SINGLE_COM, "reshape": L.UPD_RESHAPE_LINEAR, "swap": L.UPD_RESHAPE_SWAP, "pcom": L.UPD_POLYMER_COM}
     ups = [(every, e.update_create(kind[k], v0)) for k, every, v0 in wl["updates"]]

@@ -95,6 +95,8 @@ int  pimc_version(void);
 int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run kernels on this cudaStream_t   */
 /* engine options (no reference counterpart). PIMC_OPT_SWEEP_IMPL: 0 auto, 1 persistent kernel (k_run), 2 per-iteration sweep kernels */
 #define PIMC_OPT_SWEEP_IMPL 1
+/* PIMC_OPT_FAITHFUL_IMPL: proposals of the reference schedule: 0 warp-cooperative (default), 1 one thread per proposal (A/B, same bits) */
+#define PIMC_OPT_FAITHFUL_IMPL 2
 int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
 /* measurement utility (no reference counterpart): sustained non-tensor fp64 FMA rate of the current device, in TFLOP/s */

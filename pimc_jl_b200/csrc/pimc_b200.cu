@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cstdio>
 #include "pimc_moves.cuh"
+#include "pimc_faithful.cuh"
 #include "pimc_sweep.cuh"
 #include "pimc_sweep2.cuh"
 #include <cstdio>
@@ -114,16 +115,24 @@ __global__ void k_bins_export(DevSys S, int c0, int nc, long long *out)
 }
 
 // ---- run! (simulation.jl:29-42): one persistent CTA per chain, all n iterations inside the kernel ----
-// dynamic shared memory: 96 doubles (reductions) + N bytes (per-task outcome) + control words
-__global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restrict__ T, RunParams P)
+// dynamic shared memory: 96 doubles (reductions) + scratch of the warp-cooperative proposal (pimc_faithful.cuh; in HBM when
+// P.fscr is set) + N bytes (per-task outcome) + control words
+// CELLS = false: systems without hard core / pair action / cell list; the compiler is told so and drops every neighbour query
+// (they are out-of-line calls that would otherwise push the kernel to the register cap).
+template <bool CELLS>
+__device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__restrict__ T, const RunParams &P)
 {
+    if (!CELLS) { __builtin_assume(S.need_cells == 0); __builtin_assume(S.interactions == 0); __builtin_assume(!(S.a > 0.0)); }
     extern __shared__ double smem[];
     double *red = smem;
-    unsigned char *flag = (unsigned char *)(smem + 96);
+    const size_t fs_doubles = P.fimpl == 0 ? faithful_scratch_doubles(S.N, S.M) : 0;
+    double *fscr = P.fscr ? P.fscr + (size_t)blockIdx.x * fs_doubles : smem + 96;
+    unsigned char *flag = (unsigned char *)(smem + 96 + (P.fscr ? 0 : fs_doubles));
     __shared__ unsigned long long s_bead;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int M = S.M, N = S.N;
     unsigned long long tot_bead = 0, tot_prop = 0;
+    unsigned long long prof_c[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }; // cycles per update kind [0..3], proposals [4..7], bookkeeping, estimators
 
     for (int c = blockIdx.x; c < S.C; c += gridDim.x) {
         for (long long it = 0; it < P.n; ++it) {
@@ -136,8 +145,38 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
             if (tid == 0) { s_bead = 0; }
             for (int i = tid; i < N; i += blockDim.x) flag[i] = 2; // 2 = slot not proposed
             __syncthreads();
+            const long long t_move0 = P.prof ? clock64() : 0;
 
-            if (U.kind == PIMC_UPD_RESHAPE_LINEAR) {
+            if (U.kind == PIMC_UPD_RESHAPE_LINEAR && !sweep && P.fimpl == 0) {
+                if (warp == 0) { // one proposal, the whole warp on it (pimc_faithful.cuh)
+                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    int n = (int)pimc_index(dt.w[0], (uint32_t)N);
+                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
+                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+                    GSrc g; g.xi = nullptr; g.st = st; g.slot = 0; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
+                    int r = d_reshape_linear_w(S, c, n, j0, m, g, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
+                    if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)(m - 1); }
+                }
+            } else if (U.kind == PIMC_UPD_RESHAPE_SWAP && P.fimpl == 0) {
+                if (warp == 0 && N > 1) {
+                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    pimc_u4 dsw = pimc_draw(st, 0, PIMC_K_SWAP, 0, 0);
+                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
+                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+                    int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
+                    int n2 = d_sample_partner_w(S, c, n1, j0, m, pimc_u01_co(dsw.w[2], dsw.w[3]), fscr);
+                    if (n1 == n2) { if (lane == 0) flag[0] = 3; } // early return without queue!(counter_var) (reshape.jl:134-136)
+                    else {
+                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
+                        int r = d_reshape_swap_w(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
+                        if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = 2ull * (unsigned long long)(m - 1); }
+                    }
+                } else if (tid == 0 && N <= 1) flag[0] = 3;
+            } else if (U.kind == PIMC_UPD_RESHAPE_LINEAR) {
                 const int ntask = sweep ? N : 1;
                 const int j0w = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
                 unsigned long long bm = 0;
@@ -191,6 +230,22 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                         int r = d_com_warp(S, c, slot, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
                         if (lane == 0) { flag[slot] = r == 1 ? 1 : 0; atomicAdd(&s_bead, (unsigned long long)M * npol); }
                     }
+                } else if (P.fimpl == 0) { // one proposal, the whole CTA on it (hard-core tests of all beads: pimc_faithful.cuh)
+                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    int n = -1;
+                    if (polymer) n = (int)pimc_index(dt.w[0], (uint32_t)N);
+                    else { // uniform among particles with next == self (com.jl:144-164)
+                        int cnt = 0; for (int i = 0; i < N; ++i) cnt += nextc[i] == i;
+                        if (cnt > 0) { int k = (int)pimc_index(dt.w[0], (uint32_t)cnt); for (int i = 0; i < N; ++i) if (nextc[i] == i && k-- == 0) { n = i; break; } }
+                    }
+                    if (n < 0) { if (tid == 0) flag[0] = 3; }
+                    else {
+                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = 0;
+                        int npol = 1;
+                        int r = d_com_cta(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol);
+                        if (tid == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)M * npol; }
+                    }
                 } else if (warp == 0) {
                     pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
                     pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
@@ -210,6 +265,8 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                 }
             }
             __syncthreads();
+            const long long t_move1 = P.prof ? clock64() : 0;
+            if (P.prof && tid == 0) { prof_c[U.kind & 3] += (unsigned long long)(t_move1 - t_move0); prof_c[4 + (U.kind & 3)] += 1; }
 
             // apply! bookkeeping (simulation.jl:19-27), replayed in slot order by one thread
             if (tid == 0) {
@@ -231,6 +288,8 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                 if (adj) d_adjust(U, c, R);
                 tot_bead += s_bead; tot_prop += (unsigned long long)cnt;
             }
+            const long long t_book = P.prof ? clock64() : 0;
+            if (P.prof && tid == 0) prof_c[8] += (unsigned long long)(t_book - t_move1);
             // measurement_Z_sector (measurement.jl:1-17): deterministic cadence, identical on every chain
             if (P.nen + P.nde > 0) {
                 long long ctrv = P.Nctr0 + it + 1;
@@ -252,10 +311,15 @@ __global__ void __launch_bounds__(256) k_run(DevSys S, const DevTables *__restri
                 }
             }
             __syncthreads();
+            if (P.prof && tid == 0) prof_c[9] += (unsigned long long)(clock64() - t_book);
         }
     }
+    if (tid == 0 && P.prof) for (int i = 0; i < 10; ++i) atomicAdd(P.prof + i, prof_c[i]);
     if (tid == 0 && P.stats) { atomicAdd(P.stats + 0, tot_prop); atomicAdd(P.stats + 2, tot_bead); }
 }
+__global__ void __launch_bounds__(256, 3) k_run(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<false>(S, T, P); }
+// interacting systems: CTAs of at most 64 threads, eight per SM (every chain of the 1024-chain configurations resident at once)
+__global__ void __launch_bounds__(64, 8) k_run_cells(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<true>(S, T, P); }
 
 // ---- estimator / action hooks ----
 __global__ void k_energy_now(DevSys S, double *E, double *Ev, double *parts)
@@ -403,7 +467,8 @@ struct pimc_handle {
     std::vector<void *> allocs;
     long long de_ndata[PIMC_MAXD];
     double r_a; double vol;
-    int opt_sweep_impl;
+    int opt_sweep_impl, opt_faithful_impl;
+    double *fscr;       // HBM scratch for warp-cooperative proposals that do not fit shared memory (lazily allocated)
     cudaEvent_t ev0, ev1;
     int device;
 };
@@ -500,7 +565,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr;
     memset(&h->T, 0, sizeof h->T);
     int rc = PIMC_OK;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
@@ -535,7 +600,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         CKC(cudaMemcpy(t, cfg->tab, sizeof(double) * cfg->tab_n * cfg->tab_n, cudaMemcpyHostToDevice));
         S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
     }
-    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 4)); RCC(dalloc(h, &h->dS, 1));
+    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 16)); RCC(dalloc(h, &h->dS, 1));
     {   // table of the division-free log of the Gaussian transform (include/pimc_rng.h), filled with IEEE operations on the host
         double htab[2 * PIMC_LOGTAB_N]; pimc_logtab_fill(htab);
         double *dl; RCC(dalloc(h, &dl, 2 * PIMC_LOGTAB_N));
@@ -569,6 +634,7 @@ extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
 {
     if (!h) return PIMC_ERR_INVALID;
     if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 3) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_FAITHFUL_IMPL && value >= 0 && value <= 1) { h->opt_faithful_impl = (int)value; return PIMC_OK; }
     SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
 }
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
@@ -997,10 +1063,22 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         long long cnt; int rc = energy_count(h, P.en_id[i], &cnt); if (rc) return rc;
         if (cnt + nmeas > h->T.en[P.en_id[i]].cap) { SETERR(h, "Energy buffer of %lld entries would overflow (%lld + %lld)", (long long)h->T.en[P.en_id[i]].cap, cnt, nmeas); return PIMC_ERR_STATE; }
     }
-    CK(h, cudaMemsetAsync(h->dstats, 0, 4 * sizeof(unsigned long long), h->stream));
-    int threads = sched == PIMC_SCHED_SWEEP ? 64 : 32;
+    CK(h, cudaMemsetAsync(h->dstats, 0, 16 * sizeof(unsigned long long), h->stream));
+    // FAITHFUL: warp 0 owns the proposal; large chains get three more warps for the estimators (Energy / Density stream N*M beads)
+    int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? 64 : 32);
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
+    P.fimpl = h->opt_faithful_impl; P.fscr = nullptr;
+    P.prof = getenv("PIMC_PROF") ? h->dstats + 4 : nullptr;   // per-phase cycle counters of k_run, printed to stderr after the run
+    if (P.fimpl == 0) {
+        const size_t fs = faithful_scratch_doubles(S.N, S.M) * sizeof(double);
+        if (smem + fs <= 160 * 1024) smem += fs;
+        else { // rows of one chain do not fit shared memory: scratch in HBM, one slab per CTA
+            if (!h->fscr) { int rc = dalloc(h, &h->fscr, (size_t)S.C * faithful_scratch_doubles(S.N, S.M)); if (rc) return rc; }
+            P.fscr = h->fscr;
+        }
+        if (smem > 48 * 1024) CK(h, cudaFuncSetAttribute(S.need_cells ? k_run_cells : k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
@@ -1024,7 +1102,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     bool batched = batched_ok && (h->opt_sweep_impl >= 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
     if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    if (n > 0 && !batched) { k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); LAUNCHED(); launches++; }
+    if (n > 0 && !batched) {
+        if (S.need_cells) k_run_cells<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); else k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P);
+        LAUNCHED(); launches++;
+    }
     if (n > 0 && batched) {
         bool has_rs = false, has_com = false, has_swap = false;
         for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
@@ -1095,7 +1176,13 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     float ms = 0; CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    unsigned long long st[4]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
+    unsigned long long st[16]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
+    if (P.prof && n > 0) {
+        const char *kn[4] = { "ReshapeLinear", "ReshapeSwap", "SingleCOM", "PolymerCOM" };
+        fprintf(stderr, "[pimc prof] k_run %.3f ms, %lld iterations x %d chains; mean cycles per proposal:", ms, (long long)n, S.C);
+        for (int k = 0; k < 4; ++k) if (st[4 + 4 + k]) fprintf(stderr, " %s %.0f (x%llu)", kn[k], (double)st[4 + k] / (double)st[4 + 4 + k], st[4 + 4 + k]);
+        fprintf(stderr, "; per iteration: bookkeeping %.0f, estimators %.0f\n", (double)st[4 + 8] / ((double)n * S.C), (double)st[4 + 9] / ((double)n * S.C));
+    }
     h->iter += (unsigned long long)n;
     if (nen + nde > 0) { h->N_MC += nmeas; h->Nctr = (h->Nctr + n) % h->cfg.Ncycle; for (int i = 0; i < nde; ++i) h->de_ndata[P.de_id[i]] += nmeas * (long long)S.M * S.C; }
     if (stats) {

@@ -66,6 +66,9 @@ struct RunParams {
     int sched;
     long long Nctr0, N_MC0; int Ncycle;
     unsigned long long *stats; // [4] proposals, accepted, bead_moves, (unused)
+    int fimpl;                 // FAITHFUL proposals: 0 warp-cooperative (pimc_faithful.cuh), 1 one thread (pimc_moves.cuh)
+    unsigned long long *prof;  // [10] per-phase cycle counters (PIMC_PROF=1), else null
+    double *fscr;              // HBM scratch of the warp-cooperative proposal when it does not fit shared memory, else null
 };
 
 #define RIDX(S, c, n, k, j) ((((size_t)(c) * (S).N + (n)) * (S).dim + (k)) * (S).M + (j))
@@ -81,6 +84,17 @@ __device__ __forceinline__ double d_distance(double x1, double x2, double L) // 
 __device__ __forceinline__ double d_teleport(double x, double L) // propagator.jl:30-32
 {
     return ((x + L) - floor(x / (2 * L) + 0.5) * (2 * L)) - L;
+}
+// the same value without the IEEE division on the fast path: q = x * (1 / 2L) differs from x / 2L by <= 1 ulp, so floor(q + 0.5) can
+// differ only when q + 0.5 sits within a few ulp of an integer; that case (and NaN / huge arguments) takes the exact path
+__device__ __forceinline__ double d_teleport_q(double x, double L)
+{
+    const double twoL = 2 * L, inv2L = 1.0 / twoL;
+    double s = x * inv2L + 0.5;
+    double f = floor(s);
+    double d = s - f;
+    if (!(fabs(d - 0.5) <= 0.5 - 1e-9) || !(fabs(s) < 1e6)) f = floor(x / twoL + 0.5);
+    return ((x + L) - f * twoL) - L;
 }
 __device__ __forceinline__ double d_sign(double x) { return (double)((x > 0) - (x < 0)); }
 
@@ -193,38 +207,53 @@ __device__ __forceinline__ double d_lnU(const DevSys &S, double r1x, double r1y,
 }
 
 // ---------------- cell list (nearest_neighbours.jl) ----------------
+// floor((x + L) / w) through the reciprocal, re-evaluated with the true division whenever the product lies within a few ulp of an
+// integer (the only case in which the two floors can differ)
+__device__ __forceinline__ int d_floor_div(double s, double w, double inv)
+{
+    const double t = s * inv;
+    double f = floor(t);
+    const double fr = t - f, thr = (fabs(t) + 1.0) * 4e-15;
+    if (!(fr >= thr && 1.0 - fr >= thr)) f = floor(s / w);
+    return (int)f;
+}
 __device__ __forceinline__ int d_bin(const DevSys &S, double x, double y) // :26-33, 0-based, clamped
 {
-    int ix = (int)floor((x + S.L) / S.cellw);
+    const double inv = 1.0 / S.cellw;
+    int ix = d_floor_div(x + S.L, S.cellw, inv);
     ix = ix < 0 ? 0 : (ix > S.nbins - 1 ? S.nbins - 1 : ix);
     if (S.dim == 1) return ix;
-    int iy = (int)floor((y + S.L) / S.cellw);
+    int iy = d_floor_div(y + S.L, S.cellw, inv);
     iy = iy < 0 ? 0 : (iy > S.nbins - 1 ? S.nbins - 1 : iy);
     return ix + S.nbins * iy;
 }
 __device__ __forceinline__ int d_imod(int x, int n) { int m = x % n; return m < 0 ? m + n : m; }
+// periodic wrap of a cell coordinate that left [0, n) by at most one cell (== d_imod for -1 <= x <= n)
+__device__ __forceinline__ int d_wrap1(int x, int n) { return x < 0 ? x + n : (x >= n ? x - n : x); }
 // stencil cell q of cell b, same order as bin_neighbors (:55-65)
 __device__ __forceinline__ int d_stencil(const DevSys &S, int b, int q)
 {
     if (S.dim == 2) {
         const int dx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 };
         const int dy[9] = { 0, 1, 1, 1, 0, 0, -1, -1, -1 };
-        int x = b % S.nbins, y = b / S.nbins;
-        return d_imod(x + dx[q], S.nbins) + S.nbins * d_imod(y + dy[q], S.nbins);
+        int y = b / S.nbins, x = b - y * S.nbins;
+        return d_wrap1(x + dx[q], S.nbins) + S.nbins * d_wrap1(y + dy[q], S.nbins);
     }
     const int d1[3] = { 0, -1, 1 };
-    return d_imod(b % S.nbins + d1[q], S.nbins);
+    return d_wrap1(b % S.nbins + d1[q], S.nbins);
 }
+// Distances.PeriodicEuclidean on the +L shifted coordinates.  mod(s1, p) = s1 - p * floor(s1 / p) is s1 itself whenever s1 < p
+// (floor of a quotient below one is zero), which holds for every pair of teleported positions: no division on that path.
 __device__ __forceinline__ double d_peuclid(const DevSys &S, double ax, double ay, double bx, double by)
 {
     double p = 2 * S.L;
     double s1 = fabs((ax + S.L) - (bx + S.L));
-    double s2 = s1 - p * floor(s1 / p);
+    double s2 = s1 < p ? s1 : s1 - p * floor(s1 / p);
     double s3 = s2 < p - s2 ? s2 : p - s2;
     double acc = s3 * s3;
     if (S.dim > 1) {
         s1 = fabs((ay + S.L) - (by + S.L));
-        s2 = s1 - p * floor(s1 / p);
+        s2 = s1 < p ? s1 : s1 - p * floor(s1 / p);
         s3 = s2 < p - s2 ? s2 : p - s2;
         acc = acc + s3 * s3;
     }
@@ -254,19 +283,52 @@ __device__ __forceinline__ void d_cell_update(const DevSys &S, int c, int j, int
     d_cell_remove(S, c, j, n);
     d_cell_insert(S, c, j, n, d_bin(S, x, y));
 }
-// find_nn (:156-179): nearest stencil occupant (periodic metric on +L shifted coordinates), -1 if none
-__device__ __forceinline__ int d_find_nn(const DevSys &S, int c, double x, double y, int j, int exc)
+// Stencil prefetch: the (up to) nine list heads of a query are independent loads, and so are the position / successor of the first
+// occupant of every non-empty cell.  Issuing them together turns the 9..18 dependent HBM round trips of a naive stencil walk into
+// two; longer lists (rare at the cell widths of the examples) continue with dependent loads.  Visiting order is unchanged.
+struct NbFirst { int h[9], n[9]; double x[9], y[9]; };
+__device__ __forceinline__ void d_nb_first(const DevSys &S, int c, int j, int b, NbFirst &F)
 {
-    int b = d_bin(S, x, y), nst = S.dim == 2 ? 9 : 3, best = -1;
-    double bd = 0.0;
+    const int nst = S.dim == 2 ? 9 : 3;
     const int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell;
     const int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
-    for (int q = 0; q < nst; ++q)
-        for (int p = head[d_stencil(S, b, q)]; p >= 0; p = nxt[p]) {
-            if (p == exc) continue;
-            double d = d_peuclid(S, S.r[RIDX(S, c, p, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, p, 1, j)] : 0.0, x, y);
-            if (best < 0 || d < bd) { best = p; bd = d; }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) F.h[q] = q < nst ? head[d_stencil(S, b, q)] : -1;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        F.n[q] = -1; F.x[q] = 0.0; F.y[q] = 0.0;
+        if (F.h[q] >= 0) {
+            F.n[q] = nxt[F.h[q]];
+            F.x[q] = S.r[RIDX(S, c, F.h[q], 0, j)];
+            if (S.dim > 1) F.y[q] = S.r[RIDX(S, c, F.h[q], 1, j)];
         }
+    }
+}
+// iterate the stencil occupants in bin_neighbors order (:55-65): BODY sees o (occupant), ox, oy (its position at slice j)
+#define PIMC_FOR_STENCIL(S_, c_, j_, F_, ...)                                                                       \
+    _Pragma("unroll") for (int q_ = 0; q_ < 9; ++q_) {                                                               \
+        int o = (F_).h[q_], on_ = (F_).n[q_]; double ox = (F_).x[q_], oy = (F_).y[q_];                                \
+        while (o >= 0) {                                                                                             \
+            __VA_ARGS__                                                                                              \
+            o = on_;                                                                                                 \
+            if (o >= 0) {                                                                                            \
+                on_ = (S_).cell_next[((size_t)(c_) * (S_).M + (j_)) * (S_).N + o];                                   \
+                ox = (S_).r[RIDX(S_, c_, o, 0, j_)]; oy = (S_).dim > 1 ? (S_).r[RIDX(S_, c_, o, 1, j_)] : 0.0;       \
+            }                                                                                                        \
+        }                                                                                                            \
+    }
+// find_nn (:156-179): nearest stencil occupant (periodic metric on +L shifted coordinates), -1 if none
+__device__ __noinline__ int d_find_nn(const DevSys &S, int c, double x, double y, int j, int exc)
+{
+    int best = -1;
+    double bd = 0.0;
+    NbFirst F; d_nb_first(S, c, j, d_bin(S, x, y), F);
+    PIMC_FOR_STENCIL(S, c, j, F, {
+        if (o != exc) {
+            double d = d_peuclid(S, ox, oy, x, y);
+            if (best < 0 || d < bd) { best = o; bd = d; }
+        }
+    })
     return best;
 }
 // hard-core test used by hardspherelevy! (helper.jl:167-170) and move_polymer! (helper.jl:385-390)

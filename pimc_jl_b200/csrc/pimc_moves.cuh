@@ -11,47 +11,42 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // pair action: interaction_action! (helper.jl:306-366) and the inlined copies of ReshapeSwapLinear (reshape.jl:166-199 old
 // configuration, :209-240 new configuration)
-__device__ __forceinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl)
+__device__ __noinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl)
 {
     // find_nns(s, p, sl, exceptions=[p]) with the STORED bin of p, then lnU of (bead, next bead) distances
     double w = 0.0;
-    const int M = S.M, nst = S.dim == 2 ? 9 : 3;
+    const int M = S.M;
     double x = S.r[RIDX(S, c, p, 0, sl)], y = S.dim > 1 ? S.r[RIDX(S, c, p, 1, sl)] : 0.0;
     int b = S.bins[VIDX(S, c, p, sl)];
-    const int *head = S.cell_head + ((size_t)c * M + sl) * S.ncell;
-    const int *nxt = S.cell_next + ((size_t)c * M + sl) * S.N;
     int pn = sl == M - 1 ? S.next[(size_t)c * S.N + p] : p, sn = (sl + 1) % M;
     double xn = S.r[RIDX(S, c, pn, 0, sn)], yn = S.dim > 1 ? S.r[RIDX(S, c, pn, 1, sn)] : 0.0;
-    for (int q = 0; q < nst; ++q)
-        for (int o = head[d_stencil(S, b, q)]; o >= 0; o = nxt[o]) {
-            if (o == p) continue;
-            double ox = S.r[RIDX(S, c, o, 0, sl)], oy = S.dim > 1 ? S.r[RIDX(S, c, o, 1, sl)] : 0.0;
-            if (!(d_peuclid(S, ox, oy, x, y) <= S.cellw)) continue;
-            int on = sl == M - 1 ? S.next[(size_t)c * S.N + o] : o;
-            double oxn = S.r[RIDX(S, c, on, 0, sn)], oyn = S.dim > 1 ? S.r[RIDX(S, c, on, 1, sn)] : 0.0;
+    NbFirst F; d_nb_first(S, c, sl, b, F);
+    PIMC_FOR_STENCIL(S, c, sl, F, {
+        if (o != p && d_peuclid(S, ox, oy, x, y) <= S.cellw) {
+            int onx = sl == M - 1 ? S.next[(size_t)c * S.N + o] : o;
+            double oxn = S.r[RIDX(S, c, onx, 0, sn)], oyn = S.dim > 1 ? S.r[RIDX(S, c, onx, 1, sn)] : 0.0;
             double lu = d_lnU(S, d_distance(ox, x, S.L), d_distance(oy, y, S.L), d_distance(oxn, xn, S.L), d_distance(oyn, yn, S.L));
             for (int rep = S.mult[VIDX(S, c, o, sl)]; rep > 0; --rep) w += lu;
         }
+    })
     return w;
 }
-__device__ __forceinline__ double d_pairs_new(const DevSys &S, int c, double x, double y, double xn, double yn, int sl, int e1, int e2, bool skip_next_exc)
+__device__ __noinline__ double d_pairs_new(const DevSys &S, int c, double x, double y, double xn, double yn, int sl, int e1, int e2, bool skip_next_exc)
 {
     double w = 0.0;
-    const int M = S.M, nst = S.dim == 2 ? 9 : 3;
-    int b = d_bin(S, x, y), sn = (sl + 1) % M;
-    const int *head = S.cell_head + ((size_t)c * M + sl) * S.ncell;
-    const int *nxt = S.cell_next + ((size_t)c * M + sl) * S.N;
-    for (int q = 0; q < nst; ++q)
-        for (int o = head[d_stencil(S, b, q)]; o >= 0; o = nxt[o]) {
-            if (o == e1 || o == e2) continue;
-            double ox = S.r[RIDX(S, c, o, 0, sl)], oy = S.dim > 1 ? S.r[RIDX(S, c, o, 1, sl)] : 0.0;
-            if (!(d_peuclid(S, ox, oy, x, y) <= S.cellw)) continue;
-            int on = sl == M - 1 ? S.next[(size_t)c * S.N + o] : o;
-            if (skip_next_exc && (on == e1 || on == e2)) continue;
-            double oxn = S.r[RIDX(S, c, on, 0, sn)], oyn = S.dim > 1 ? S.r[RIDX(S, c, on, 1, sn)] : 0.0;
-            double lu = d_lnU(S, d_distance(ox, x, S.L), d_distance(oy, y, S.L), d_distance(oxn, xn, S.L), d_distance(oyn, yn, S.L));
-            for (int rep = S.mult[VIDX(S, c, o, sl)]; rep > 0; --rep) w += lu;
+    const int M = S.M;
+    int sn = (sl + 1) % M;
+    NbFirst F; d_nb_first(S, c, sl, d_bin(S, x, y), F);
+    PIMC_FOR_STENCIL(S, c, sl, F, {
+        if (o != e1 && o != e2 && d_peuclid(S, ox, oy, x, y) <= S.cellw) {
+            int onx = sl == M - 1 ? S.next[(size_t)c * S.N + o] : o;
+            if (!(skip_next_exc && (onx == e1 || onx == e2))) {
+                double oxn = S.r[RIDX(S, c, onx, 0, sn)], oyn = S.dim > 1 ? S.r[RIDX(S, c, onx, 1, sn)] : 0.0;
+                double lu = d_lnU(S, d_distance(ox, x, S.L), d_distance(oy, y, S.L), d_distance(oxn, xn, S.L), d_distance(oyn, yn, S.L));
+                for (int rep = S.mult[VIDX(S, c, o, sl)]; rep > 0; --rep) w += lu;
+            }
         }
+    })
     return w;
 }
 
@@ -302,25 +297,46 @@ __device__ __forceinline__ int d_com_warp(const DevSys &S, int c, int n, double 
 }
 
 // ---- Energy functor (measurement.jl:92-122), whole CTA; result valid in thread 0. red = 3 * 32 doubles of shared memory.
+// A warp owns a worldline; every lane first issues the loads of EST_U beads and of their successors (independent, coalesced; the
+// successor loads hit the lines just fetched), then does the arithmetic: inside the persistent kernel a chain has one or two warps
+// and the estimator is bound by memory latency, so the loads in flight per lane are what counts.
+#define EST_U 4
 __device__ __forceinline__ void d_energy_block(const DevSys &S, int c, double *red, double *E, double *Ev, double *parts)
 {
     const int M = S.M, N = S.N, dim = S.dim;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     double link = 0.0, pot = 0.0, vkin = 0.0;
-    for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
-        int i = idx / M, j = idx - i * M;
-        int in = j == M - 1 ? S.next[(size_t)c * N + i] : i, jn = j == M - 1 ? 0 : j + 1;
-        double ax = S.r[RIDX(S, c, i, 0, j)], ay = dim > 1 ? S.r[RIDX(S, c, i, 1, j)] : 0.0;
-        double bx = S.r[RIDX(S, c, in, 0, jn)], by = dim > 1 ? S.r[RIDX(S, c, in, 1, jn)] : 0.0;
-        double dr = d_distance(ax, bx, S.L), d2 = dr * dr;
-        if (dim > 1) { dr = d_distance(ay, by, S.L); d2 = d2 + dr * dr; }
-        link += d2;
-        pot += d_pot(S.pot, ax, ay, dim) + d_pot(S.pot, bx, by, dim);
-        vkin += d_rdv(S.pot, ax, ay, dim);
+    for (int i = w; i < N; i += nw) {
+        const int in = S.next[(size_t)c * N + i];
+        const double *xr = S.r + RIDX(S, c, i, 0, 0), *yr = xr + M;
+        const double *xn = S.r + RIDX(S, c, in, 0, 0), *yn = xn + M;
+        for (int jb = 0; jb < M; jb += 32 * EST_U) {
+            double ax[EST_U], ay[EST_U], bx[EST_U], by[EST_U];
+#pragma unroll
+            for (int u = 0; u < EST_U; ++u) {
+                const int j = jb + 32 * u + lane;
+                ax[u] = ay[u] = bx[u] = by[u] = 0.0;
+                if (j < M) {
+                    ax[u] = xr[j]; bx[u] = j == M - 1 ? xn[0] : xr[j + 1];
+                    if (dim > 1) { ay[u] = yr[j]; by[u] = j == M - 1 ? yn[0] : yr[j + 1]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EST_U; ++u) {
+                const int j = jb + 32 * u + lane;
+                if (j < M) {
+                    double dr = d_distance(ax[u], bx[u], S.L), d2 = dr * dr;
+                    if (dim > 1) { dr = d_distance(ay[u], by[u], S.L); d2 = d2 + dr * dr; }
+                    link += d2;
+                    pot += d_pot(S.pot, ax[u], ay[u], dim) + d_pot(S.pot, bx[u], by[u], dim);
+                    vkin += d_rdv(S.pot, ax[u], ay[u], dim);
+                }
+            }
+        }
     }
     link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
-    int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[w] = link; red[32 + w] = pot; red[64 + w] = vkin; }
+    if (lane == 0) { red[w] = link; red[32 + w] = pot; red[64 + w] = vkin; }
     __syncthreads();
     if (threadIdx.x == 0) {
         link = 0.0; pot = 0.0; vkin = 0.0;
@@ -331,19 +347,47 @@ __device__ __forceinline__ void d_energy_block(const DevSys &S, int c, double *r
     }
 }
 
-// ---- Density functor (measurement.jl:45-55), whole CTA, integer counters in HBM (column-major like the Julia array)
+// ---- Density functor (measurement.jl:45-55), whole CTA, integer counters in HBM (column-major like the Julia array).
+// ibin = floor((r + L) / bin) (measurement.jl:47): evaluated as floor((r + L) * (1 / bin)), and re-evaluated with the true division
+// whenever the product lies within a few ulps of an integer -- the only case in which the two floors can differ.  A warp owns a
+// worldline and loads EST_U beads per lane before binning them (see d_energy_block).
+__device__ __forceinline__ long long d_density_bin(double x, double L, double bin, double inv)
+{
+    const double s = x + L, t = s * inv;
+    double f = floor(t);
+    const double fr = t - f, thr = (fabs(t) + 1.0) * 4e-15;
+    if (fr < thr || 1.0 - fr < thr) f = floor(s / bin);
+    return (long long)f;
+}
 __device__ __forceinline__ void d_density_block(const DevSys &S, int c, const DeDev &D)
 {
     const int M = S.M, N = S.N, dim = S.dim;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     const bool shift = (S.compat & PIMC_COMPAT_DENSITY_SHIFT) != 0;
-    for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
-        int i = idx / M, j = idx - i * M;
-        long long ib0 = (long long)floor((S.r[RIDX(S, c, i, 0, j)] + S.L) / D.bin);
-        long long ib1 = dim > 1 ? (long long)floor((S.r[RIDX(S, c, i, 1, j)] + S.L) / D.bin) : 1;
-        bool ok;
-        if (shift) ok = ib0 > 0 && ib0 < D.nbins + 1 && (dim == 1 || (ib1 > 0 && ib1 < D.nbins + 1));
-        else { ok = ib0 >= 0 && ib0 < D.nbins && (dim == 1 || (ib1 >= 0 && ib1 < D.nbins)); ib0 += 1; ib1 += 1; }
-        if (ok) atomicAdd(D.dens + (ib0 - 1) + (dim > 1 ? D.nbins * (ib1 - 1) : 0), 1ull);
+    const double inv = 1.0 / D.bin;
+    for (int i = w; i < N; i += nw) {
+        const double *xr = S.r + RIDX(S, c, i, 0, 0), *yr = xr + M;
+        for (int jb = 0; jb < M; jb += 32 * EST_U) {
+            double xv[EST_U], yv[EST_U];
+#pragma unroll
+            for (int u = 0; u < EST_U; ++u) {
+                const int j = jb + 32 * u + lane;
+                xv[u] = yv[u] = 0.0;
+                if (j < M) { xv[u] = xr[j]; if (dim > 1) yv[u] = yr[j]; }
+            }
+#pragma unroll
+            for (int u = 0; u < EST_U; ++u) {
+                const int j = jb + 32 * u + lane;
+                if (j < M) {
+                    long long ib0 = d_density_bin(xv[u], S.L, D.bin, inv);
+                    long long ib1 = dim > 1 ? d_density_bin(yv[u], S.L, D.bin, inv) : 1;
+                    bool ok;
+                    if (shift) ok = ib0 > 0 && ib0 < D.nbins + 1 && (dim == 1 || (ib1 > 0 && ib1 < D.nbins + 1));
+                    else { ok = ib0 >= 0 && ib0 < D.nbins && (dim == 1 || (ib1 >= 0 && ib1 < D.nbins)); ib0 += 1; ib1 += 1; }
+                    if (ok) atomicAdd(D.dens + (ib0 - 1) + (dim > 1 ? D.nbins * (ib1 - 1) : 0), 1ull);
+                }
+            }
+        }
     }
 }
 
@@ -354,13 +398,13 @@ __device__ __forceinline__ void d_ring_push(const UpdDev &U, int c, RingReg &R, 
     unsigned *ring = U.ring + (size_t)c * U.ring_words;
     long long cap = U.range + 1;
     R.tries += 1;
-    long long pos = ((long long)R.head + R.len) % cap;
+    long long pos = (long long)R.head + R.len; if (pos >= cap) pos -= cap;   // head < cap, len <= range = cap - 1
     unsigned bit = 1u << (pos & 31);
     if (acc) ring[pos >> 5] |= bit; else ring[pos >> 5] &= ~bit;
     R.len += 1; R.sum += acc ? 1 : 0;
     if (R.len > U.range) {
         R.sum -= (ring[R.head >> 5] >> (R.head & 31)) & 1u;
-        R.head = (int)(((long long)R.head + 1) % cap);
+        R.head = R.head + 1 >= cap ? 0 : R.head + 1;
         R.len -= 1;
     }
 }

@@ -206,15 +206,18 @@ def _mk_updates(ob, e, s_list, spec):
     return ge, oo
 
 
-@pytest.mark.parametrize("sched,impl", [(L.SCHED_FAITHFUL, 0), (L.SCHED_SWEEP, 1), (L.SCHED_SWEEP, 2)],
-                         ids=["faithful", "sweep-persistent", "sweep-batched"])
+@pytest.mark.parametrize("sched,impl", [(L.SCHED_FAITHFUL, 0), (L.SCHED_FAITHFUL, -1), (L.SCHED_SWEEP, 1), (L.SCHED_SWEEP, 2)],
+                         ids=["faithful", "faithful-one-thread", "sweep-persistent", "sweep-batched"])
 @pytest.mark.parametrize("cfg", CONFIGS + [dict(pot="harmonic", dim=2, M=40, N=70, L=6.0, T=0.5, lam=0.5, Ncycle=4)], ids=lambda c: f"{c['pot']}-N{c['N']}-M{c['M']}")
 def test_run_trajectory_bit_exact(oracle, cfg, sched, impl):
     """Same seed, same schedule: the GPU Markov chains follow the oracle's chains bit for bit, including the adaptive
     step / slice variables, acceptance windows, and the measured energies / density histograms."""
     ob = oracle
     e, os_ = make_pair(ob, cfg, chains=3, seed=21)
-    e.set_option(L.OPT_SWEEP_IMPL, impl)
+    if impl < 0:
+        e.set_option(L.OPT_FAITHFUL_IMPL, 1)  # one thread per proposal (pimc_moves.cuh) instead of the warp-cooperative bodies
+    else:
+        e.set_option(L.OPT_SWEEP_IMPL, impl)
     spec = [(2, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 6)]
     if cfg["N"] > 1:
         spec += [(1, L.UPD_RESHAPE_SWAP, 5), (3, L.UPD_POLYMER_COM, 0.7)]
@@ -287,13 +290,15 @@ def synthetic_table(n=64, hi=12.0):
     return -0.004 * np.exp(-0.5 * (X + Y)) * (1 + 0.3 * np.cos(X - Y)), 1e-3, hi
 
 
+@pytest.mark.parametrize("fimpl", [0, 1], ids=["warp", "one-thread"])
 @pytest.mark.parametrize("compat", [L.COMPAT_ALL, L.COMPAT_PAIR_BYVALUE | L.COMPAT_DENSITY_SHIFT, 0], ids=["as-shipped", "swap-fixes", "intended"])
-def test_interacting_faithful_cell_list(oracle, compat):
+def test_interacting_faithful_cell_list(oracle, compat, fimpl):
     """Hard core a > 0, pair action through the lnU table, cell list queries: faithful schedule against the oracle."""
     ob = oracle
     tab, lo, hi = synthetic_table()
     cfg = dict(pot="harmonic", dim=2, M=10, N=8, L=4.0, T=0.5, lam=0.5, Ncycle=2)
     e, os_ = make_pair(ob, cfg, chains=2, seed=77, interactions=True, g=1.6, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    e.set_option(L.OPT_FAITHFUL_IMPL, fimpl)
     assert e.a > 0 and e.a == os_[0].a and e.nbins == os_[0].nbins == 8
     _sync_paths(e, os_)
     rng = np.random.default_rng(4)
@@ -328,6 +333,52 @@ def test_interacting_faithful_cell_list(oracle, compat):
         assert acc == acc_o and close(gwi, wi.value, 1e-11, 1e-12) and close(gwu, wu.value, 1e-11, 1e-12), (t, gwi, wi.value, gwu, wu.value)
     with pytest.raises(pj.PimcError):
         e.run(10, ge, sched=L.SCHED_SWEEP)
+
+
+@pytest.mark.parametrize("compat", [L.COMPAT_ALL, 0], ids=["as-shipped", "intended"])
+@pytest.mark.parametrize("cfg,g,n_it", [
+    (dict(pot="harmonic", dim=2, M=40, N=24, L=3.0, T=0.5, lam=0.5, Ncycle=3), 3.5, 500),   # a = 0.166: dense, hard-core redraws and failed bridges
+    (dict(pot="zero", dim=2, M=48, N=36, L=4.0, T=1.0, lam=1.0, Ncycle=4), 2.4, 400),       # windows longer than a warp (m up to 46)
+    (dict(pot="sin2", dim=1, M=12, N=5, L=4.0, T=1.0, lam=1.0, Ncycle=3), 2.0, 300),        # 1-D: three-cell stencil
+], ids=["dense-hardcore", "long-windows", "one-dim"])
+def test_interacting_faithful_warp_stress(oracle, cfg, g, n_it, compat):
+    """The warp-cooperative proposals (pimc_faithful.cuh) on denser systems: speculative hard-core bridges with redraws, pair sums of
+    many neighbours per slice, windows longer than 32 slices, cycle-merging swaps; measured Energy and Density included."""
+    ob = oracle
+    tab, lo, hi = synthetic_table()
+    e, os_ = make_pair(ob, cfg, chains=3, seed=123, interactions=True, g=g, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    assert e.a > 0 and e.a == os_[0].a
+    exact = cfg["pot"] in ("zero", "harmonic")
+    _sync_paths(e, os_, exact)
+    m0 = cfg["M"] - 2
+    spec = [(2, L.UPD_SINGLE_COM, 0.4), (1, L.UPD_RESHAPE_LINEAR, m0), (1, L.UPD_RESHAPE_SWAP, m0), (3, L.UPD_POLYMER_COM, 0.3)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    en_id, de_id = e.energy_create(1000), e.density_create(24)
+    oen = [ob.Energy(1000) for _ in os_]
+    ode = [ob.Density(s, 24) for s in os_]
+    st = e.run(n_it, ge, energies=[en_id], densities=[de_id])
+    for s, ups, en, de in zip(os_, oo, oen, ode):
+        s.run(n_it, ups, energies=[en], densities=[de])
+    _sync_paths(e, os_, exact)
+    for (_, uid), k in zip(ge, range(len(spec))):
+        for c in range(3):
+            gq, o = e.update_get(uid, c), oo[c][k][1].get()
+            assert gq["tries"] == o["tries"] and gq["accepted"] == o["accepted"] and gq["var"] == o["var"] and gq["bead_moves"] == o["bead_moves"], (k, c, gq, o)
+    scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+    for c in range(3):
+        E, Ev, n = e.energy_read(en_id, c)
+        Eo, Evo = oen[c].read()
+        assert n == len(Eo) and np.all(np.abs(E - Eo) <= 1e-12 * scale)
+    dg, ndg, _ = e.density_read(de_id, 24)
+    assert np.array_equal(dg, sum(d.read()[0] for d in ode))
+    # the one-thread bodies give the same bits from the same start
+    e2, _ = make_pair(ob, cfg, chains=3, seed=123, interactions=True, g=g, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    e2.set_option(L.OPT_FAITHFUL_IMPL, 1)
+    ge2 = [(every, e2.update_create(kind, v0)) for every, kind, v0 in spec]
+    e2.run(n_it, ge2, energies=[e2.energy_create(1000)], densities=[e2.density_create(24)])   # measuring runs cap redraws at 1000 (simulation.jl:31-32)
+    r1, V1, b1, n1 = e.paths()
+    r2, V2, b2, n2 = e2.paths()
+    assert np.array_equal(r1, r2) and np.array_equal(V1, V2) and np.array_equal(b1, b2) and np.array_equal(n1, n2)
 
 
 @pytest.mark.parametrize("impl", [1, 2], ids=["sweep-persistent", "sweep-batched"])
