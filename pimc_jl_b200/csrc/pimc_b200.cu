@@ -137,7 +137,7 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
     for (int c = blockIdx.x; c < S.C; c += gridDim.x) {
         for (long long it = 0; it < P.n; ++it) {
             pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter0 + (unsigned long long)it);
-            pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+            pimc_u4 di = f_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
             int pick = d_sample_weighted(P.w, P.nupd, pimc_u01_co(di.w[0], di.w[1]));
             const UpdDev &U = T->upd[P.upd_id[pick]];
             const double var = U.var[c];
@@ -149,8 +149,8 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
 
             if (U.kind == PIMC_UPD_RESHAPE_LINEAR && !sweep && P.fimpl == 0) {
                 if (warp == 0) { // one proposal, the whole warp on it (pimc_faithful.cuh)
-                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
                     int n = (int)pimc_index(dt.w[0], (uint32_t)N);
                     int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
                     int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
@@ -161,9 +161,9 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
                 }
             } else if (U.kind == PIMC_UPD_RESHAPE_SWAP && P.fimpl == 0) {
                 if (warp == 0 && N > 1) {
-                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    pimc_u4 dsw = pimc_draw(st, 0, PIMC_K_SWAP, 0, 0);
+                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    pimc_u4 dsw = f_draw(st, 0, PIMC_K_SWAP, 0, 0);
                     int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
                     int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
                     int m = (int)U.vmax < mm ? (int)U.vmax : mm;
@@ -231,8 +231,8 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
                         if (lane == 0) { flag[slot] = r == 1 ? 1 : 0; atomicAdd(&s_bead, (unsigned long long)M * npol); }
                     }
                 } else if (P.fimpl == 0) { // one proposal, the whole CTA on it (hard-core tests of all beads: pimc_faithful.cuh)
-                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
+                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
+                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
                     int n = -1;
                     if (polymer) n = (int)pimc_index(dt.w[0], (uint32_t)N);
                     else { // uniform among particles with next == self (com.jl:144-164)
@@ -243,7 +243,7 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
                     else {
                         DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = 0;
                         int npol = 1;
-                        int r = d_com_cta(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol);
+                        int r = d_com_cta(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol, fscr, fs_doubles);
                         if (tid == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)M * npol; }
                     }
                 } else if (warp == 0) {

@@ -306,7 +306,7 @@ __device__ __forceinline__ void d_nb_first(const DevSys &S, int c, int j, int b,
 }
 // iterate the stencil occupants in bin_neighbors order (:55-65): BODY sees o (occupant), ox, oy (its position at slice j)
 #define PIMC_FOR_STENCIL(S_, c_, j_, F_, ...)                                                                       \
-    _Pragma("unroll") for (int q_ = 0; q_ < 9; ++q_) {                                                               \
+    _Pragma("unroll 1") for (int q_ = 0; q_ < 9; ++q_) {   /* one copy of the body: code size (instruction fetch) over registers */ \
         int o = (F_).h[q_], on_ = (F_).n[q_]; double ox = (F_).x[q_], oy = (F_).y[q_];                                \
         while (o >= 0) {                                                                                             \
             __VA_ARGS__                                                                                              \

@@ -18,6 +18,18 @@
 #define FA_ARR 6
 __host__ __device__ inline size_t faithful_scratch_doubles(int N, int M) { return (size_t)((N + 1) & ~1) + 2 * FA_ARR * (size_t)(M + 1); }
 
+// ---- out-of-line leaves.  The persistent reference-schedule kernel runs ONE warp per proposal through long straight-line code:
+// with every helper inlined at every call site the kernel was 1.2 MB of SASS and the warps stalled on instruction fetch
+// (ncu: 28.6 cycles of "no instruction" per issue, profiles/r01e_*).  One shared copy of each helper keeps the hot code of all
+// proposal kinds within the instruction caches.  Same arithmetic, same bits.
+__device__ __noinline__ pimc_u4 f_draw(pimc_stream st, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead) { return pimc_draw(st, slot, kind, retry, bead); }
+__device__ __noinline__ double2 f_gauss(const GSrc &g, int dim, int bead, int retry) { double a, b; d_gauss(g, dim, bead, retry, a, b); return make_double2(a, b); }
+__device__ __noinline__ double f_teleport(double x, double L) { return d_teleport_q(x, L); }
+__device__ __noinline__ double f_exp(double x) { return pimc_exp(x); }
+__device__ __noinline__ double f_lnK2(double ax, double ay, double bx, double by, int dim, double tau, double lambda, double L) { return d_lnK2(ax, ay, bx, by, dim, tau, lambda, L); }
+__device__ __noinline__ bool f_hardcore_hit(const DevSys &S, int c, double x, double y, int j, int exc) { return d_hardcore_hit(S, c, x, y, j, exc); }
+__device__ __noinline__ void f_cell_update(const DevSys &S, int c, int j, int n, double x, double y) { d_cell_update(S, c, j, n, x, y); }
+
 __device__ __forceinline__ int warp_min_int(int v)
 {
 #pragma unroll
@@ -27,7 +39,7 @@ __device__ __forceinline__ int warp_min_int(int v)
 
 // hardspherelevy! (helper.jl:141-181); == levy! (helper.jl:118-139) when a == 0.  Every lane passes the same arguments.
 // bb: x = bb, y = bb + R1, v = bb + 2 R1 (receives V(row)), gx = bb + 4 R1, gy = bb + 5 R1.  Returns 1, or 0 when a bead exhausted s.ctr.
-__device__ __forceinline__ int d_bridge_w(const DevSys &S, int c, double bx, double by, double ex, double ey, int rows, int j0,
+__device__ __noinline__ int d_bridge_w(const DevSys &S, int c, double bx, double by, double ex, double ey, int rows, int j0,
                                           int exc, const GSrc &g, double *bb, int R1)
 {
     const int lane = threadIdx.x & 31, dim = S.dim, m = rows - 2;
@@ -38,65 +50,69 @@ __device__ __forceinline__ int d_bridge_w(const DevSys &S, int c, double bx, dou
     for (int j = 1 + lane; j <= m; j += 32) {              // retry-0 draws of every interior bead, scaled by sigma_j; alpha_j parked in v
         const double alpha = (double)(m + 1 - j) / (double)(m + 2 - j);
         const double sig = sqrt(2 * S.lambda * alpha * S.tau);
-        double g0, g1; d_gauss(g, dim, j, 0, g0, g1);
+        const double2 gg = f_gauss(g, dim, j, 0); const double g0 = gg.x, g1 = gg.y;
         gx[j] = g0 * sig; gy[j] = dim > 1 ? g1 * sig : 0.0; pv[j] = alpha;
     }
     __syncwarp();
-    {                                                      // the recurrence (helper.jl:128-135), un-teleported rows
-        double qx = bx, qy = by;
-        if (lane == 0) { px[0] = bx; py[0] = by; px[rows - 1] = ex; py[rows - 1] = ey; }
-        for (int j = 1; j <= m; ++j) {
-            const double alpha = pv[j], om = 1 - alpha;
-            qx = alpha * qx + om * ex + gx[j];
-            if (dim > 1) qy = alpha * qy + om * ey + gy[j];
-            if (lane == 0) { px[j] = qx; py[j] = qy; }
-        }
-    }
-    __syncwarp();
-    for (int row = lane; row < rows; row += 32) {          // teleport every row incl. both endpoints (helper.jl:136-138)
-        px[row] = d_teleport_q(px[row], L);
-        py[row] = dim > 1 ? d_teleport_q(py[row], L) : 0.0;
-    }
-    __syncwarp();
-    if (S.a > 0.0) {
-        int jf = 0x7fffffff;
-        for (int j = 1 + lane; j <= m; j += 32) {
-            const int sl = (j0 + j - 1) % S.M;             // mod1(j0 + j, M) - 1
-            if (d_hardcore_hit(S, c, px[j], py[j], sl, exc) && j < jf) jf = j;
-        }
-        jf = warp_min_int(jf);
-        if (jf <= m) {                                     // redraw loop from the first rejected bead on (helper.jl:160-176), warp-uniform
-            double qx = bx, qy = by;
-            for (int j = 1; j < jf; ++j) {
+    // Speculate -> test -> repair, repeated: lay rows jstart..m with the retry-0 draws (helper.jl:128-135), teleport and test them all
+    // at once (a lane per bead); if bead jf is the first to hit the hard core, redraw THAT bead serially (helper.jl:160-176) and
+    // speculate again from jf + 1.  Beads behind jf always start from their retry-0 draw, exactly as the serial loop does.
+    double sx0 = bx, sy0 = by;                             // un-teleported row jstart - 1
+    int jstart = 1;
+    if (lane == 0) { px[0] = f_teleport(bx, L); py[0] = dim > 1 ? f_teleport(by, L) : 0.0; px[rows - 1] = f_teleport(ex, L); py[rows - 1] = dim > 1 ? f_teleport(ey, L) : 0.0; }
+    while (jstart <= m) {
+        {
+            double qx = sx0, qy = sy0;
+            for (int j = jstart; j <= m; ++j) {
                 const double alpha = pv[j], om = 1 - alpha;
                 qx = alpha * qx + om * ex + gx[j];
                 if (dim > 1) qy = alpha * qy + om * ey + gy[j];
+                if (lane == 0) { px[j] = qx; py[j] = qy; }
             }
-            for (int j = jf; j <= m; ++j) {
-                const double alpha = pv[j], om = 1 - alpha;
-                const double sig = sqrt(2 * S.lambda * alpha * S.tau);
-                const int sl = (j0 + j - 1) % S.M;
-                double nx = 0.0, ny = 0.0, tx = 0.0, ty = 0.0; long long ctr = 0; bool pass = true;
-                while (pass) {
-                    pass = false; ctr += 1;
-                    if (ctr > S.ctr) { pass = true; break; }
-                    double sx, sy;
-                    if (ctr == 1) { sx = gx[j]; sy = gy[j]; }
-                    else { double g0, g1; d_gauss(g, dim, j, (int)(ctr - 1), g0, g1); sx = g0 * sig; sy = g1 * sig; }
-                    nx = alpha * qx + om * ex + sx;
-                    if (dim > 1) ny = alpha * qy + om * ey + sy;
-                    tx = d_teleport_q(nx, L); ty = dim > 1 ? d_teleport_q(ny, L) : 0.0;
-                    if (d_hardcore_hit(S, c, tx, ty, sl, exc)) pass = true;
-                }
-                if (pass) return 0;
-                qx = nx; qy = ny;
-                __syncwarp();
-                if (lane == 0) { px[j] = tx; py[j] = ty; }
-            }
-            __syncwarp();
         }
+        __syncwarp();
+        for (int j = jstart + lane; j <= m; j += 32) {     // teleport (helper.jl:136-138)
+            px[j] = f_teleport(px[j], L);
+            py[j] = dim > 1 ? f_teleport(py[j], L) : 0.0;
+        }
+        __syncwarp();
+        if (!(S.a > 0.0)) break;
+        int jf = 0x7fffffff;
+        for (int j = jstart + lane; j <= m; j += 32) {
+            const int sl = (j0 + j - 1) % S.M;             // mod1(j0 + j, M) - 1
+            if (f_hardcore_hit(S, c, px[j], py[j], sl, exc) && j < jf) jf = j;
+        }
+        jf = warp_min_int(jf);
+        if (jf > m) break;
+        for (int j = jstart; j < jf; ++j) {                // un-teleported row jf - 1
+            const double alpha = pv[j], om = 1 - alpha;
+            sx0 = alpha * sx0 + om * ex + gx[j];
+            if (dim > 1) sy0 = alpha * sy0 + om * ey + gy[j];
+        }
+        {                                                  // bead jf: its retry-0 draw is known to hit; redraw (warp-uniform)
+            const double alpha = pv[jf], om = 1 - alpha;
+            const double sig = sqrt(2 * S.lambda * alpha * S.tau);
+            const int sl = (j0 + jf - 1) % S.M;
+            double nx = 0.0, ny = 0.0, tx = 0.0, ty = 0.0; long long ctr = 1; bool pass = true;
+            while (pass) {
+                pass = false; ctr += 1;
+                if (ctr > S.ctr) { pass = true; break; }
+                const double2 gg = f_gauss(g, dim, jf, (int)(ctr - 1));
+                nx = alpha * sx0 + om * ex + gg.x * sig;
+                if (dim > 1) ny = alpha * sy0 + om * ey + gg.y * sig;
+                tx = f_teleport(nx, L); ty = dim > 1 ? f_teleport(ny, L) : 0.0;
+                if (f_hardcore_hit(S, c, tx, ty, sl, exc)) pass = true;
+            }
+            if (pass) return 0;
+            sx0 = nx; sy0 = ny;
+            __syncwarp();
+            if (lane == 0) { px[jf] = tx; py[jf] = ty; }
+        }
+        jstart = jf + 1;
+        __syncwarp();
     }
-    for (int row = lane; row < rows; row += 32) pv[row] = d_pot(S.pot, px[row], py[row], dim);
+    __syncwarp();
+    for (int row = lane; row < rows; row += 32) pv[row] = f_pot(S.pot, px[row], py[row], dim);
     __syncwarp();
     return 1;
 }
@@ -140,7 +156,7 @@ __device__ __forceinline__ int d_reshape_linear_w(const DevSys &S, int c, int n,
             sv = jp == 1 ? lk[0] : sv + lk[jp - 1];
         }
         w_updated += sv;
-        ret = d_metropolis(pimc_exp(w_updated - w_initial), u) ? 1 : 0;
+        ret = d_metropolis(f_exp(w_updated - w_initial), u) ? 1 : 0;
     }
     ret = __shfl_sync(0xffffffffu, ret, 0);
     if (ret) {
@@ -150,7 +166,7 @@ __device__ __forceinline__ int d_reshape_linear_w(const DevSys &S, int c, int n,
             S.r[RIDX(S, c, p, 0, sl)] = px[jp - 1];
             if (dim > 1) S.r[RIDX(S, c, p, 1, sl)] = py[jp - 1];
             S.Vl[VIDX(S, c, p, sl)] = lk[jp - 1];
-            d_cell_update(S, c, sl, p, px[jp - 1], py[jp - 1]);               // one list per slice: lanes touch different lists
+            f_cell_update(S, c, sl, p, px[jp - 1], py[jp - 1]);               // one list per slice: lanes touch different lists
         }
         __syncwarp();
     }
@@ -170,9 +186,9 @@ __device__ __forceinline__ int d_sample_partner_w(const DevSys &S, int c, int n1
     const double cx = S.r[RIDX(S, c, n1next, 0, jmw)], cy = dim > 1 ? S.r[RIDX(S, c, n1next, 1, jmw)] : 0.0;
     for (int i = lane; i < N; i += 32) {
         const int inext = wrap ? nextc[i] : i;
-        const double t = d_lnK2(ax, ay, S.r[RIDX(S, c, inext, 0, jmw)], dim > 1 ? S.r[RIDX(S, c, inext, 1, jmw)] : 0.0, dim, S.lambda, mt, S.L);
-        const double y = d_lnK2(S.r[RIDX(S, c, i, 0, j0 - 1)], dim > 1 ? S.r[RIDX(S, c, i, 1, j0 - 1)] : 0.0, cx, cy, dim, S.lambda, mt, S.L);
-        w[i] = pimc_exp(t + y);
+        const double t = f_lnK2(ax, ay, S.r[RIDX(S, c, inext, 0, jmw)], dim > 1 ? S.r[RIDX(S, c, inext, 1, jmw)] : 0.0, dim, S.lambda, mt, S.L);
+        const double y = f_lnK2(S.r[RIDX(S, c, i, 0, j0 - 1)], dim > 1 ? S.r[RIDX(S, c, i, 1, j0 - 1)] : 0.0, cx, cy, dim, S.lambda, mt, S.L);
+        w[i] = f_exp(t + y);
     }
     __syncwarp();
     double norm = 0.0;
@@ -239,7 +255,7 @@ __device__ __forceinline__ int d_reshape_swap_w(const DevSys &S, int c, int n1, 
             }
         }
         w_updated += s1 + s2;
-        ret = d_metropolis(pimc_exp(w_updated - w_initial), u) ? 1 : 0;
+        ret = d_metropolis(f_exp(w_updated - w_initial), u) ? 1 : 0;
     }
     ret = __shfl_sync(0xffffffffu, ret, 0);
     if (ret) {
@@ -249,9 +265,9 @@ __device__ __forceinline__ int d_reshape_swap_w(const DevSys &S, int c, int n1, 
             const int j = j0 + jr - 1;
             const int q1 = j <= M ? n1 : x2, q2 = j <= M ? n2 : x1, sl = (j <= M ? j : j - M) - 1;
             S.r[RIDX(S, c, q1, 0, sl)] = b1[jr - 1]; if (dim > 1) S.r[RIDX(S, c, q1, 1, sl)] = b1[R1 + jr - 1];
-            d_cell_update(S, c, sl, q1, b1[jr - 1], b1[R1 + jr - 1]);
+            f_cell_update(S, c, sl, q1, b1[jr - 1], b1[R1 + jr - 1]);
             S.r[RIDX(S, c, q2, 0, sl)] = b2[jr - 1]; if (dim > 1) S.r[RIDX(S, c, q2, 1, sl)] = b2[R1 + jr - 1];
-            d_cell_update(S, c, sl, q2, b2[jr - 1], b2[R1 + jr - 1]);
+            f_cell_update(S, c, sl, q2, b2[jr - 1], b2[R1 + jr - 1]);
         }
         for (int jp = 1 + lane; jp <= m; jp += 32) {
             const int j = j0 + jp - 1;
@@ -266,8 +282,8 @@ __device__ __forceinline__ int d_reshape_swap_w(const DevSys &S, int c, int n1, 
                 }
                 const double tv = S.Vl[VIDX(S, c, n1, sl)]; S.Vl[VIDX(S, c, n1, sl)] = S.Vl[VIDX(S, c, n2, sl)]; S.Vl[VIDX(S, c, n2, sl)] = tv;
                 if (S.need_cells) {
-                    d_cell_update(S, c, sl, n1, S.r[RIDX(S, c, n1, 0, sl)], dim > 1 ? S.r[RIDX(S, c, n1, 1, sl)] : 0.0);
-                    d_cell_update(S, c, sl, n2, S.r[RIDX(S, c, n2, 0, sl)], dim > 1 ? S.r[RIDX(S, c, n2, 1, sl)] : 0.0);
+                    f_cell_update(S, c, sl, n1, S.r[RIDX(S, c, n1, 0, sl)], dim > 1 ? S.r[RIDX(S, c, n1, 1, sl)] : 0.0);
+                    f_cell_update(S, c, sl, n2, S.r[RIDX(S, c, n2, 0, sl)], dim > 1 ? S.r[RIDX(S, c, n2, 1, sl)] : 0.0);
                 }
             }
         __syncwarp();
@@ -305,7 +321,8 @@ __device__ __forceinline__ double block_sum(double v, double *red)
     __syncthreads();
     return red[32];
 }
-__device__ __forceinline__ int d_com_cta(const DevSys &S, int c, int n, double maxd, const DSrc &ds, double u, double *red, int *npol_out)
+__device__ __forceinline__ int d_com_cta(const DevSys &S, int c, int n, double maxd, const DSrc &ds, double u, double *red, int *npol_out,
+                                         double *scr, size_t scr_cap)
 {
     const int tid = threadIdx.x, nt = blockDim.x, M = S.M, N = S.N, dim = S.dim;
     const int *nextc = S.next + (size_t)c * N;
@@ -318,55 +335,87 @@ __device__ __forceinline__ int d_com_cta(const DevSys &S, int c, int n, double m
             }
             npol += 1; p = nextc[p]; } while (p != n && npol <= N); }
     const double w_initial = block_sum(part, red);
+    // short cycles: the displaced positions and their potentials are staged once (scr: x | y | V, npol * M each) and reused by the
+    // hard-core test, the action and the commit; longer cycles recompute them (same expressions, same bits)
+    const bool staged = (size_t)3 * npol * M <= scr_cap;
+    double *sx = scr, *sy = scr + (size_t)npol * M, *sv = scr + (size_t)2 * npol * M;
     double dx = 0.0, dy = 0.0; bool ok = false;
     for (long long ctr = 1; ctr <= S.ctr; ++ctr) {
-        pimc_u4 w = pimc_draw(ds.st, ds.slot, PIMC_K_COM, (uint32_t)(ctr - 1), 0);
+        pimc_u4 w = f_draw(ds.st, ds.slot, PIMC_K_COM, (uint32_t)(ctr - 1), 0);
         dx = maxd * 2 * (pimc_u01_co(w.w[0], w.w[1]) - 0.5);
         dy = maxd * 2 * (pimc_u01_co(w.w[2], w.w[3]) - 0.5);
         int hit = 0;
-        if (S.a > 0.0) {
+        if (S.a > 0.0 || staged) {
             int p = n, cnt = 0;
             do { for (int j = tid; j < M; j += nt) {
-                    double x = d_teleport_q(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
-                    if (d_hardcore_hit(S, c, x, y, j, p)) hit = 1;
+                    double x = f_teleport(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? f_teleport(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
+                    if (staged) { sx[(size_t)cnt * M + j] = x; sy[(size_t)cnt * M + j] = y; }
+                    if (S.a > 0.0 && f_hardcore_hit(S, c, x, y, j, p)) hit = 1;
                 }
                 p = nextc[p]; cnt++; } while (p != n && cnt <= N);
         }
         if (!__syncthreads_or(hit)) { ok = true; break; }
     }
     int ret = -1;
-    if (ok) {
+    if (ok && staged) {
+        const double mht = -0.5 * S.tau;
+        for (int idx = tid; idx < npol * M; idx += nt) sv[idx] = f_pot(S.pot, sx[idx], sy[idx], dim);
+        __syncthreads();
+        part = 0.0;
+        int p = n, k = 0;
+        do { const int kn = k + 1 == npol ? 0 : k + 1;
+            for (int j = tid; j < M; j += nt) {
+                const size_t a0 = (size_t)k * M + j, a1 = j == M - 1 ? (size_t)kn * M : a0 + 1;
+                part += mht * (sv[a0] + sv[a1]);
+                if (pairs) part += d_pairs_new(S, c, sx[a0], sy[a0], sx[a1], sy[a1], j, p, -1, false);
+            }
+            p = nextc[p]; k++; } while (p != n && k <= N);
+        const double w_updated = block_sum(part, red);
+        ret = d_metropolis(f_exp(w_updated - w_initial), u) ? 1 : 0;             // same value on every thread
+        if (ret == 1) {
+            p = n; k = 0;
+            do { const int kn = k + 1 == npol ? 0 : k + 1;
+                for (int j = tid; j < M; j += nt) {                               // a thread owns its slices: per-slice list order as in d_com_warp
+                    const size_t a0 = (size_t)k * M + j, a1 = j == M - 1 ? (size_t)kn * M : a0 + 1;
+                    S.Vl[VIDX(S, c, p, j)] = mht * (sv[a0] + sv[a1]);
+                    S.r[RIDX(S, c, p, 0, j)] = sx[a0]; if (dim > 1) S.r[RIDX(S, c, p, 1, j)] = sy[a0];
+                    f_cell_update(S, c, j, p, sx[a0], sy[a0]);
+                }
+                p = nextc[p]; k++; } while (p != n && k <= N);
+            __syncthreads();
+        }
+    } else if (ok) {
         const double mht = -0.5 * S.tau;
         part = 0.0;
         int p = n, cnt = 0;
         do { int pn = nextc[p];
             for (int j = tid; j < M; j += nt) {
                 int q = j == M - 1 ? pn : p, jn = j == M - 1 ? 0 : j + 1;
-                double x = d_teleport_q(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
-                double xn = d_teleport_q(S.r[RIDX(S, c, q, 0, jn)] + dx, S.L), yn = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, q, 1, jn)] + dy, S.L) : 0.0;
-                part += mht * (d_pot(S.pot, x, y, dim) + d_pot(S.pot, xn, yn, dim));
+                double x = f_teleport(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? f_teleport(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
+                double xn = f_teleport(S.r[RIDX(S, c, q, 0, jn)] + dx, S.L), yn = dim > 1 ? f_teleport(S.r[RIDX(S, c, q, 1, jn)] + dy, S.L) : 0.0;
+                part += mht * (f_pot(S.pot, x, y, dim) + f_pot(S.pot, xn, yn, dim));
                 if (pairs) part += d_pairs_new(S, c, x, y, xn, yn, j, p, -1, false);
             }
             p = pn; cnt++; } while (p != n && cnt <= N);
         const double w_updated = block_sum(part, red);
-        ret = d_metropolis(pimc_exp(w_updated - w_initial), u) ? 1 : 0;          // same value on every thread
+        ret = d_metropolis(f_exp(w_updated - w_initial), u) ? 1 : 0;          // same value on every thread
         if (ret == 1) {
             // link cache first (it reads the still-unshifted neighbours), then the positions
             p = n; cnt = 0;
             do { int pn = nextc[p];
                 for (int j = tid; j < M; j += nt) {
                     int q = j == M - 1 ? pn : p, jn = j == M - 1 ? 0 : j + 1;
-                    double x = d_teleport_q(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
-                    double xn = d_teleport_q(S.r[RIDX(S, c, q, 0, jn)] + dx, S.L), yn = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, q, 1, jn)] + dy, S.L) : 0.0;
-                    S.Vl[VIDX(S, c, p, j)] = mht * (d_pot(S.pot, x, y, dim) + d_pot(S.pot, xn, yn, dim));
+                    double x = f_teleport(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? f_teleport(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
+                    double xn = f_teleport(S.r[RIDX(S, c, q, 0, jn)] + dx, S.L), yn = dim > 1 ? f_teleport(S.r[RIDX(S, c, q, 1, jn)] + dy, S.L) : 0.0;
+                    S.Vl[VIDX(S, c, p, j)] = mht * (f_pot(S.pot, x, y, dim) + f_pot(S.pot, xn, yn, dim));
                 }
                 p = pn; cnt++; } while (p != n && cnt <= N);
             __syncthreads();
             p = n; cnt = 0;
             do { for (int j = tid; j < M; j += nt) {                              // a thread owns its slices: per-slice list order as in d_com_warp
-                    double x = d_teleport_q(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? d_teleport_q(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
+                    double x = f_teleport(S.r[RIDX(S, c, p, 0, j)] + dx, S.L), y = dim > 1 ? f_teleport(S.r[RIDX(S, c, p, 1, j)] + dy, S.L) : 0.0;
                     S.r[RIDX(S, c, p, 0, j)] = x; if (dim > 1) S.r[RIDX(S, c, p, 1, j)] = y;
-                    d_cell_update(S, c, j, p, x, y);
+                    f_cell_update(S, c, j, p, x, y);
                 }
                 p = nextc[p]; cnt++; } while (p != n && cnt <= N);
             __syncthreads();

@@ -301,6 +301,8 @@ __device__ __forceinline__ int d_com_warp(const DevSys &S, int c, int n, double 
 // successor loads hit the lines just fetched), then does the arithmetic: inside the persistent kernel a chain has one or two warps
 // and the estimator is bound by memory latency, so the loads in flight per lane are what counts.
 #define EST_U 4
+__device__ __noinline__ double f_pot(const PotDev &p, double x, double y, int dim) { return d_pot(p, x, y, dim); }   // one copy (code size)
+__device__ __noinline__ double f_rdv(const PotDev &p, double x, double y, int dim) { return d_rdv(p, x, y, dim); }
 __device__ __forceinline__ void d_energy_block(const DevSys &S, int c, double *red, double *E, double *Ev, double *parts)
 {
     const int M = S.M, N = S.N, dim = S.dim;
@@ -328,8 +330,8 @@ __device__ __forceinline__ void d_energy_block(const DevSys &S, int c, double *r
                     double dr = d_distance(ax[u], bx[u], S.L), d2 = dr * dr;
                     if (dim > 1) { dr = d_distance(ay[u], by[u], S.L); d2 = d2 + dr * dr; }
                     link += d2;
-                    pot += d_pot(S.pot, ax[u], ay[u], dim) + d_pot(S.pot, bx[u], by[u], dim);
-                    vkin += d_rdv(S.pot, ax[u], ay[u], dim);
+                    if (S.pot.kind != PIMC_POT_ZERO) pot += f_pot(S.pot, ax[u], ay[u], dim) + f_pot(S.pot, bx[u], by[u], dim);
+                    if (S.pot.dv_kind != PIMC_DV_ZERO) vkin += f_rdv(S.pot, ax[u], ay[u], dim);
                 }
             }
         }
