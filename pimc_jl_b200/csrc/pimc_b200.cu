@@ -119,6 +119,9 @@ __global__ void k_bins_export(DevSys S, int c0, int nc, long long *out)
 // P.fscr is set) + N bytes (per-task outcome) + control words
 // CELLS = false: systems without hard core / pair action / cell list; the compiler is told so and drops every neighbour query
 // (they are out-of-line calls that would otherwise push the kernel to the register cap).
+#ifndef PIMC_CELLS_THREADS
+#define PIMC_CELLS_THREADS 128
+#endif
 template <bool CELLS>
 __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__restrict__ T, const RunParams &P)
 {
@@ -319,7 +322,7 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
 }
 __global__ void __launch_bounds__(256, 3) k_run(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<false>(S, T, P); }
 // interacting systems: CTAs of at most 64 threads, eight per SM (every chain of the 1024-chain configurations resident at once)
-__global__ void __launch_bounds__(64, 8) k_run_cells(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<true>(S, T, P); }
+__global__ void __launch_bounds__(PIMC_CELLS_THREADS, 8) k_run_cells(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<true>(S, T, P); }
 
 // ---- estimator / action hooks ----
 __global__ void k_energy_now(DevSys S, double *E, double *Ev, double *parts)
@@ -468,6 +471,7 @@ struct pimc_handle {
     long long de_ndata[PIMC_MAXD];
     double r_a; double vol;
     int opt_sweep_impl, opt_faithful_impl;
+    double *dens_out; size_t dens_out_n;   // density read-out staging
     double *fscr;       // HBM scratch for warp-cooperative proposals that do not fit shared memory (lazily allocated)
     cudaEvent_t ev0, ev1;
     int device;
@@ -565,7 +569,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0;
     memset(&h->T, 0, sizeof h->T);
     int rc = PIMC_OK;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
@@ -1027,7 +1031,9 @@ extern "C" int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64
     CK(h, cudaStreamSynchronize(h->stream));
     DeDev &D = h->T.de[id]; size_t sz = h->S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins;
     if (dens) {
-        TmpBuf t; double *o = t.up((double *)nullptr, sz); if (!o) return PIMC_ERR_NOMEM;
+        // read-out buffer kept with the handle: a cudaMalloc / cudaFree pair per block costs a device-wide synchronisation each
+        if (h->dens_out_n < sz) { double *o2 = nullptr; int rc = dalloc(h, &o2, sz); if (rc) return rc; h->dens_out = o2; h->dens_out_n = sz; }
+        double *o = h->dens_out;
         k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(D.dens, sz, o); LAUNCHED(); CK(h, cudaGetLastError());
         CK(h, cudaStreamSynchronize(h->stream));
         CK(h, cudaMemcpy(dens, o, sz * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1065,7 +1071,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     }
     CK(h, cudaMemsetAsync(h->dstats, 0, 16 * sizeof(unsigned long long), h->stream));
     // FAITHFUL: warp 0 owns the proposal; large chains get three more warps for the estimators (Energy / Density stream N*M beads)
-    int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? 64 : 32);
+    int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? (S.need_cells ? PIMC_CELLS_THREADS : 64) : 32);
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
     P.fimpl = h->opt_faithful_impl; P.fscr = nullptr;
