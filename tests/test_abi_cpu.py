@@ -35,6 +35,32 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert L.pimc_version() >= 100 and L.pimc_launch_count() == 0
 
 
+def test_constants_mirror_the_header(lib):
+    """the ctypes layer's enum / option / compat constants are the ones include/pimc_b200.h defines"""
+    src = open(os.path.join(ROOT, "include", "pimc_b200.h")).read()
+    vals = {k: int(v, 0) for k, v in re.findall(r"#define\s+(PIMC_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", src)}
+    for body in re.findall(r"enum\s*\{([^}]*)\}", src):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, v = [t.strip() for t in item.split("=")]
+                nxt = int(v, 0)
+            else:
+                name = item
+            vals[name] = nxt
+            nxt += 1
+    checked = 0
+    for name in dir(lib):
+        if name.startswith(("POT_", "DV_", "UPD_", "SCHED_", "OPT_", "COMPAT_")) and name != "COMPAT_ALL":
+            assert ("PIMC_" + name) in vals, f"{name} has no counterpart in the header"
+            assert vals["PIMC_" + name] == getattr(lib, name), name
+            checked += 1
+    assert checked >= 16
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
