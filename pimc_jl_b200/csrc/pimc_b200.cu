@@ -1137,11 +1137,9 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         // Used for register tiles KM <= 4 and enough worldlines to fill the CTA; PIMC_OPT_SWEEP_IMPL = 2 keeps generation one.
         typedef void (*kfn2)(const DevSys, const DevTables *, const Sweep2Params);
         kfn2 k_sw2 = nullptr; int cap2 = 0; size_t smem2 = 0;
-        const char *th2env = getenv("PIMC_SW2_TH");
-        const int th2 = th2env ? atoi(th2env) : 512;          // 512 threads, two CTAs per SM (256 / four CTAs: experiment)
-        if (KM <= 4 && h->opt_sweep_impl == 3 && S.N >= 32 && (th2 == 512 || th2 == 256)) {   // measured slower than generation one: opt-in only
-#define PICK_SWEEP2(P_) (th2 == 512 ? (KM <= 1 ? k_sweep2<P_, 1, 512> : KM <= 2 ? k_sweep2<P_, 2, 512> : k_sweep2<P_, 4, 512>) \
-                                    : (KM <= 1 ? k_sweep2<P_, 1, 256> : KM <= 2 ? k_sweep2<P_, 2, 256> : k_sweep2<P_, 4, 256>))
+        const int th2 = 512;                                  // 512 threads, two CTAs per SM (the 256-thread / four-CTA variant measured no better and is gone)
+        if (KM <= 4 && h->opt_sweep_impl == 3 && S.N >= 32) {   // measured slower than generation one: opt-in only
+#define PICK_SWEEP2(P_) (KM <= 1 ? k_sweep2<P_, 1, 512> : KM <= 2 ? k_sweep2<P_, 2, 512> : k_sweep2<P_, 4, 512>)
             k_sw2 = pk == PIMC_POT_ZERO ? PICK_SWEEP2(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP2(PIMC_POT_HARMONIC) : PICK_SWEEP2(PIMC_POT_LATTICE));
 #undef PICK_SWEEP2
             const size_t budget = th2 == 512 ? 112000 : 55500;   // two / four CTAs per SM
