@@ -1124,7 +1124,7 @@ int ora_run(ora_system *s, int64_t n, ora_update **upd, const int64_t *every, in
         pimc_u4 di = pimc_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
         int64_t pick = sample_weighted(w, nupd, pimc_u01_co(di.w[0], di.w[1]));
         ora_update *u = upd[pick - 1];
-        if (sched == ORA_SCHED_FAITHFUL || u->kind == ORA_UPD_RESHAPE_SWAP) {
+        if ((sched != ORA_SCHED_SWEEP && sched != ORA_SCHED_SWEEP_SEQ) || u->kind == ORA_UPD_RESHAPE_SWAP) {
             int acc = functor_call(s, u, 0, 0, 0, u->m, u->size);
             apply_bookkeeping(u, acc);
         } else {

@@ -64,7 +64,10 @@ typedef struct ora_energy ora_energy;
 typedef struct ora_density ora_density;
 
 enum { ORA_UPD_RESHAPE_LINEAR = 0, ORA_UPD_RESHAPE_SWAP = 1, ORA_UPD_SINGLE_COM = 2, ORA_UPD_POLYMER_COM = 3 };
-enum { ORA_SCHED_FAITHFUL = 0, ORA_SCHED_SWEEP = 1 };
+/* ORA_SCHED_SWEEP_SEQ: the sweep executed strictly sequentially (proposal n sees the committed results of the proposals before it), also for
+ * systems with a hard core / pair action -- the definition a future GPU sweep for interacting worldlines is held to.
+ * ORA_SCHED_SWEEP is the same loop restricted to independent worldlines, where the order cannot matter. */
+enum { ORA_SCHED_FAITHFUL = 0, ORA_SCHED_SWEEP = 1, ORA_SCHED_SWEEP_SEQ = 2 };
 
 /* ---- pure functions ---- */
 double ora_distance(double x1, double x2, double L);

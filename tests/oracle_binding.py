@@ -12,7 +12,7 @@ _SO = os.path.join(_ROOT, "oracle", "libpimc_oracle.so")
 POT_ZERO, POT_HARMONIC, POT_SIN2_1D, POT_LATTICE = 0, 1, 2, 3
 DV_ZERO, DV_IDENTITY, DV_GRADIENT = 0, 1, 2
 UPD_RESHAPE_LINEAR, UPD_RESHAPE_SWAP, UPD_SINGLE_COM, UPD_POLYMER_COM = 0, 1, 2, 3
-SCHED_FAITHFUL, SCHED_SWEEP = 0, 1
+SCHED_FAITHFUL, SCHED_SWEEP, SCHED_SWEEP_SEQ = 0, 1, 2
 COMPAT_PAIR_BYVALUE, COMPAT_SWAP_SIGN, COMPAT_DENSITY_SHIFT, COMPAT_SWAP_STALE_LINK, COMPAT_ALL = 1, 2, 4, 8, 15
 MAX_ANGLES = 32
 

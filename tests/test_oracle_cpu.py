@@ -305,6 +305,51 @@ def test_sweep_equals_sequential_definition(oracle):
         s2.run(1, [(1, ob.Update(s2, ob.UPD_RESHAPE_LINEAR, 3))], sched=ob.SCHED_SWEEP)
 
 
+def _hardcore_system(ob, chain, seed, sched_tag, N=4, M=8):
+    return ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=3.0, T=1.0, lam=0.5, Ncycle=4, seed=seed, chain=chain,
+                     interactions=True, g=3.5, r_a=1.0)   # a = exp(-2 pi / 3.5) = 0.166, lnU == 0 (no table): pure hard core
+
+
+def test_interacting_sequential_sweep_invariants_and_z_test(oracle):
+    """ORA_SCHED_SWEEP_SEQ (the definition the GPU sweep for interacting worldlines will be held to): every
+    worldline proposes once per iteration, strictly in order.  Invariants after a run: hard core respected, beads in the box,
+    every bead filed in the cell its position names; and the sampled energy agrees with the reference schedule's (|z| < 4)."""
+    ob = oracle
+    N, M = 4, 8
+    spec = [(1, ob.UPD_SINGLE_COM, 0.5), (1, ob.UPD_RESHAPE_LINEAR, 4)]
+    means = {}
+    for tag, sched, therm, n in (("faithful", ob.SCHED_FAITHFUL, 8000, 120000), ("sweep", ob.SCHED_SWEEP_SEQ, 2000, 30000)):
+        Es = []
+        for c in range(16):
+            s = _hardcore_system(ob, c, 77, tag, N, M)
+            ups = [(every, ob.Update(s, kind, v0)) for every, kind, v0 in spec]
+            s.run(therm, ups, sched=sched)
+            e = ob.Energy(n // 4 + 1)
+            s.run(n, ups, energies=[e], sched=sched)
+            Es.append(e.read()[0].mean())
+            if c == 0:
+                r, V, bins, nxt = s.paths()
+                assert np.all(np.abs(r) <= 3.0)
+                for j in range(M):
+                    for a_ in range(N):
+                        assert bins[a_, j] == ob.lib().ora_bin(ob._p(np.ascontiguousarray(r[a_, :, j])), 2, s.nbins, 3.0)
+                        out = np.zeros(16, dtype=np.int64)
+                        k = ob.lib().ora_nn_cell(s.h, j + 1, int(bins[a_, j]), ob._pi(out))
+                        assert out[:k].tolist().count(a_ + 1) == 1
+                        for b_ in range(a_ + 1, N):
+                            d = np.abs(r[a_, :, j] - r[b_, :, j]); d = np.minimum(d, 6.0 - d)
+                            assert math.hypot(*d) >= s.a
+                assert abs(ob.lib().ora_action_links(s.h) - ob.lib().ora_action_links_recomputed(s.h)) < 1e-10
+                if tag == "sweep":
+                    g = ups[1][1].get()
+                    assert g["tries"] % N == 0 and g["tries"] > 0   # N proposals per picked iteration
+        means[tag] = np.array(Es)
+    a, b = means["faithful"], means["sweep"]
+    z = (a.mean() - b.mean()) / math.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+    assert abs(z) < 4, (a.mean(), b.mean(), z)
+    assert a.mean() > 8.6 and b.mean() > 8.6   # the hard core is felt: the same gas without it has <E> = 8.48(3)
+
+
 # ---------- second opinions for the move functors (numpy, written from src/updates/*.jl) ----------
 def _lnV_py(a, b, tau, V):
     return -0.5 * tau * (V(a) + V(b))
