@@ -150,7 +150,45 @@ __device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__r
             __syncthreads();
             const long long t_move0 = P.prof ? clock64() : 0;
 
-            if (U.kind == PIMC_UPD_RESHAPE_LINEAR && !sweep && P.fimpl == 0) {
+            if (CELLS && sweep && P.fimpl == 0 && U.kind == PIMC_UPD_RESHAPE_LINEAR) {
+                // sweep of INTERACTING worldlines: every worldline proposes once per iteration in one common time window, strictly in
+                // order (proposal n sees the committed results of the proposals before it: the oracle's ORA_SCHED_SWEEP_SEQ); each
+                // proposal is the warp-cooperative body.  Amortises the iteration overhead and the estimators over N proposals.
+                if (warp == 0) {
+                    const int j0w = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
+                    unsigned long long bm = 0;
+                    for (int slot = 0; slot < N; ++slot) {
+                        pimc_u4 dt = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 0);
+                        pimc_u4 dm = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
+                        int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
+                        int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+                        GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
+                        int r = d_reshape_linear_w(S, c, slot, j0w, m, g, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
+                        if (lane == 0) flag[slot] = r == 1 ? 1 : 0;
+                        bm += (unsigned long long)(m - 1);
+                        __syncwarp();
+                    }
+                    if (lane == 0) s_bead = bm;
+                }
+            } else if (CELLS && sweep && P.fimpl == 0) { // centre-of-mass sweep of interacting worldlines: the whole CTA on one proposal at a time, in order
+                const bool polymer = U.kind == PIMC_UPD_POLYMER_COM;
+                const int *nextc = S.next + (size_t)c * N;
+                unsigned long long bm = 0;
+                for (int slot = 0; slot < N; ++slot) {
+                    bool run_it;
+                    if (!polymer) run_it = nextc[slot] == slot;
+                    else { run_it = true; int p = nextc[slot], cnt = 0; while (p != slot && cnt <= N) { if (p < slot) run_it = false; p = nextc[p]; cnt++; } }
+                    if (!run_it) continue;
+                    pimc_u4 dm = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
+                    DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)slot;
+                    int npol = 1;
+                    int r = d_com_cta(S, c, slot, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol, fscr, fs_doubles);
+                    if (tid == 0) flag[slot] = r == 1 ? 1 : 0;
+                    bm += (unsigned long long)M * npol;
+                    __syncthreads();
+                }
+                if (tid == 0) s_bead = bm;
+            } else if (U.kind == PIMC_UPD_RESHAPE_LINEAR && !sweep && P.fimpl == 0) {
                 if (warp == 0) { // one proposal, the whole warp on it (pimc_faithful.cuh)
                     pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
                     pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
@@ -1051,7 +1089,8 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     if (n < 0 || nupd < 1 || nupd > PIMC_MAXU || nen < 0 || nen > PIMC_MAXE || nde < 0 || nde > PIMC_MAXD || !update_ids || !every) { SETERR(h, "pimc_run: bad arguments"); return PIMC_ERR_INVALID; }
     if (sched != PIMC_SCHED_FAITHFUL && sched != PIMC_SCHED_SWEEP) { SETERR(h, "unknown schedule %d", sched); return PIMC_ERR_INVALID; }
     DevSys &S = h->S;
-    if (sched == PIMC_SCHED_SWEEP && S.need_cells) { SETERR(h, "sweep schedule needs independent worldlines (a == 0, no interactions); use PIMC_SCHED_FAITHFUL"); return PIMC_ERR_UNSUPPORTED; }
+    // sweep of interacting worldlines: sequential per chain inside the persistent kernel (warp- / CTA-cooperative bodies only)
+    if (sched == PIMC_SCHED_SWEEP && S.need_cells && h->opt_faithful_impl != 0) { SETERR(h, "the sweep schedule of interacting worldlines needs the cooperative proposals (PIMC_OPT_FAITHFUL_IMPL = 0)"); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaSetDevice(h->device));
     RunParams P; memset(&P, 0, sizeof P);
     P.n = n; P.iter0 = h->iter; P.nupd = nupd; P.nen = nen; P.nde = nde; P.sched = sched;
@@ -1073,6 +1112,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     // FAITHFUL: warp 0 owns the proposal; large chains get three more warps for the estimators (Energy / Density stream N*M beads)
     int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? (S.need_cells ? PIMC_CELLS_THREADS : 64) : 32);
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
+    if (S.need_cells && threads > PIMC_CELLS_THREADS) threads = PIMC_CELLS_THREADS;   // launch bound of k_run_cells
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
     P.fimpl = h->opt_faithful_impl; P.fscr = nullptr;
     P.prof = getenv("PIMC_PROF") ? h->dstats + 4 : nullptr;   // per-phase cycle counters of k_run, printed to stderr after the run
@@ -1104,9 +1144,9 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         return com_flag + (size_t)(threads / 32) * 16 + (stage > cyc ? stage : cyc) + 16;
     };
     const size_t smem_cs = com_bytes(SWEEP_THREADS);
-    const bool batched_ok = sched == PIMC_SCHED_SWEEP && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
+    const bool batched_ok = sched == PIMC_SCHED_SWEEP && !S.need_cells && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl >= 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
-    if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
+    if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need independent worldlines and M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
     if (n > 0 && !batched) {
         if (S.need_cells) k_run_cells<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); else k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P);

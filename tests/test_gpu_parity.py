@@ -331,8 +331,44 @@ def test_interacting_faithful_cell_list(oracle, compat, fimpl):
         acc_o = ob.lib().ora_reshape_linear_explicit(os_[c].h, n, j0, m, ob._p(xi), u, 0, C.byref(wi), C.byref(wu), None)
         acc, gwi, gwu, _ = e.reshape_linear_explicit(c, n, j0, m, xi, u, commit=False)
         assert acc == acc_o and close(gwi, wi.value, 1e-11, 1e-12) and close(gwu, wu.value, 1e-11, 1e-12), (t, gwi, wi.value, gwu, wu.value)
-    with pytest.raises(pj.PimcError):
-        e.run(10, ge, sched=L.SCHED_SWEEP)
+    if fimpl == 1:   # the sweep of interacting worldlines exists only with the cooperative proposals
+        with pytest.raises(pj.PimcError):
+            e.run(10, ge, sched=L.SCHED_SWEEP)
+
+
+@pytest.mark.parametrize("compat", [L.COMPAT_ALL, 0], ids=["as-shipped", "intended"])
+def test_interacting_sweep_sequential(oracle, compat):
+    """Sweep schedule of INTERACTING worldlines (hard core, lnU table, cell list): every worldline proposes once per iteration, strictly
+    in order, inside the persistent kernel; held to the oracle's ORA_SCHED_SWEEP_SEQ bit for bit."""
+    ob = oracle
+    tab, lo, hi = synthetic_table()
+    cfg = dict(pot="harmonic", dim=2, M=12, N=9, L=3.0, T=0.5, lam=0.5, Ncycle=3)
+    e, os_ = make_pair(ob, cfg, chains=3, seed=31, interactions=True, g=3.0, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    assert e.a > 0
+    spec = [(2, L.UPD_SINGLE_COM, 0.4), (1, L.UPD_RESHAPE_LINEAR, 6), (2, L.UPD_RESHAPE_SWAP, 6), (3, L.UPD_POLYMER_COM, 0.3)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    en_id, de_id = e.energy_create(400), e.density_create(16)
+    oen = [ob.Energy(400) for _ in os_]
+    ode = [ob.Density(s, 16) for s in os_]
+    st = e.run(120, ge, energies=[en_id], densities=[de_id], sched=L.SCHED_SWEEP)
+    for s, ups, en, de in zip(os_, oo, oen, ode):
+        s.run(120, ups, energies=[en], densities=[de], sched=ob.SCHED_SWEEP_SEQ)
+    _sync_paths(e, os_)
+    tot = 0
+    for (_, uid), k in zip(ge, range(len(spec))):
+        for c in range(3):
+            gq, o = e.update_get(uid, c), oo[c][k][1].get()
+            assert gq["tries"] == o["tries"] and gq["tries_var"] == o["tries_var"] and gq["accepted"] == o["accepted"], (k, c, gq, o)
+            assert gq["var"] == o["var"] and gq["bead_moves"] == o["bead_moves"], (k, c, gq, o)
+            tot += o["bead_moves"]
+    assert st["bead_moves"] == tot and st["proposals"] > 120 * 3
+    scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+    for c in range(3):
+        E, Ev, n = e.energy_read(en_id, c)
+        Eo, Evo = oen[c].read()
+        assert n == len(Eo) == 40 and np.all(np.abs(E - Eo) <= 1e-12 * scale)
+    dg, _, _ = e.density_read(de_id, 16)
+    assert np.array_equal(dg, sum(d.read()[0] for d in ode))
 
 
 @pytest.mark.parametrize("compat", [L.COMPAT_ALL, 0], ids=["as-shipped", "intended"])
