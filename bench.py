@@ -155,10 +155,13 @@ def main():
     ap.add_argument("--iters", type=int, default=0, help="run! iterations per step (default 400; 40000 for the reference schedule)")
     ap.add_argument("--therm", type=int, default=-1, help="untimed thermalisation iterations before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sched", default="", choices=["", "faithful", "sweep"], help="override the workload's schedule (side measurements)")
     ap.add_argument("--faithful-impl", type=int, default=0, help="reference-schedule proposals: 0 warp-cooperative (default), 1 one thread (A/B)")
     ap.add_argument("--cpu-iters", type=int, default=0)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.sched:
+        wl["sched"] = args.sched
     if args.chains:
         wl["chains"] = args.chains
     faithful = wl["sched"] == "faithful"
