@@ -97,6 +97,9 @@ int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run k
 #define PIMC_OPT_SWEEP_IMPL 1
 /* PIMC_OPT_FAITHFUL_IMPL: proposals of the reference schedule: 0 warp-cooperative (default), 1 one thread per proposal (A/B, same bits) */
 #define PIMC_OPT_FAITHFUL_IMPL 2
+/* PIMC_OPT_FUSE_ENERGY: 1 (default) evaluates the Energy functor inside the sweep launch for chains whose picked update streamed every
+ * worldline anyway; 0 always uses the separate estimator launch (A/B, same values to 1e-12) */
+#define PIMC_OPT_FUSE_ENERGY 3
 int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
 /* measurement utility (no reference counterpart): sustained non-tensor fp64 FMA rate of the current device, in TFLOP/s */

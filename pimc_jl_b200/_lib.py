@@ -17,6 +17,7 @@ UPD_RESHAPE_LINEAR, UPD_RESHAPE_SWAP, UPD_SINGLE_COM, UPD_POLYMER_COM = 0, 1, 2,
 SCHED_FAITHFUL, SCHED_SWEEP = 0, 1
 OPT_SWEEP_IMPL = 1
 OPT_FAITHFUL_IMPL = 2
+OPT_FUSE_ENERGY = 3
 COMPAT_PAIR_BYVALUE, COMPAT_SWAP_SIGN, COMPAT_DENSITY_SHIFT, COMPAT_SWAP_STALE_LINK, COMPAT_ALL = 1, 2, 4, 8, 15
 
 f64p = C.POINTER(C.c_double)

@@ -2,9 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cstdio>
 #include "pimc_moves.cuh"
-#include "pimc_faithful.cuh"
-#include "pimc_sweep.cuh"
-#include "pimc_sweep2.cuh"
+#include "pimc_launch.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -113,254 +111,6 @@ __global__ void k_bins_export(DevSys S, int c0, int nc, long long *out)
         out[idx] = d_bin(S, S.r[RIDX(S, c, n, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0) + 1;
     }
 }
-
-// ---- run! (simulation.jl:29-42): one persistent CTA per chain, all n iterations inside the kernel ----
-// dynamic shared memory: 96 doubles (reductions) + scratch of the warp-cooperative proposal (pimc_faithful.cuh; in HBM when
-// P.fscr is set) + N bytes (per-task outcome) + control words
-// CELLS = false: systems without hard core / pair action / cell list; the compiler is told so and drops every neighbour query
-// (they are out-of-line calls that would otherwise push the kernel to the register cap).
-#ifndef PIMC_CELLS_THREADS
-#define PIMC_CELLS_THREADS 128
-#endif
-template <bool CELLS>
-__device__ __forceinline__ void d_run_body(const DevSys &S, const DevTables *__restrict__ T, const RunParams &P)
-{
-    if (!CELLS) { __builtin_assume(S.need_cells == 0); __builtin_assume(S.interactions == 0); __builtin_assume(!(S.a > 0.0)); }
-    extern __shared__ double smem[];
-    double *red = smem;
-    const size_t fs_doubles = P.fimpl == 0 ? faithful_scratch_doubles(S.N, S.M) : 0;
-    double *fscr = P.fscr ? P.fscr + (size_t)blockIdx.x * fs_doubles : smem + 96;
-    unsigned char *flag = (unsigned char *)(smem + 96 + (P.fscr ? 0 : fs_doubles));
-    __shared__ unsigned long long s_bead;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int M = S.M, N = S.N;
-    unsigned long long tot_bead = 0, tot_prop = 0;
-    unsigned long long prof_c[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }; // cycles per update kind [0..3], proposals [4..7], bookkeeping, estimators
-
-    for (int c = blockIdx.x; c < S.C; c += gridDim.x) {
-        for (long long it = 0; it < P.n; ++it) {
-            pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter0 + (unsigned long long)it);
-            pimc_u4 di = f_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-            int pick = d_sample_weighted(P.w, P.nupd, pimc_u01_co(di.w[0], di.w[1]));
-            const UpdDev &U = T->upd[P.upd_id[pick]];
-            const double var = U.var[c];
-            const int sweep = (P.sched == PIMC_SCHED_SWEEP) && U.kind != PIMC_UPD_RESHAPE_SWAP;
-            if (tid == 0) { s_bead = 0; }
-            for (int i = tid; i < N; i += blockDim.x) flag[i] = 2; // 2 = slot not proposed
-            __syncthreads();
-            const long long t_move0 = P.prof ? clock64() : 0;
-
-            if (CELLS && sweep && P.fimpl == 0 && U.kind == PIMC_UPD_RESHAPE_LINEAR) {
-                // sweep of INTERACTING worldlines: every worldline proposes once per iteration in one common time window, strictly in
-                // order (proposal n sees the committed results of the proposals before it: the oracle's ORA_SCHED_SWEEP_SEQ); each
-                // proposal is the warp-cooperative body.  Amortises the iteration overhead and the estimators over N proposals.
-                if (warp == 0) {
-                    const int j0w = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
-                    unsigned long long bm = 0;
-                    for (int slot = 0; slot < N; ++slot) {
-                        pimc_u4 dt = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 0);
-                        pimc_u4 dm = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
-                        int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
-                        int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                        GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
-                        int r = d_reshape_linear_w(S, c, slot, j0w, m, g, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
-                        if (lane == 0) flag[slot] = r == 1 ? 1 : 0;
-                        bm += (unsigned long long)(m - 1);
-                        __syncwarp();
-                    }
-                    if (lane == 0) s_bead = bm;
-                }
-            } else if (CELLS && sweep && P.fimpl == 0) { // centre-of-mass sweep of interacting worldlines: the whole CTA on one proposal at a time, in order
-                const bool polymer = U.kind == PIMC_UPD_POLYMER_COM;
-                const int *nextc = S.next + (size_t)c * N;
-                unsigned long long bm = 0;
-                for (int slot = 0; slot < N; ++slot) {
-                    bool run_it;
-                    if (!polymer) run_it = nextc[slot] == slot;
-                    else { run_it = true; int p = nextc[slot], cnt = 0; while (p != slot && cnt <= N) { if (p < slot) run_it = false; p = nextc[p]; cnt++; } }
-                    if (!run_it) continue;
-                    pimc_u4 dm = f_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
-                    DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)slot;
-                    int npol = 1;
-                    int r = d_com_cta(S, c, slot, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol, fscr, fs_doubles);
-                    if (tid == 0) flag[slot] = r == 1 ? 1 : 0;
-                    bm += (unsigned long long)M * npol;
-                    __syncthreads();
-                }
-                if (tid == 0) s_bead = bm;
-            } else if (U.kind == PIMC_UPD_RESHAPE_LINEAR && !sweep && P.fimpl == 0) {
-                if (warp == 0) { // one proposal, the whole warp on it (pimc_faithful.cuh)
-                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    int n = (int)pimc_index(dt.w[0], (uint32_t)N);
-                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
-                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
-                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                    GSrc g; g.xi = nullptr; g.st = st; g.slot = 0; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
-                    int r = d_reshape_linear_w(S, c, n, j0, m, g, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
-                    if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)(m - 1); }
-                }
-            } else if (U.kind == PIMC_UPD_RESHAPE_SWAP && P.fimpl == 0) {
-                if (warp == 0 && N > 1) {
-                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    pimc_u4 dsw = f_draw(st, 0, PIMC_K_SWAP, 0, 0);
-                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
-                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
-                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                    int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
-                    int n2 = d_sample_partner_w(S, c, n1, j0, m, pimc_u01_co(dsw.w[2], dsw.w[3]), fscr);
-                    if (n1 == n2) { if (lane == 0) flag[0] = 3; } // early return without queue!(counter_var) (reshape.jl:134-136)
-                    else {
-                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
-                        int r = d_reshape_swap_w(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
-                        if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = 2ull * (unsigned long long)(m - 1); }
-                    }
-                } else if (tid == 0 && N <= 1) flag[0] = 3;
-            } else if (U.kind == PIMC_UPD_RESHAPE_LINEAR) {
-                const int ntask = sweep ? N : 1;
-                const int j0w = 1 + (int)pimc_index(di.w[2], (uint32_t)M);
-                unsigned long long bm = 0;
-                for (int slot = tid; slot < ntask; slot += blockDim.x) {
-                    pimc_u4 dt = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
-                    int n = sweep ? slot : (int)pimc_index(dt.w[0], (uint32_t)N);
-                    int j0 = sweep ? j0w : 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
-                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
-                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                    GSrc g; g.xi = nullptr; g.st = st; g.slot = (uint32_t)slot; g.kind = PIMC_K_BRIDGE; g.tab = S.logtab;
-                    int r = d_reshape_linear(S, c, n, j0, m, g, pimc_u01_co(dm.w[0], dm.w[1]), 1, slot, nullptr, nullptr);
-                    flag[slot] = r == 1 ? 1 : 0;
-                    bm += (unsigned long long)(m - 1);
-                }
-                if (bm) atomicAdd(&s_bead, bm);
-            } else if (U.kind == PIMC_UPD_RESHAPE_SWAP) {
-                if (tid == 0 && N > 1) {
-                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    pimc_u4 dsw = pimc_draw(st, 0, PIMC_K_SWAP, 0, 0);
-                    int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
-                    int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)((int)var - 1));
-                    int m = (int)U.vmax < mm ? (int)U.vmax : mm;
-                    int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
-                    double *w = S.wtab + (size_t)c * N;
-                    d_swap_weights(S, c, n1, j0, m, w);
-                    double norm = w[0]; for (int i = 1; i < N; ++i) norm = norm + w[i];
-                    for (int i = 0; i < N; ++i) w[i] = w[i] / norm;
-                    int n2 = d_sample_weighted(w, N, pimc_u01_co(dsw.w[2], dsw.w[3]));
-                    if (n1 == n2) flag[0] = 3; // early return without queue!(counter_var) (reshape.jl:134-136)
-                    else {
-                        GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
-                        int r = d_reshape_swap(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr);
-                        flag[0] = r == 1 ? 1 : 0;
-                        s_bead = 2ull * (unsigned long long)(m - 1);
-                    }
-                } else if (tid == 0) flag[0] = 3;
-            } else { // centre-of-mass moves: one warp per proposal
-                const bool polymer = U.kind == PIMC_UPD_POLYMER_COM;
-                const int *nextc = S.next + (size_t)c * N;
-                if (sweep) {
-                    for (int slot = warp; slot < N; slot += nwarp) {
-                        bool run_it;
-                        if (!polymer) run_it = nextc[slot] == slot;
-                        else { run_it = true; int p = nextc[slot], cnt = 0; while (p != slot && cnt <= N) { if (p < slot) run_it = false; p = nextc[p]; cnt++; } }
-                        if (!run_it) continue;
-                        pimc_u4 dm = pimc_draw(st, (uint32_t)slot, PIMC_K_TASK, 0, 1);
-                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = (uint32_t)slot;
-                        int npol = 1;
-                        int r = d_com_warp(S, c, slot, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
-                        if (lane == 0) { flag[slot] = r == 1 ? 1 : 0; atomicAdd(&s_bead, (unsigned long long)M * npol); }
-                    }
-                } else if (P.fimpl == 0) { // one proposal, the whole CTA on it (hard-core tests of all beads: pimc_faithful.cuh)
-                    pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = f_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    int n = -1;
-                    if (polymer) n = (int)pimc_index(dt.w[0], (uint32_t)N);
-                    else { // uniform among particles with next == self (com.jl:144-164)
-                        int cnt = 0; for (int i = 0; i < N; ++i) cnt += nextc[i] == i;
-                        if (cnt > 0) { int k = (int)pimc_index(dt.w[0], (uint32_t)cnt); for (int i = 0; i < N; ++i) if (nextc[i] == i && k-- == 0) { n = i; break; } }
-                    }
-                    if (n < 0) { if (tid == 0) flag[0] = 3; }
-                    else {
-                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = 0;
-                        int npol = 1;
-                        int r = d_com_cta(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), red, &npol, fscr, fs_doubles);
-                        if (tid == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)M * npol; }
-                    }
-                } else if (warp == 0) {
-                    pimc_u4 dt = pimc_draw(st, 0, PIMC_K_TASK, 0, 0);
-                    pimc_u4 dm = pimc_draw(st, 0, PIMC_K_TASK, 0, 1);
-                    int n = -1;
-                    if (polymer) n = (int)pimc_index(dt.w[0], (uint32_t)N);
-                    else { // uniform among particles with next == self (com.jl:144-164)
-                        int cnt = 0; for (int i = 0; i < N; ++i) cnt += nextc[i] == i;
-                        if (cnt > 0) { int k = (int)pimc_index(dt.w[0], (uint32_t)cnt); for (int i = 0; i < N; ++i) if (nextc[i] == i && k-- == 0) { n = i; break; } }
-                    }
-                    if (n < 0) { if (lane == 0) flag[0] = 3; }
-                    else {
-                        DSrc ds; ds.d = nullptr; ds.st = st; ds.slot = 0;
-                        int npol = 1;
-                        int r = d_com_warp(S, c, n, var, ds, pimc_u01_co(dm.w[0], dm.w[1]), 1, nullptr, nullptr, &npol);
-                        if (lane == 0) { flag[0] = r == 1 ? 1 : 0; s_bead = (unsigned long long)M * npol; }
-                    }
-                }
-            }
-            __syncthreads();
-            const long long t_move1 = P.prof ? clock64() : 0;
-            if (P.prof && tid == 0) { prof_c[U.kind & 3] += (unsigned long long)(t_move1 - t_move0); prof_c[4 + (U.kind & 3)] += 1; }
-
-            // apply! bookkeeping (simulation.jl:19-27), replayed in slot order by one thread
-            if (tid == 0) {
-                RingReg R; R.head = U.ring_head[c]; R.len = U.ring_len[c]; R.sum = U.ring_sum[c]; R.tries = U.tries_var[c];
-                const long long tries0 = R.tries; long long tr = U.tries[c], ac = U.accepted[c]; int cnt = 0;
-                const int ntask = sweep ? N : 1;
-                for (int slot = 0; slot < ntask; ++slot) {
-                    int f = flag[slot];
-                    if (f == 2) continue;
-                    cnt += 1; tr += 1;
-                    if (f == 3) continue;
-                    ac += f; d_ring_push(U, c, R, f);
-                }
-                bool adj;
-                if (sweep) adj = cnt > 0 && (R.tries / U.adj) != (tries0 / U.adj);
-                else adj = (R.tries % U.adj) == 0;
-                U.ring_head[c] = R.head; U.ring_len[c] = R.len; U.ring_sum[c] = R.sum; U.tries_var[c] = R.tries;
-                U.tries[c] = tr; U.accepted[c] = ac; U.bead_moves[c] += (long long)s_bead;
-                if (adj) d_adjust(U, c, R);
-                tot_bead += s_bead; tot_prop += (unsigned long long)cnt;
-            }
-            const long long t_book = P.prof ? clock64() : 0;
-            if (P.prof && tid == 0) prof_c[8] += (unsigned long long)(t_book - t_move1);
-            // measurement_Z_sector (measurement.jl:1-17): deterministic cadence, identical on every chain
-            if (P.nen + P.nde > 0) {
-                long long ctrv = P.Nctr0 + it + 1;
-                if (ctrv % P.Ncycle == 0) {
-                    long long k = P.N_MC0 + ctrv / P.Ncycle - 1; // 0-based index of this measurement
-                    __syncthreads();
-                    for (int e = 0; e < P.nen; ++e) {
-                        const EnDev &En = T->en[P.en_id[e]];
-                        double E, Ev;
-                        d_energy_block(S, c, red, &E, &Ev, nullptr);
-                        if (tid == 0) {
-                            if (k < En.cap) { En.E[(size_t)k * S.C + c] = E; En.Ev[(size_t)k * S.C + c] = Ev; }
-                            double *a = En.acc + (size_t)c * 5;
-                            a[0] += 1.0; a[1] += E; a[2] += E * E; a[3] += Ev; a[4] += Ev * Ev;
-                        }
-                        __syncthreads();
-                    }
-                    for (int d = 0; d < P.nde; ++d) d_density_block(S, c, T->de[P.de_id[d]]);
-                }
-            }
-            __syncthreads();
-            if (P.prof && tid == 0) prof_c[9] += (unsigned long long)(clock64() - t_book);
-        }
-    }
-    if (tid == 0 && P.prof) for (int i = 0; i < 10; ++i) atomicAdd(P.prof + i, prof_c[i]);
-    if (tid == 0 && P.stats) { atomicAdd(P.stats + 0, tot_prop); atomicAdd(P.stats + 2, tot_bead); }
-}
-__global__ void __launch_bounds__(256, 3) k_run(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<false>(S, T, P); }
-// interacting systems: CTAs of at most 64 threads, eight per SM (every chain of the 1024-chain configurations resident at once)
-__global__ void __launch_bounds__(PIMC_CELLS_THREADS, 8) k_run_cells(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<true>(S, T, P); }
 
 // ---- estimator / action hooks ----
 __global__ void k_energy_now(DevSys S, double *E, double *Ev, double *parts)
@@ -504,6 +254,9 @@ struct pimc_handle {
     long long N_MC, Nctr;
     int nupd, nen, nde;
     long long en_cap[PIMC_MAXE];
+    long long en_count[PIMC_MAXE];   // samples every Energy object holds (its own count, measurement.jl:119-120)
+    unsigned char *mdone;            // [C] per-chain flag: Energy of the current measurement evaluated inside the sweep launch
+    int opt_fuse_energy;
     unsigned long long *dstats;
     std::vector<void *> allocs;
     long long de_ndata[PIMC_MAXD];
@@ -607,7 +360,8 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1;
+    memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
     int rc = PIMC_OK;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
@@ -675,8 +429,9 @@ extern "C" int pimc_set_stream(pimc_handle *h, void *s) { if (!h) return PIMC_ER
 extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
 {
     if (!h) return PIMC_ERR_INVALID;
-    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 3) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FAITHFUL_IMPL && value >= 0 && value <= 1) { h->opt_faithful_impl = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_FUSE_ENERGY && value >= 0 && value <= 1) { h->opt_fuse_energy = (int)value; return PIMC_OK; }
     SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
 }
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
@@ -704,7 +459,8 @@ extern "C" int pimc_get_paths(pimc_handle *h, int32_t c0, int32_t nc, double *r,
     if (bins) {
         long long *tmp; CK(h, cudaMalloc(&tmp, sizeof(long long) * nc * per));
         k_bins_export<<<grid_for(nc * per, 256), 256, 0, h->stream>>>(S, c0, nc, tmp); LAUNCHED();
-        cudaError_t e = cudaMemcpy(bins, tmp, sizeof(long long) * nc * per, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaStreamSynchronize(h->stream);   // h->stream may be non-blocking: the copy below runs on the legacy stream
+        if (e == cudaSuccess) e = cudaMemcpy(bins, tmp, sizeof(long long) * nc * per, cudaMemcpyDeviceToHost);
         cudaFree(tmp); CK(h, e);
     }
     if (next) {
@@ -1005,11 +761,7 @@ extern "C" int pimc_energy_create(pimc_handle *h, int64_t cap, int32_t *id)
     *id = h->nen++;
     return sync_tables(h);
 }
-static int energy_count(pimc_handle *h, int id, long long *n)
-{
-    double a0; CK(h, cudaMemcpy(&a0, h->T.en[id].acc, sizeof(double), cudaMemcpyDeviceToHost));
-    *n = (long long)a0; return PIMC_OK;
-}
+static int energy_count(pimc_handle *h, int id, long long *n) { *n = h->en_count[id]; return PIMC_OK; }
 extern "C" int pimc_energy_read_range(pimc_handle *h, int32_t id, int32_t chain, int64_t start, int64_t count, double *E, double *Ev, int64_t *n)
 {
     if (!h || id < 0 || id >= h->nen || chain < -1 || chain >= h->S.C || start < 0 || count < 0) return PIMC_ERR_INVALID;
@@ -1098,14 +850,18 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         if (update_ids[i] < 0 || update_ids[i] >= h->nupd || every[i] < 1) { SETERR(h, "bad update id / every"); return PIMC_ERR_INVALID; }
         P.upd_id[i] = update_ids[i]; P.w[i] = 1.0 / (double)every[i];
     }
-    for (int i = 0; i < nen; ++i) { if (energy_ids[i] < 0 || energy_ids[i] >= h->nen) { SETERR(h, "bad energy id"); return PIMC_ERR_INVALID; } P.en_id[i] = energy_ids[i]; }
+    for (int i = 0; i < nen; ++i) {
+        if (energy_ids[i] < 0 || energy_ids[i] >= h->nen) { SETERR(h, "bad energy id"); return PIMC_ERR_INVALID; }
+        for (int k = 0; k < i; ++k) if (energy_ids[k] == energy_ids[i]) { SETERR(h, "Energy object %d listed twice", energy_ids[i]); return PIMC_ERR_INVALID; }
+        P.en_id[i] = energy_ids[i]; P.en_k0[i] = h->en_count[energy_ids[i]];
+    }
     for (int i = 0; i < nde; ++i) { if (density_ids[i] < 0 || density_ids[i] >= h->nde) { SETERR(h, "bad density id"); return PIMC_ERR_INVALID; } P.de_id[i] = density_ids[i]; }
     P.Nctr0 = h->Nctr; P.N_MC0 = h->N_MC; P.Ncycle = h->cfg.Ncycle; P.stats = h->dstats;
     S.ctr = (nen + nde == 0) ? 10000 : 1000; // simulation.jl:31-32
-    // energy overflow: the reference errors when the pre-sized vector is full (measurement.jl:119-120)
-    long long nmeas = (nen + nde > 0) ? (h->Nctr + n) / h->cfg.Ncycle : 0;
+    // energy overflow: the reference errors when the pre-sized vector is full (measurement.jl:119-120); every Energy object counts its own samples
+    const long long nmeas = (nen + nde > 0) ? (h->Nctr + n) / h->cfg.Ncycle : 0;
     for (int i = 0; i < nen; ++i) {
-        long long cnt; int rc = energy_count(h, P.en_id[i], &cnt); if (rc) return rc;
+        const long long cnt = h->en_count[P.en_id[i]];
         if (cnt + nmeas > h->T.en[P.en_id[i]].cap) { SETERR(h, "Energy buffer of %lld entries would overflow (%lld + %lld)", (long long)h->T.en[P.en_id[i]].cap, cnt, nmeas); return PIMC_ERR_STATE; }
     }
     CK(h, cudaMemsetAsync(h->dstats, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -1123,12 +879,11 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
             if (!h->fscr) { int rc = dalloc(h, &h->fscr, (size_t)S.C * faithful_scratch_doubles(S.N, S.M)); if (rc) return rc; }
             P.fscr = h->fscr;
         }
-        if (smem > 48 * 1024) CK(h, cudaFuncSetAttribute(S.need_cells ? k_run_cells : k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int launches = 0;
     // per-iteration sweep kernels (pimc_sweep.cuh) for large batches, the persistent kernel otherwise
     const int pk = S.pot.kind;
-    // generation-one staging half: xs, ys, (pv) and the row map take BCAP rows; BCAP fills what four CTAs per SM leave of the shared memory
+    // staging half: xs, ys, (pv) and the row map take BCAP rows; BCAP fills what four CTAs per SM leave of the shared memory
     const size_t rs_fixed = (size_t)SWEEP_THREADS * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 32;
     const size_t rs_row = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
     const size_t rs_budget = ((S.M + 31) / 32 <= 4 ? 56000 : 74000);   // launch bounds: four (KM <= 4) or three CTAs per SM
@@ -1149,19 +904,12 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need independent worldlines and M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
     if (n > 0 && !batched) {
-        if (S.need_cells) k_run_cells<<<S.C, threads, smem, h->stream>>>(S, h->dT, P); else k_run<<<S.C, threads, smem, h->stream>>>(S, h->dT, P);
+        CK(h, pimc_launch_run(S.need_cells != 0, S.C, threads, smem, h->stream, S, h->dT, P));
         LAUNCHED(); launches++;
     }
     if (n > 0 && batched) {
         bool has_rs = false, has_com = false, has_swap = false;
         for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
-        const int KM = (S.M + 31) / 32;
-        typedef void (*kfn)(const DevSys, const DevTables *, const Sweep2Params);
-#define PICK_SWEEP(P_) (KM <= 1 ? k_sweep<P_, 1> : KM <= 2 ? k_sweep<P_, 2> : KM <= 4 ? k_sweep<P_, 4> : k_sweep<P_, 8>)
-        kfn k_sw = pk == PIMC_POT_ZERO ? PICK_SWEEP(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP(PIMC_POT_HARMONIC) : PICK_SWEEP(PIMC_POT_LATTICE));
-#undef PICK_SWEEP
-        cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         SweepParams SP; memset(&SP, 0, sizeof SP);
         SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS; const char *padenv = getenv("PIMC_EXP_SMEM_PAD"); const size_t smem_pad = padenv ? (size_t)atol(padenv) : 0;
         pimc_roundkeys_make(S.seed, &SP.rk);
@@ -1171,49 +919,23 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         for (int i = 0; i < nupd; ++i) { SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; }
         MeasParams MP; memset(&MP, 0, sizeof MP);
         MP.nen = nen; MP.nde = nde;
-        for (int i = 0; i < nen; ++i) MP.en_id[i] = P.en_id[i];
+        for (int i = 0; i < nen; ++i) { MP.en_id[i] = P.en_id[i]; MP.en_k0[i] = P.en_k0[i]; }
         for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
-        // second-generation staging sweep (pimc_sweep2.cuh): 512-thread CTAs, the whole chain staged as one rank-sorted batch.
-        // Used for register tiles KM <= 4 and enough worldlines to fill the CTA; PIMC_OPT_SWEEP_IMPL = 2 keeps generation one.
-        typedef void (*kfn2)(const DevSys, const DevTables *, const Sweep2Params);
-        kfn2 k_sw2 = nullptr; int cap2 = 0; size_t smem2 = 0;
-        const int th2 = 512;                                  // 512 threads, two CTAs per SM (the 256-thread / four-CTA variant measured no better and is gone)
-        if (KM <= 4 && h->opt_sweep_impl == 3 && S.N >= 32) {   // measured slower than generation one: opt-in only
-#define PICK_SWEEP2(P_) (KM <= 1 ? k_sweep2<P_, 1, 512> : KM <= 2 ? k_sweep2<P_, 2, 512> : k_sweep2<P_, 4, 512>)
-            k_sw2 = pk == PIMC_POT_ZERO ? PICK_SWEEP2(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_SWEEP2(PIMC_POT_HARMONIC) : PICK_SWEEP2(PIMC_POT_LATTICE));
-#undef PICK_SWEEP2
-            const size_t budget = th2 == 512 ? 112000 : 55500;   // two / four CTAs per SM
-            const size_t fixed = sw2_smem_bytes(pk, 0, S.N, S.M);
-            const size_t per_slot = (pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
-            const size_t com2 = com_bytes(th2);
-            cap2 = fixed < budget ? (int)(((budget - fixed) / per_slot) & ~(size_t)15) : 0;
-            if (cap2 < 1024 || com2 > budget) k_sw2 = nullptr;
-            else {
-                smem2 = sw2_smem_bytes(pk, cap2, S.N, S.M); if (com2 > smem2) smem2 = com2;
-                cudaFuncSetAttribute(k_sw2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-                cudaFuncSetAttribute(k_sw2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            }
-        }
-        Sweep2Params SP2; memset(&SP2, 0, sizeof SP2); SP2.cap = k_sw2 ? cap2 : bcap;
+        Sweep2Params SP2; memset(&SP2, 0, sizeof SP2); SP2.cap = bcap;
         for (int i = 0; i < nupd; ++i) SP2.upd[i] = h->T.upd[update_ids[i]];
-        if (h->opt_sweep_impl == 3 && !k_sw2) { SETERR(h, "second-generation sweep kernel needs M <= 128, N >= 32"); return PIMC_ERR_UNSUPPORTED; }
+        // Energy fused into the sweep launch of a measurement iteration (chains whose centre-of-mass sweep streams every worldline anyway)
+        const bool fuse_ok = nen > 0 && has_com && h->opt_fuse_energy != 0;
+        if (fuse_ok && !h->mdone) { int rc = dalloc(h, &h->mdone, (size_t)S.C); if (rc) return rc; }
         for (long long it = 0; it < n; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
-            if ((has_com || has_rs) && k_sw2) { SP2.sp = SP; k_sw2<<<S.C, th2, smem2, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
-            else if (has_com || has_rs) { SP2.sp = SP; k_sw<<<S.C, SWEEP_THREADS, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
-            if (has_swap) { SP2.sp = SP; k_swap_iter<<<S.C, 32, swap_smem_bytes(S.N, S.M), h->stream>>>(S, h->dT, SP2); LAUNCHED(); launches++; }
-            if (nen + nde > 0) {
-                long long ctrv = h->Nctr + it + 1;
-                if (ctrv % h->cfg.Ncycle == 0) {
-                    MP.k = h->N_MC + ctrv / h->cfg.Ncycle - 1;
-                    typedef void (*mfn)(const DevSys, const DevTables *, const MeasParams);
-#define PICK_MEAS(P_) (KM <= 1 ? k_measure<P_, 1> : KM <= 2 ? k_measure<P_, 2> : KM <= 4 ? k_measure<P_, 4> : KM <= 8 ? k_measure<P_, 8> : k_measure<P_, 0>)
-                    mfn k_me = pk == PIMC_POT_ZERO ? PICK_MEAS(PIMC_POT_ZERO) : (pk == PIMC_POT_HARMONIC ? PICK_MEAS(PIMC_POT_HARMONIC) : PICK_MEAS(PIMC_POT_LATTICE));
-#undef PICK_MEAS
-                    k_me<<<S.C, 256, 0, h->stream>>>(S, h->dT, MP);
-                    LAUNCHED(); launches++;
-                }
-            }
+            const long long ctrv = h->Nctr + it + 1;
+            const bool meas_now = nen + nde > 0 && ctrv % h->cfg.Ncycle == 0;
+            MP.ord = ctrv / h->cfg.Ncycle - 1;
+            SP2.sp = SP; SP2.fuse = meas_now && fuse_ok; SP2.mp = MP; SP2.mdone = h->mdone;
+            if (SP2.fuse) CK(h, cudaMemsetAsync(h->mdone, 0, (size_t)S.C, h->stream));
+            if (has_com || has_rs) { CK(h, pimc_launch_sweep(S.C, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
+            if (has_swap) { CK(h, pimc_launch_swap_iter(S.C, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
+            if (meas_now) { CK(h, pimc_launch_measure(S.C, h->stream, S, h->dT, MP, SP2.fuse ? h->mdone : nullptr)); LAUNCHED(); launches++; }
         }
     }
     CK(h, cudaEventRecord(h->ev1, h->stream));
@@ -1228,7 +950,11 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         fprintf(stderr, "; per iteration: bookkeeping %.0f, estimators %.0f\n", (double)st[4 + 8] / ((double)n * S.C), (double)st[4 + 9] / ((double)n * S.C));
     }
     h->iter += (unsigned long long)n;
-    if (nen + nde > 0) { h->N_MC += nmeas; h->Nctr = (h->Nctr + n) % h->cfg.Ncycle; for (int i = 0; i < nde; ++i) h->de_ndata[P.de_id[i]] += nmeas * (long long)S.M * S.C; }
+    if (nen + nde > 0) {
+        h->N_MC += nmeas; h->Nctr = (h->Nctr + n) % h->cfg.Ncycle;
+        for (int i = 0; i < nen; ++i) h->en_count[P.en_id[i]] += nmeas;
+        for (int i = 0; i < nde; ++i) h->de_ndata[P.de_id[i]] += nmeas * (long long)S.M * S.C;
+    }
     if (stats) {
         stats->iterations = n; stats->proposals = (int64_t)st[0]; stats->accepted = 0; stats->bead_moves = (int64_t)st[2];
         stats->measurements = nmeas; stats->launches = launches; stats->kernel_ms = ms;

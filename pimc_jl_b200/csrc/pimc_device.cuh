@@ -61,7 +61,7 @@ struct RunParams {
     long long n;
     unsigned long long iter0;
     int nupd; int upd_id[PIMC_MAXU]; double w[PIMC_MAXU];
-    int nen; int en_id[PIMC_MAXE];
+    int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC_MAXE];   // en_k0: samples the Energy object already holds (its own count)
     int nde; int de_id[PIMC_MAXD];
     int sched;
     long long Nctr0, N_MC0; int Ncycle;
@@ -318,7 +318,7 @@ __device__ __forceinline__ void d_nb_first(const DevSys &S, int c, int j, int b,
         }                                                                                                            \
     }
 // find_nn (:156-179): nearest stencil occupant (periodic metric on +L shifted coordinates), -1 if none
-__device__ __noinline__ int d_find_nn(const DevSys &S, int c, double x, double y, int j, int exc)
+static __device__ __noinline__ int d_find_nn(const DevSys &S, int c, double x, double y, int j, int exc)
 {
     int best = -1;
     double bd = 0.0;

@@ -14,21 +14,20 @@
 // Scratch per proposal (shared memory, or HBM when a chain's rows do not fit): w[N] | 2 bridges x { x, y, v, link, gx, gy }[M + 1].
 #pragma once
 #include "pimc_moves.cuh"
+#include "pimc_launch.h"
 
-#define FA_ARR 6
-__host__ __device__ inline size_t faithful_scratch_doubles(int N, int M) { return (size_t)((N + 1) & ~1) + 2 * FA_ARR * (size_t)(M + 1); }
 
 // ---- out-of-line leaves.  The persistent reference-schedule kernel runs ONE warp per proposal through long straight-line code:
 // with every helper inlined at every call site the kernel was 1.2 MB of SASS and the warps stalled on instruction fetch
 // (ncu: 28.6 cycles of "no instruction" per issue, profiles/r01e_*).  One shared copy of each helper keeps the hot code of all
 // proposal kinds within the instruction caches.  Same arithmetic, same bits.
-__device__ __noinline__ pimc_u4 f_draw(pimc_stream st, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead) { return pimc_draw(st, slot, kind, retry, bead); }
-__device__ __noinline__ double2 f_gauss(const GSrc &g, int dim, int bead, int retry) { double a, b; d_gauss(g, dim, bead, retry, a, b); return make_double2(a, b); }
-__device__ __noinline__ double f_teleport(double x, double L) { return d_teleport_q(x, L); }
-__device__ __noinline__ double f_exp(double x) { return pimc_exp(x); }
-__device__ __noinline__ double f_lnK2(double ax, double ay, double bx, double by, int dim, double tau, double lambda, double L) { return d_lnK2(ax, ay, bx, by, dim, tau, lambda, L); }
-__device__ __noinline__ bool f_hardcore_hit(const DevSys &S, int c, double x, double y, int j, int exc) { return d_hardcore_hit(S, c, x, y, j, exc); }
-__device__ __noinline__ void f_cell_update(const DevSys &S, int c, int j, int n, double x, double y) { d_cell_update(S, c, j, n, x, y); }
+static __device__ __noinline__ pimc_u4 f_draw(pimc_stream st, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead) { return pimc_draw(st, slot, kind, retry, bead); }
+static __device__ __noinline__ double2 f_gauss(const GSrc &g, int dim, int bead, int retry) { double a, b; d_gauss(g, dim, bead, retry, a, b); return make_double2(a, b); }
+static __device__ __noinline__ double f_teleport(double x, double L) { return d_teleport_q(x, L); }
+static __device__ __noinline__ double f_exp(double x) { return pimc_exp(x); }
+static __device__ __noinline__ double f_lnK2(double ax, double ay, double bx, double by, int dim, double tau, double lambda, double L) { return d_lnK2(ax, ay, bx, by, dim, tau, lambda, L); }
+static __device__ __noinline__ bool f_hardcore_hit(const DevSys &S, int c, double x, double y, int j, int exc) { return d_hardcore_hit(S, c, x, y, j, exc); }
+static __device__ __noinline__ void f_cell_update(const DevSys &S, int c, int j, int n, double x, double y) { d_cell_update(S, c, j, n, x, y); }
 
 __device__ __forceinline__ int warp_min_int(int v)
 {
@@ -39,7 +38,7 @@ __device__ __forceinline__ int warp_min_int(int v)
 
 // hardspherelevy! (helper.jl:141-181); == levy! (helper.jl:118-139) when a == 0.  Every lane passes the same arguments.
 // bb: x = bb, y = bb + R1, v = bb + 2 R1 (receives V(row)), gx = bb + 4 R1, gy = bb + 5 R1.  Returns 1, or 0 when a bead exhausted s.ctr.
-__device__ __noinline__ int d_bridge_w(const DevSys &S, int c, double bx, double by, double ex, double ey, int rows, int j0,
+static __device__ __noinline__ int d_bridge_w(const DevSys &S, int c, double bx, double by, double ex, double ey, int rows, int j0,
                                           int exc, const GSrc &g, double *bb, int R1)
 {
     const int lane = threadIdx.x & 31, dim = S.dim, m = rows - 2;

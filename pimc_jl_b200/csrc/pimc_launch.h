@@ -1,0 +1,43 @@
+// pimc_launch.h -- parameter blocks shared by the kernel translation units and the host side (pimc_b200.cu), and the
+// launchers each kernel TU exports.  The library is built from several TUs compiled in parallel (no relocatable device code:
+// every device function lives in a header and each TU carries its own copy).
+#pragma once
+#include "pimc_device.cuh"
+
+#define SWEEP_THREADS 256
+
+struct SweepParams {
+    unsigned long long iter;
+    const DevSys *Sg;   // device copy of the system descriptor (for out-of-line slow paths)
+    int nupd; int upd_id[PIMC_MAXU]; double w[PIMC_MAXU];
+    int kind[PIMC_MAXU]; double vmax[PIMC_MAXU];   // copies of the update descriptors' constants (no global load on the prologue path)
+    unsigned long long *stats;
+    pimc_roundkeys rk;  // Philox round keys of the seed (constant-bank operands)
+    int com_stage_off;  // byte offset of the COM half's TMA staging area in dynamic shared memory (0: register path with plain loads)
+};
+
+// measurement_Z_sector (measurement.jl:1-17) for every chain at one cadence hit.  ord = 0-based ordinal of this measurement within
+// the current run; Energy object e stores it at index en_k0[e] + ord (its OWN count, like the reference's findfirst(ismissing, ...),
+// measurement.jl:119-120).
+struct MeasParams { int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC_MAXE]; int nde; int de_id[PIMC_MAXD]; long long ord; };
+
+// The update descriptors travel by value in the kernel parameters (constant bank): no dependent global loads of T->upd[...]
+// on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).
+// fuse: the sweep launch of a measurement iteration also evaluates the Energy functor for the chains whose picked update streamed
+// every worldline anyway (centre-of-mass sweep of a chain without exchange cycles); mdone[c] = 1 tells k_measure to skip that chain.
+struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; };
+
+__host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
+__host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }
+#define FA_ARR 6
+__host__ __device__ inline size_t faithful_scratch_doubles(int N, int M) { return (size_t)((N + 1) & ~1) + 2 * FA_ARR * (size_t)(M + 1); }
+
+#ifndef PIMC_CELLS_THREADS
+#define PIMC_CELLS_THREADS 128
+#endif
+
+// ---- launchers (host functions defined next to their kernels) ----
+cudaError_t pimc_launch_run(bool cells, int grid, int threads, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const RunParams &P);
+cudaError_t pimc_launch_sweep(int grid, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
+cudaError_t pimc_launch_swap_iter(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
+cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const MeasParams &P, const unsigned char *mdone);

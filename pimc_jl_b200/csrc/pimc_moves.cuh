@@ -11,7 +11,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // pair action: interaction_action! (helper.jl:306-366) and the inlined copies of ReshapeSwapLinear (reshape.jl:166-199 old
 // configuration, :209-240 new configuration)
-__device__ __noinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl)
+static __device__ __noinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl)
 {
     // find_nns(s, p, sl, exceptions=[p]) with the STORED bin of p, then lnU of (bead, next bead) distances
     double w = 0.0;
@@ -31,7 +31,7 @@ __device__ __noinline__ double d_pairs_old(const DevSys &S, int c, int p, int sl
     })
     return w;
 }
-__device__ __noinline__ double d_pairs_new(const DevSys &S, int c, double x, double y, double xn, double yn, int sl, int e1, int e2, bool skip_next_exc)
+static __device__ __noinline__ double d_pairs_new(const DevSys &S, int c, double x, double y, double xn, double yn, int sl, int e1, int e2, bool skip_next_exc)
 {
     double w = 0.0;
     const int M = S.M;
@@ -301,8 +301,8 @@ __device__ __forceinline__ int d_com_warp(const DevSys &S, int c, int n, double 
 // successor loads hit the lines just fetched), then does the arithmetic: inside the persistent kernel a chain has one or two warps
 // and the estimator is bound by memory latency, so the loads in flight per lane are what counts.
 #define EST_U 4
-__device__ __noinline__ double f_pot(const PotDev &p, double x, double y, int dim) { return d_pot(p, x, y, dim); }   // one copy (code size)
-__device__ __noinline__ double f_rdv(const PotDev &p, double x, double y, int dim) { return d_rdv(p, x, y, dim); }
+static __device__ __noinline__ double f_pot(const PotDev &p, double x, double y, int dim) { return d_pot(p, x, y, dim); }   // one copy (code size)
+static __device__ __noinline__ double f_rdv(const PotDev &p, double x, double y, int dim) { return d_rdv(p, x, y, dim); }
 __device__ __forceinline__ void d_energy_block(const DevSys &S, int c, double *red, double *E, double *Ev, double *parts)
 {
     const int M = S.M, N = S.N, dim = S.dim;

@@ -10,8 +10,8 @@
 //   k_com_sweep     : Single/PolymerCenterOfMass (com.jl) for every worldline, one warp per proposal, one pass over HBM.
 #pragma once
 #include "pimc_moves.cuh"
+#include "pimc_launch.h"
 
-#define SWEEP_THREADS 256
 // staged rows per batch: runtime (Sweep2Params::cap), sized by the host from the shared-memory budget
 #define SWEEP_TBMAX 256   // tasks per batch
 #ifdef EXP_TIMING
@@ -19,20 +19,6 @@
 #else
 #define TICK(i) do { } while (0)
 #endif
-
-struct SweepParams {
-    unsigned long long iter;
-    const DevSys *Sg;   // device copy of the system descriptor (for out-of-line slow paths)
-    int nupd; int upd_id[PIMC_MAXU]; double w[PIMC_MAXU];
-    int kind[PIMC_MAXU]; double vmax[PIMC_MAXU];   // copies of the update descriptors' constants (no global load on the prologue path)
-    unsigned long long *stats;
-    pimc_roundkeys rk;  // Philox round keys of the seed (constant-bank operands)
-    int com_stage_off;  // byte offset of the COM half's TMA staging area in dynamic shared memory (0: register path with plain loads)
-};
-
-// The update descriptors travel by value in the kernel parameters (constant bank): no dependent global loads of T->upd[...]
-// on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).
-struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; };
 
 // teleport (propagator.jl:30-32) without the IEEE division on the fast path: q = x * (1/2L) differs from x / 2L by
 // <= 1 ulp, so floor(q + 0.5) can differ only when q + 0.5 sits within a few ulp of an integer; that case takes the exact path.
@@ -547,7 +533,6 @@ __device__ __forceinline__ void d_com_member(const DevSys &S, const double *rx, 
 // leaders (smallest index of a cycle) by pointer jumping in shared memory, one warp per MEMBER for the link-action sums, one thread
 // per cycle for the sums in cycle order + Metropolis, one warp per member again for the commit.  Same draws as the one-warp-per-cycle
 // implementation d_com_warp (slot = leader); the reduction order differs (per-member warp sums, then cycle order).
-__host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
 template <int POT, int KM, int TH>
 __device__ __forceinline__ void d_pcom_cycles(const DevSys &S, const SweepParams &P, const pimc_stream &st, const int c, const double maxd,
                                               unsigned char *flag, char *scratch, unsigned long long &my_beads)
@@ -764,7 +749,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
 // tail exchange); the two staging recurrences run on four lanes (bridge x dim); every SUM keeps the sequential order of the
 // one-thread reference implementation d_reshape_swap / d_swap_weights on lane 0, so results are bit-identical to it and to the oracle.
 // Shared memory (dynamic): w[N] | 2 bridges x { x[M+1], y[M+1], v[M+1], link[M+1], vold[M+1] }.
-__host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }
 __global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
 {
     extern __shared__ double sm[];
@@ -916,8 +900,6 @@ __global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys
     if (P.stats) { atomicAdd(P.stats + 0, 1ull); atomicAdd(P.stats + 2, beads); }
 }
 
-// measurement_Z_sector (measurement.jl:1-17) for every chain at one cadence hit; k = 0-based measurement index
-struct MeasParams { int nen; int en_id[PIMC_MAXE]; int nde; int de_id[PIMC_MAXD]; long long k; };
 // Energy functor (measurement.jl:92-122) with one warp per worldline (lanes stride the slices: coalesced, no index division)
 template <int POT>
 __device__ __forceinline__ void d_energy_block_fast(const DevSys &S, int c, double *red, double *E, double *Ev)
@@ -1004,17 +986,20 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
     }
 }
 template <int POT, int KM>
-__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P)
+__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
+                                                    const unsigned char *__restrict__ mdone)
 {
     __shared__ double red[96];
     const int c = blockIdx.x;
-    for (int e = 0; e < P.nen; ++e) {
+    const bool en_done = mdone && mdone[c];     // Energy of this chain was evaluated inside the sweep launch (fused)
+    for (int e = 0; e < P.nen && !en_done; ++e) {
         const EnDev &En = T->en[P.en_id[e]];
+        const long long k = P.en_k0[e] + P.ord; // the object's own count (measurement.jl:119-120)
         double E, Ev;
         if (KM > 0) d_energy_block_reg<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev);
         else d_energy_block_fast<POT>(S, c, red, &E, &Ev);
         if (threadIdx.x == 0) {
-            if (P.k < En.cap) { En.E[(size_t)P.k * S.C + c] = E; En.Ev[(size_t)P.k * S.C + c] = Ev; }
+            if (k < En.cap) { En.E[(size_t)k * S.C + c] = E; En.Ev[(size_t)k * S.C + c] = Ev; }
             double *a = En.acc + (size_t)c * 5;
             a[0] += 1.0; a[1] += E; a[2] += E * E; a[3] += Ev; a[4] += Ev * Ev;
         }

@@ -245,7 +245,10 @@ class System:                       # src/system.jl:93-168
                             "(zero_potential(), harmonic(), sin2_1d(), generate_V(), lattice())")
         else:
             spec = dict(potential)
-        spec["dv"] = dV if isinstance(dV, str) else "identity"
+        if not isinstance(dV, str) or dV not in ("zero", "identity", "gradient"):
+            raise TypeError("dV must be 'zero' (the reference's default `zero`), 'identity' (dV = identity, as the example scripts pass) or "
+                            "'gradient' (the analytic gradient of the potential descriptor); arbitrary callables cannot run inside a CUDA kernel")
+        spec["dv"] = dV
         chains = int(os.environ.get("PIMC_CHAINS", "1")) if chains is None else chains
         seed = int(os.environ.get("PIMC_SEED", str(0x5EEDB200))) if seed is None else seed
         self.schedule = schedule or os.environ.get("PIMC_SCHED", "faithful")

@@ -430,19 +430,6 @@ def test_sweep_edge_cases_bit_exact(oracle, cfg, rng_, n_it, impl):
     _run_sweep_case(oracle, cfg, rng_, n_it, impl)
 
 
-@pytest.mark.parametrize("cfg,rng_,n_it", [
-    (dict(pot="zero", dim=2, M=33, N=300, L=5.0, T=1.0, lam=1.0, Ncycle=3), 10000, 14),       # ragged M (KM = 2), one super-batch
-    (dict(pot="zero", dim=2, M=128, N=64, L=16.0, T=1.0, lam=1.0, Ncycle=2), 10000, 24),      # the C2 shape: segments up to 126 links
-    (dict(pot="harmonic", dim=2, M=128, N=64, L=6.0, T=0.5, lam=0.5, Ncycle=2), 10000, 24),   # C2 shape in a trap: rejections, wrapped windows
-    (dict(pot="harmonic", dim=2, M=64, N=600, L=8.0, T=1.0, lam=0.5, Ncycle=4), 10000, 10),   # two super-batches, several batches per sweep
-    (dict(pot="lattice", dim=2, M=40, N=33, L=8.0, T=0.5, lam=1.0 / np.pi ** 2, Ncycle=3), 500, 30),   # 12-beam lattice, window wrap
-    (dict(pot="sin2", dim=1, M=64, N=40, L=4.0, T=1.0, lam=1.0, Ncycle=5), 200, 40),          # 1-D
-], ids=["N300-M33", "C2-free", "C2-trap", "N600-M64", "lattice-N33", "1d-N40"])
-def test_sweep_gen2_bit_exact(oracle, cfg, rng_, n_it):
-    """second-generation staging sweep (pimc_sweep2.cuh: 512-thread CTAs, rank-sorted single batch) against the oracle"""
-    _run_sweep_case(oracle, cfg, rng_, n_it, 3)
-
-
 def _run_sweep_case(oracle, cfg, rng_, n_it, impl):
     ob = oracle
     e, os_ = make_pair(ob, cfg, chains=2, seed=99)
@@ -472,6 +459,212 @@ def _run_sweep_case(oracle, cfg, rng_, n_it, impl):
         assert n == len(Eo) and np.all(np.abs(E - Eo) <= 1e-12 * scale)
     Eb, Evb, n = e.energy_read_range(en_id, 1, 2)
     assert len(Eb) == min(2, max(0, n - 1)) and np.array_equal(Eb, e.energy_read(en_id, -1)[0][1:3])
+
+
+# ---- the BASELINE.json shapes, held to the oracle with the kernels bench.py times (C2, C2 in a trap, C3, C4, C5) ----
+BASELINE_SHAPES = {
+    "C2": (dict(pot="zero", dim=2, M=128, N=64, L=16.0, T=1.0, lam=1.0, Ncycle=2), [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 20)], "energy", 12),
+    "C2-trap": (dict(pot="harmonic", dim=2, M=128, N=64, L=6.0, T=0.5, lam=0.5, Ncycle=2), [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 20)], "energy", 12),
+    "C2s": (dict(pot="zero", dim=2, M=128, N=64, L=16.0, T=1.0, lam=1.0, Ncycle=2),
+            [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 20), (1, L.UPD_RESHAPE_SWAP, 20)], "energy", 18),
+    "C3": (dict(pot="harmonic", dim=2, M=100, N=256, L=16.0, T=0.5, lam=0.5, Ncycle=5),
+           [(1, L.UPD_POLYMER_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 20), (1, L.UPD_RESHAPE_SWAP, 20)], "density", 15),
+    "C4": (dict(pot="lattice", dim=2, M=256, N=128, L=8.0, T=0.2, lam=1.0 / np.pi ** 2, Ncycle=3),
+           [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 5), (20, L.UPD_RESHAPE_SWAP, 20)], "density", 9),
+    "C5": (dict(pot="harmonic", dim=2, M=64, N=1024, L=100.0, T=1.0, lam=0.5, Ncycle=10), [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 2)], "energy", 10),
+}
+
+
+def _check_against_oracle(ob, e, ge, spec, cfg, chains, measure, n_it, seed, sched_o=None, en_cap=64, nbins=500, **extra):
+    """runs the oracle on `chains` (global ids) with the same seed / schedule and compares positions, link cache, permutation, counters,
+    energies (<= 1e-12 dN/2tau) and the density histogram (integer-equal) of those chains"""
+    po = pots(ob)[cfg["pot"]][0]
+    kw = dict(dim=cfg["dim"], M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=seed)
+    kw.update(extra)
+    exact = cfg["pot"] in ("zero", "harmonic")
+    scale = cfg["dim"] * cfg["N"] / (2 * e.tau)
+    dsum = None
+    for c in chains:
+        s = ob.System(po, L=cfg["L"], chain=c, **kw)
+        ups = [(every, ob.Update(s, kind, v0)) for every, kind, v0 in spec]
+        oen, ode = ob.Energy(en_cap), ob.Density(s, nbins)
+        s.run(n_it, ups, energies=[oen] if measure == "energy" else [], densities=[ode] if measure == "density" else [],
+              sched=ob.SCHED_SWEEP if sched_o is None else sched_o)
+        r, V, bins, nxt = e.paths(c, 1)
+        ro, Vo, bo, no = s.paths()
+        assert np.array_equal(nxt[0], no), f"chain {c}: permutation differs"
+        assert np.array_equal(r[0], ro), f"chain {c}: positions differ"
+        assert np.array_equal(bins[0], bo), f"chain {c}: bins differ"
+        assert np.array_equal(V[0], Vo) if exact else close(V[0], Vo, 1e-12, 1e-14), f"chain {c}: link cache differs"
+        for (_, uid), (_, uo) in zip(ge, ups):
+            g, o = e.update_get(uid, c), uo.get()
+            assert (g["tries"], g["tries_var"], g["accepted"], g["bead_moves"], g["var"]) == (o["tries"], o["tries_var"], o["accepted"], o["bead_moves"], o["var"]), (c, g, o)
+        if measure == "energy":
+            E, Ev, n = e.energy_read(e._test_en, c)
+            Eo, Evo = oen.read()
+            assert n == len(Eo) == n_it // cfg["Ncycle"]
+            assert np.all(np.abs(E - Eo) <= 1e-12 * scale) and np.all(np.abs(Ev - Evo) <= 1e-12 * np.maximum(1.0, np.abs(Evo))), c
+        else:
+            d = ode.read()[0]
+            dsum = d if dsum is None else dsum + d
+    return dsum
+
+
+@pytest.mark.parametrize("name", sorted(BASELINE_SHAPES))
+def test_baseline_shapes_batched_kernels_vs_oracle(oracle, name):
+    """k_sweep<POT,KM> / k_swap_iter / k_measure<POT,KM> -- the per-iteration kernels bench.py times -- at every BASELINE shape against the
+    oracle: bit-exact positions / link cache / permutation / counters, E within 1e-12 dN/2tau, histogram integer-equal."""
+    ob = oracle
+    cfg, spec, measure, n_it = BASELINE_SHAPES[name]
+    chains = 2 if cfg["N"] >= 256 else 3
+    pg = pots(ob)[cfg["pot"]][1]
+    e = pj.Engine(pg, chains=chains, L_=cfg["L"], dim=cfg["dim"], M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=2025)
+    e.set_option(L.OPT_SWEEP_IMPL, 2)          # the per-iteration sweep kernels regardless of the batch size
+    ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
+    e._test_en = e.energy_create(64)
+    de = e.density_create(500)
+    st = e.run(n_it, ge, energies=[e._test_en] if measure == "energy" else [], densities=[de] if measure == "density" else [], sched=L.SCHED_SWEEP)
+    assert st["launches"] >= n_it              # one k_sweep (+ k_swap_iter, + k_measure) launch per iteration, not the persistent kernel
+    dsum = _check_against_oracle(ob, e, ge, spec, cfg, range(chains), measure, n_it, 2025)
+    if measure == "density":
+        dg, nd, _ = e.density_read(de, 500)
+        assert np.array_equal(dg, dsum) and nd == chains * (n_it // cfg["Ncycle"]) * cfg["M"]
+
+
+def test_c2_default_dispatch_at_bench_scale_vs_oracle(oracle):
+    """C2 with 128 chains = 2^20 beads: the DEFAULT dispatch (PIMC_OPT_SWEEP_IMPL = 0) picks the per-iteration kernels exactly as in bench.py;
+    Energy fused into the sweep launch (default) and the separate estimator launch give the oracle's values; spot-checked chains vs oracle."""
+    ob = oracle
+    cfg, spec, measure, n_it = BASELINE_SHAPES["C2"]
+    out = []
+    for fuse in (1, 0):
+        e = pj.Engine(pots(ob)["zero"][1], chains=128, L_=cfg["L"], dim=2, M=128, N=64, T=1.0, lam=1.0, Ncycle=2, seed=7)
+        e.set_option(L.OPT_FUSE_ENERGY, fuse)
+        ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
+        e._test_en = e.energy_create(64)
+        st = e.run(n_it, ge, energies=[e._test_en], sched=L.SCHED_SWEEP)
+        assert st["launches"] >= n_it
+        _check_against_oracle(ob, e, ge, spec, cfg, [0, 37, 127], "energy", n_it, 7)
+        out.append((e.paths(want=("r",))[0], e.energy_read(e._test_en, -1)[0]))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.all(np.abs(out[0][1] - out[1][1]) <= 1e-12 * 2 * 64 / (2 * e.tau))
+
+
+def _real_table(Lbox, g, T, M):
+    from pimc_jl_b200 import propint
+    import math
+    tau = (1.0 / T) / M
+    p = propint.build_prop_int(math.ceil(math.sqrt(2) * Lbox), g, tau)      # examples/density_SRL_lattice.jl:17
+    return p, tau
+
+
+@pytest.mark.parametrize("sched", ["faithful", "sweep"])
+@pytest.mark.parametrize("name", ["C3i", "C4i"])
+def test_interacting_baseline_scale_real_table(oracle, name, sched):
+    """The interacting BASELINE configurations at full per-chain size with the REAL pair-propagator table (propint.build_prop_int) on both
+    sides: C3i (N=256, M=100, L=16, a=0.05, r_a=1 -> 32x32 cells per slice) and C4i (N=128, M=256, l25 lattice, g=2 -> a=exp(-pi),
+    r_a from determine_nnrange); reference schedule and sweep schedule (oracle: ORA_SCHED_SWEEP_SEQ)."""
+    import math
+    from pimc_jl_b200 import propint
+    ob = oracle
+    if name == "C3i":
+        cfg = dict(pot="harmonic", dim=2, M=100, N=256, L=16.0, T=0.5, lam=0.5, Ncycle=5)
+        g = -2 * math.pi / math.log(0.05)
+        spec = [(1, L.UPD_POLYMER_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 20), (1, L.UPD_RESHAPE_SWAP, 20)]
+        p, tau = _real_table(cfg["L"], g, cfg["T"], cfg["M"])
+        r_a = 1.0
+    else:
+        cfg = dict(pot="lattice", dim=2, M=256, N=128, L=8.0, T=0.2, lam=1.0 / np.pi ** 2, Ncycle=3)
+        g = 2.0
+        spec = [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 5), (20, L.UPD_RESHAPE_SWAP, 20)]
+        p, tau = _real_table(cfg["L"], g, cfg["T"], cfg["M"])
+        r_a = propint.determine_nnrange(p, tau, 1e-20, cfg["L"])
+    ia = dict(interactions=True, g=g, r_a=r_a, tab=p["tab"], tab_lo=p["lo"], tab_hi=p["hi"])
+    chains = 2
+    e = pj.Engine(pots(ob)[cfg["pot"]][1], chains=chains, L_=cfg["L"], dim=2, M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=31, **ia)
+    assert e.a > 0 and (name != "C3i" or e.nbins == 32)
+    ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
+    de = e.density_create(500)
+    n_it = 150 if sched == "faithful" else 6
+    e.run(n_it, ge, densities=[de], sched=L.SCHED_FAITHFUL if sched == "faithful" else L.SCHED_SWEEP)
+    dsum = _check_against_oracle(ob, e, ge, spec, cfg, range(chains), "density", n_it, 31,
+                                 sched_o=ob.SCHED_FAITHFUL if sched == "faithful" else ob.SCHED_SWEEP_SEQ, **ia)
+    dg, nd, _ = e.density_read(de, 500)
+    assert np.array_equal(dg, dsum)
+
+
+def test_swap_weights_and_update_nnbins_hooks(oracle):
+    """direct tests of two C-ABI hooks: pimc_swap_weights (sampleparticles table, helper.jl:230-260) bit for bit against the oracle on
+    permuted worlds, and pimc_update_nnbins (nearest_neighbours.jl:182-196): a full rebuild leaves bins and every neighbour query unchanged."""
+    ob = oracle
+    tab, lo, hi = synthetic_table()
+    cfg = dict(pot="harmonic", dim=2, M=14, N=10, L=4.0, T=0.5, lam=0.5, Ncycle=2)
+    e, os_ = make_pair(ob, cfg, chains=2, seed=8, interactions=True, g=1.8, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi)
+    spec = [(1, L.UPD_RESHAPE_LINEAR, 5), (1, L.UPD_RESHAPE_SWAP, 5), (2, L.UPD_POLYMER_COM, 0.5)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    e.run(600, ge)
+    for s, ups in zip(os_, oo):
+        s.run(600, ups)
+    _sync_paths(e, os_)
+    assert any(not np.array_equal(s.paths()[3], np.arange(1, 11)) for s in os_)       # exchange cycles present
+    rng = np.random.default_rng(12)
+    for t in range(40):
+        c = t % 2
+        n1 = int(rng.integers(1, 11)); j0 = int(rng.integers(1, 15)); m = int(rng.integers(2, 13))
+        w = np.zeros(10)
+        ob.lib().ora_swap_weights(os_[c].h, n1, j0, m, ob._p(w))
+        assert np.array_equal(e.swap_weights(c, n1, j0, m), w), (t, n1, j0, m)
+    q = [(int(rng.integers(0, 2)), rng.uniform(-4, 4, 2), int(rng.integers(1, 15)), int(rng.integers(1, 11))) for _ in range(40)]
+    before = [(e.find_nn(c, r, j, x), sorted(e.find_nns(c, r, j, x).tolist())) for c, r, j, x in q]
+    b0 = e.paths(want=("bins",))[2]
+    e.update_nnbins()
+    for s in os_:
+        ob.lib().ora_update_nnbins(s.h)
+    assert np.array_equal(e.paths(want=("bins",))[2], b0)
+    after = [(e.find_nn(c, r, j, x), sorted(e.find_nns(c, r, j, x).tolist())) for c, r, j, x in q]
+    assert before == after
+    for (c, r, j, x), (nn, nns) in zip(q, after):
+        ex = np.array([x], dtype=np.int64)
+        assert nn == ob.lib().ora_find_nn(os_[c].h, ob._p(r.copy()), j, ob._pi(ex), 1)
+        out = np.zeros(64, dtype=np.int64)
+        cnt = ob.lib().ora_find_nns_pos(os_[c].h, ob._p(r.copy()), j, ob._pi(ex), 1, ob._pi(out))
+        assert nns == sorted(out[:cnt].tolist())
+    # the rebuilt lists carry on: further moves stay on the oracle's trajectory
+    e.run(100, ge)
+    for s, ups in zip(os_, oo):
+        s.run(100, ups)
+    _sync_paths(e, os_)
+
+
+def test_energy_objects_count_their_own_samples(oracle):
+    """An Energy object appends at ITS OWN first free slot (measurement.jl:119-120), not at the System's N_MC: thermalise with a Density
+    only, then add an Energy; use two Energy objects in different runs.  Both schedules / kernels."""
+    ob = oracle
+    cfg = CONFIGS[1]
+    for impl, sched in ((1, L.SCHED_FAITHFUL), (2, L.SCHED_SWEEP)):
+        e, os_ = make_pair(ob, cfg, chains=2, seed=5)
+        e.set_option(L.OPT_SWEEP_IMPL, impl)
+        spec = [(1, L.UPD_SINGLE_COM, 1.0), (1, L.UPD_RESHAPE_LINEAR, 6)]
+        ge, oo = _mk_updates(ob, e, os_, spec)
+        d, e1, e2 = e.density_create(16), e.energy_create(10), e.energy_create(10)
+        od = [ob.Density(s, 16) for s in os_]
+        o1, o2 = [ob.Energy(10) for _ in os_], [ob.Energy(10) for _ in os_]
+        so = ob.SCHED_FAITHFUL if sched == L.SCHED_FAITHFUL else ob.SCHED_SWEEP
+        e.run(12, ge, densities=[d], sched=sched)                      # 6 measurements, no Energy
+        e.run(8, ge, energies=[e1], sched=sched)                       # 4 samples into e1 at indices 0..3
+        e.run(6, ge, energies=[e2, e1], sched=sched)                   # 3 samples: e2 at 0..2, e1 at 4..6
+        for c, (s, ups) in enumerate(zip(os_, oo)):
+            s.run(12, ups, densities=[od[c]], sched=so)
+            s.run(8, ups, energies=[o1[c]], sched=so)
+            s.run(6, ups, energies=[o2[c], o1[c]], sched=so)
+        scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+        for c in range(2):
+            for gid, oe, cnt in ((e1, o1[c], 7), (e2, o2[c], 3)):
+                E, Ev, n = e.energy_read(gid, c)
+                Eo, _ = oe.read()
+                assert n == cnt == len(Eo) and len(E) == cnt and np.all(np.abs(E - Eo) <= 1e-12 * scale), (impl, c, n, E, Eo)
+        with pytest.raises(pj.PimcError):
+            e.run(8, ge, energies=[e1], sched=sched)                   # 7 + 4 > 10: the reference errors on a full vector
 
 
 def test_golden_vectors():
