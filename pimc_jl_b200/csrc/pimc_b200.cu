@@ -95,8 +95,7 @@ __global__ void k_cells_build(DevSys S, int c0, int nc)
     size_t total = (size_t)nc * M;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int c = c0 + (int)(idx / M), j = (int)(idx % M);
-        int *head = S.cell_head + ((size_t)c * M + j) * S.ncell;
-        for (int b = 0; b < S.ncell; ++b) head[b] = -1;
+        for (int b = 0; b < S.ncell; ++b) S.cell_head[HIDX(S, c, j, b)] = -1;
         for (int n = N - 1; n >= 0; --n) // push-front in reverse keeps ascending particle order in every list
             d_cell_insert(S, c, j, n, d_bin(S, S.r[RIDX(S, c, n, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, n, 1, j)] : 0.0));
     }
@@ -228,10 +227,8 @@ __global__ void k_find_nns(DevSys S, int c, double x, double y, int j, int exc, 
 {
     if (threadIdx.x != 0) return;
     int b = d_bin(S, x, y), nst = S.dim == 2 ? 9 : 3; long long cnt = 0;
-    const int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell;
-    const int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
     for (int q = 0; q < nst; ++q)
-        for (int o = head[d_stencil(S, b, q)]; o >= 0; o = nxt[o]) {
+        for (int o = S.cell_head[HIDX(S, c, j, d_stencil(S, b, q))]; o >= 0; o = S.cell_next[NIDX(S, c, j, o)]) {
             if (o == exc) continue;
             if (d_peuclid(S, S.r[RIDX(S, c, o, 0, j)], S.dim > 1 ? S.r[RIDX(S, c, o, 1, j)] : 0.0, x, y) <= S.cellw) { if (cnt < cap) out[cnt] = o + 1; cnt++; }
         }

@@ -36,8 +36,8 @@ struct DevSys {
     int need_cells, nbins, ncell;
     double cellw;
     int *bins;      // [C][N][M]  0-based cell of every bead
-    int *cell_head; // [C][M][ncell]
-    int *cell_next; // [C][M][N]
+    int *cell_head; // [C][ncell][M]  cell-major, slice fastest: consecutive beads of a worldline sit in the same or a neighbouring cell, so lanes
+    int *cell_next; // [C][N][M]      that stride the slices of one worldline read contiguous heads / successors (HIDX / NIDX below)
     unsigned char *mult; // [C][N][M] multiplicity of the bead in its cell list (2 after a cycle-merging swap: add_nn! twice)
     const double *tab; int tab_n; double tab_lo, tab_hi;
     PotDev pot;
@@ -73,6 +73,8 @@ struct RunParams {
 
 #define RIDX(S, c, n, k, j) ((((size_t)(c) * (S).N + (n)) * (S).dim + (k)) * (S).M + (j))
 #define VIDX(S, c, n, j)    (((size_t)(c) * (S).N + (n)) * (S).M + (j))
+#define HIDX(S, c, j, b)    (((size_t)(c) * (S).ncell + (b)) * (S).M + (j))   /* head of the list of cell b at slice j */
+#define NIDX(S, c, j, n)    (((size_t)(c) * (S).N + (n)) * (S).M + (j))       /* successor of particle n in its list at slice j */
 
 // ---------------- src/propagator.jl ----------------
 __device__ __forceinline__ double d_distance(double x1, double x2, double L) // propagator.jl:6-9
@@ -262,18 +264,18 @@ __device__ __forceinline__ double d_peuclid(const DevSys &S, double ax, double a
 __device__ __forceinline__ void d_cell_remove(const DevSys &S, int c, int j, int n)
 {
     int b = S.bins[VIDX(S, c, n, j)];
-    int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell + b;
-    int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
+    int *head = S.cell_head + HIDX(S, c, j, b);
+    int *nxt = S.cell_next + NIDX(S, c, j, 0);          // successor of particle p: nxt[(size_t)p * M]
+    const size_t M = (size_t)S.M;
     int p = *head, prev = -1;
-    while (p >= 0 && p != n) { prev = p; p = nxt[p]; }
+    while (p >= 0 && p != n) { prev = p; p = nxt[p * M]; }
     if (p < 0) return;
-    if (prev < 0) *head = nxt[p]; else nxt[prev] = nxt[p];
+    if (prev < 0) *head = nxt[p * M]; else nxt[prev * M] = nxt[p * M];
 }
 __device__ __forceinline__ void d_cell_insert(const DevSys &S, int c, int j, int n, int b)
 {
-    int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell + b;
-    int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
-    nxt[n] = *head; *head = n;
+    int *head = S.cell_head + HIDX(S, c, j, b);
+    S.cell_next[NIDX(S, c, j, n)] = *head; *head = n;
     S.bins[VIDX(S, c, n, j)] = b;
     S.mult[VIDX(S, c, n, j)] = 1;
 }
@@ -290,15 +292,13 @@ struct NbFirst { int h[9], n[9]; double x[9], y[9]; };
 __device__ __forceinline__ void d_nb_first(const DevSys &S, int c, int j, int b, NbFirst &F)
 {
     const int nst = S.dim == 2 ? 9 : 3;
-    const int *head = S.cell_head + ((size_t)c * S.M + j) * S.ncell;
-    const int *nxt = S.cell_next + ((size_t)c * S.M + j) * S.N;
 #pragma unroll
-    for (int q = 0; q < 9; ++q) F.h[q] = q < nst ? head[d_stencil(S, b, q)] : -1;
+    for (int q = 0; q < 9; ++q) F.h[q] = q < nst ? S.cell_head[HIDX(S, c, j, d_stencil(S, b, q))] : -1;
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
         F.n[q] = -1; F.x[q] = 0.0; F.y[q] = 0.0;
         if (F.h[q] >= 0) {
-            F.n[q] = nxt[F.h[q]];
+            F.n[q] = S.cell_next[NIDX(S, c, j, F.h[q])];
             F.x[q] = S.r[RIDX(S, c, F.h[q], 0, j)];
             if (S.dim > 1) F.y[q] = S.r[RIDX(S, c, F.h[q], 1, j)];
         }
@@ -312,7 +312,7 @@ __device__ __forceinline__ void d_nb_first(const DevSys &S, int c, int j, int b,
             __VA_ARGS__                                                                                              \
             o = on_;                                                                                                 \
             if (o >= 0) {                                                                                            \
-                on_ = (S_).cell_next[((size_t)(c_) * (S_).M + (j_)) * (S_).N + o];                                   \
+                on_ = (S_).cell_next[NIDX(S_, c_, j_, o)];                                                           \
                 ox = (S_).r[RIDX(S_, c_, o, 0, j_)]; oy = (S_).dim > 1 ? (S_).r[RIDX(S_, c_, o, 1, j_)] : 0.0;       \
             }                                                                                                        \
         }                                                                                                            \
