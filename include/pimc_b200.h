@@ -31,7 +31,7 @@ extern "C" {
 
 /* Potential descriptor: the reference passes Julia closures `V`, `dV` (src/system.jl:114-115,129-131);
  * a kernel cannot call them, so the shim lowers them to one of these families
- * (examples/*.jl, test/testsystem.jl:13, examples/tools/potentialtools.jl:1-39). */
+ * (examples/ *.jl, test/testsystem.jl:13, examples/tools/potentialtools.jl:1-39). */
 enum { PIMC_POT_ZERO = 0, PIMC_POT_HARMONIC = 1, PIMC_POT_SIN2_1D = 2, PIMC_POT_LATTICE = 3 };
 enum { PIMC_DV_ZERO = 0, PIMC_DV_IDENTITY = 1, PIMC_DV_GRADIENT = 2 };
 #define PIMC_MAX_ANGLES 32
@@ -100,6 +100,10 @@ int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run k
 /* PIMC_OPT_FUSE_ENERGY: 1 (default) evaluates the Energy functor inside the sweep launch for chains whose picked update streamed every
  * worldline anyway; 0 always uses the separate estimator launch (A/B, same values to 1e-12) */
 #define PIMC_OPT_FUSE_ENERGY 3
+/* PIMC_OPT_ISWEEP: sweep schedule of interacting worldlines: 1 (default) optimistic-parallel per-iteration kernels where they apply
+ * (hard core, pair action not counted in ReshapeLinear / centre-of-mass moves = the reference as shipped); 0 the sequential sweep inside
+ * the persistent kernel (A/B: identical trajectories) */
+#define PIMC_OPT_ISWEEP 4
 int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
 /* measurement utility (no reference counterpart): sustained non-tensor fp64 FMA rate of the current device, in TFLOP/s */
@@ -111,6 +115,14 @@ int pimc_get_paths(pimc_handle *h, int32_t chain0, int32_t nchains, double *r, d
 int pimc_set_paths(pimc_handle *h, int32_t chain0, int32_t nchains, const double *r, const int64_t *next);
 int pimc_get_scalars(pimc_handle *h, double *out5 /* beta,tau,vol,a,r_a */, int64_t *iout5 /* nbins,N_MC,Nctr,ctr,iter */);
 int pimc_set_iter(pimc_handle *h, uint64_t iter);
+/* checkpoint / resume (the reference's examples/tools/savetools.jl:4-34 saves the paths only): the COMPLETE state of every chain
+ * as one opaque host blob -- positions, permutation, cached link actions, cell lists (order and multiplicities), the iteration counter of the
+ * addressed RNG, N_MC / Nctr, every update object's variable / counters / acceptance window, every estimator's accumulators.
+ * pimc_set_state needs a handle of the same System with the same update / Energy / Density objects created in the same order;
+ * the run then continues bit for bit. */
+int pimc_state_size(pimc_handle *h, int64_t *bytes);
+int pimc_get_state(pimc_handle *h, void *buf, int64_t cap);
+int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes);
 
 /* ---- propagator primitives, evaluated on the device (parity hooks; src/propagator.jl) ---- */
 int pimc_distance(int64_t n, const double *x1, const double *x2, double L, double *out);          /* :6-9   */
@@ -167,6 +179,15 @@ int pimc_density_create(pimc_handle *h, int64_t nbins, int32_t *id);
 int pimc_density_measure(pimc_handle *h, int32_t id);                   /* Density functor now, src/measurement.jl:45-55 */
 /* dens: nbins^dim counts (column-major like the Julia array), summed over this handle's chains; ndata likewise */
 int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64_t *ndata, double *bin);
+
+/* ---- pair propagator of interacting Systems: host-side construction, no GPU needed (csrc/pimc_propint.cu) ---- */
+/* prop_rel_interpolate_terms (src/propagator.jl:34-70): the sampled term table on range(1e-20, L, delta)^2 (delta = 600 in the reference),
+ * column-major delta x delta = the `tab` of pimc_config; *lo = 1e-20, *hi = L */
+int pimc_build_prop_table(double L, double g0, double tau, int32_t delta, double *tab, double *lo, double *hi);
+/* prop_int(r1_rel, r2_rel, tau) = 1 + terms(|r1|, |r2|) / prop_rel0(r1, r2, tau), the closure build_prop_int returns (src/propagator.jl:73-89) */
+int pimc_prop_int(const double *tab, int32_t n, double lo, double hi, const double *r1_rel, const double *r2_rel, int32_t dim, double tau, double *out);
+/* determine_nnrange(propint, tau, a, b) (src/system.jl:10-15); pimc_create calls it with (1e-20, L) when interactions != 0 and r_a == 0 (system.jl:29-31) */
+int pimc_determine_nnrange(const double *tab, int32_t n, double lo, double hi, double tau, double a, double b, double *r_a);
 
 /* ---- run! (src/simulation.jl:29-42) on every chain ---- */
 int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,

@@ -1,9 +1,11 @@
 # Pimc.jl -- drop-in shim: the exported API of oameye/PIMC.jl (src/Pimc.jl:15-26) over libpimc_b200.so (include/pimc_b200.h).
 #
-# UNEXECUTED in this repository's CI: the build image has no Julia.  The same C entry points are exercised through the
-# Python mirror pimc_jl_b200/pimc.py.  Shipped example scripts (examples/energy_2d_*.jl, density_*.jl) run against this module
-# unchanged: `System`, the update constructors, `Energy`/`Density`, `run!`, `acceptance`, and the fields the example tools read
-# (s.N, s.M, s.L, s.β, s.τ, s.μ, s.a, s.Ncycle, s.N_MC, s.world[n].{r,V,bins,next}, u.var.size/m, u.counter_var.queue, d.dens ...).
+# UNEXECUTED in this repository's CI: the build image has no Julia.  The same C entry points, in the same order, are exercised through the
+# Python mirror pimc_jl_b200/pimc.py and by the C drivers tests/c/example_*.c (the call sequence of the shipped scripts through the C ABI).
+# The shipped example scripts (examples/energy_2d_*.jl, density_2d_*.jl, density_SRL_lattice.jl) are written against the surface this
+# module provides: `System`, `build_prop_int`, the update constructors, `Energy`/`Density`, `run!`, `acceptance`, and the fields the
+# example tools read (s.N, s.M, s.L, s.β, s.τ, s.μ, s.a, s.Ncycle, s.N_MC, s.world[n].{r,V,bins,next}, s.nn, s.nbs, s.lnV/lnK/lnU,
+# u.var.size/m, u.counter_var.queue, d.dens ...).
 #
 # Environment: PIMC_B200_LIB (path of the .so), PIMC_CHAINS (independent replicas, default 1), PIMC_SEED,
 #              PIMC_SCHED = "faithful" (default: exactly run!) | "sweep" (batched schedule, DESIGN.md section 3).
@@ -11,7 +13,7 @@ module Pimc
 
 using Libdl, Random
 
-export System, run!, build_prop_int, acceptance, Coord
+export System, run!, build_prop_int, acceptance, Coord, determine_nnrange
 export Worldline, Particle, levy!, distance, update_nnbins!, disallowmissing, apply!, bin, lnV
 export subcycle, pcycle, Update, Updates
 export Counter, Step, NumbOfSlices
@@ -113,7 +115,7 @@ mutable struct System
     dim::Int64; M::Int64; N::Int64; Ninit::Int64; μ::Float64; λ::Float64; L::Float64; vol::Float64; β::Float64; τ::Float64
     a::Float64; nbins::Int64; Ncycle::Int64; measure_scheme::Symbol; chains::Int64; sched::Int32
     V::Function; dV::Function
-    tab::Matrix{Float64}                       # keeps the propagator table alive
+    tab::Matrix{Float64}; tab_lo::Float64; tab_hi::Float64     # keeps the propagator table alive
     function System(potential::Function; dV::Function = zero, dim::Int64 = 2, M::Int64 = 100, N::Int64 = 2, μ::Float64 = 0.0,
                     L::Float64 = 4.0, T::Float64 = 1.0, λ::Float64 = 1.0, interactions::Bool = false, propint = _ -> 0.0,
                     g::Float64 = 0.0, rₐ::Float64 = 0.0, length_measurement_cycle::Int64 = 10, measure_scheme::Symbol = :c,
@@ -122,11 +124,16 @@ mutable struct System
         pot = lower_potential(potential, dV, dim, L)
         tab = zeros(0, 0); lo = hi = 0.0
         if interactions
-            # build_prop_int (src/propagator.jl:79-89) returns a closure over the interpolated term table `terms`
-            terms = capt(propint, :terms)
-            terms === nothing && error("interactions=true needs propint = build_prop_int(L, g, τ)")
-            tab = Matrix{Float64}(terms.itp.coefs); lo = first(terms.ranges[1]); hi = last(terms.ranges[1])
-            rₐ == 0.0 && error("pass rₐ: determine_nnrange (Optim/Roots, src/system.jl:10-15) is not part of the B200 path")
+            if propint isa PropInt               # this module's build_prop_int
+                tab = propint.tab; lo = propint.lo; hi = propint.hi
+            else                                 # the reference package's closure over the interpolated term table `terms` (src/propagator.jl:80)
+                terms = capt(propint, :terms)
+                terms === nothing && error("interactions=true needs propint = build_prop_int(L, g, τ)")
+                tab = Matrix{Float64}(terms.itp.coefs); lo = first(terms.ranges[1]); hi = last(terms.ranges[1])
+            end
+            # rₐ == 0.0: init_int (src/system.jl:29-31) takes the cut-off from the propagator; pimc_create does the same (pimc_determine_nnrange).
+            # Note the shipped script never forwards g (examples/density_SRL_lattice.jl:18-19): g = 0.0 => a = exp(-2π/0.0) = 0.0 (system.jl:151),
+            # no hard core, the interaction enters through lnU only -- reproduced as is.
         end
         cfg = Ref(CConfig(dim, M, N, chains, 0, μ, λ, L, T, interactions, g, rₐ, length_measurement_cycle, 15, 1, seed, pot,
                           isempty(tab) ? C_NULL : pointer(tab), size(tab, 1), lo, hi, -1))
@@ -136,7 +143,7 @@ mutable struct System
         check(h[], ccall((:pimc_get_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}), h[], sc, isc))
         sched = get(ENV, "PIMC_SCHED", "faithful") == "sweep" ? Int32(1) : Int32(0)
         s = new(h[], dim, M, N, N, μ, λ, L, sc[3], sc[1], sc[2], sc[4], isc[1], length_measurement_cycle, measure_scheme, chains, sched,
-                potential, dV, tab)
+                potential, dV, tab, lo, hi)
         finalizer(x -> (ccall((:pimc_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), s)
         return s
     end
@@ -160,7 +167,41 @@ function Base.getproperty(s::System, f::Symbol)
     f === :Nctr && return Dict{Int64,Int64}(getfield(s, :N) => scalars(s)[2][3])
     f === :ctr && return scalars(s)[2][4]
     f === :lnV && return (x1, x2) -> lnV(x1, x2, getfield(s, :τ), getfield(s, :V))
+    f === :lnK && return (x1, x2, τ) -> lnK(x1, x2, getfield(s, :λ), τ, getfield(s, :L))          # slot order of system.jl:163
+    f === :lnU && return (r1, r2) -> lnU(s, r1, r2)
+    f === :rₐ && return scalars(s)[1][5]
+    f === :nbs && return Vector{Int64}[bin_neighbors(i, getfield(s, :nbins), getfield(s, :dim)) for i in 1:getfield(s, :nbins)^getfield(s, :dim)]
+    f === :nn && return nn_lists(s)
     return getfield(s, f)
+end
+"""lnK(x1, x2, λ, τ, L) (src/propagator.jl:16-19), evaluated on the device"""
+function lnK(x1::AbstractVector{Float64}, x2::AbstractVector{Float64}, λ::Float64, τ::Float64, L::Float64)::Float64
+    out = Ref(0.0); a = Vector{Float64}(x1); b = Vector{Float64}(x2)
+    check(C_NULL, ccall((:pimc_lnK, LIB), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Float64, Ref{Float64}), 1, a, b, length(a), τ, λ, L, out))
+    out[]
+end
+"""s.lnU(r1_rel, r2_rel) (src/system.jl:25-27): 0 without interactions; propint < 0 ? -μ : log(propint)"""
+function lnU(s::System, r1::AbstractVector{Float64}, r2::AbstractVector{Float64})::Float64
+    isempty(getfield(s, :tab)) && return 0.0
+    p = PropInt(getfield(s, :tab), getfield(s, :tab_lo), getfield(s, :tab_hi))(r1, r2, getfield(s, :τ))
+    p < 0.0 ? -getfield(s, :μ) : log(p)
+end
+bin_index(x::Int64, y::Int64, w::Int64)::Int64 = x + w * y + 1                     # src/nearest_neighbours.jl:6-16
+bin_index(x::Int64, w::Int64)::Int64 = x + 1
+function bin_neighbors(b::Int64, nbins::Int64, dim::Int64)::Vector{Int64}          # src/nearest_neighbours.jl:52-63
+    x = rem(b - 1, nbins)
+    dim == 2 || return [bin_index(mod(x + dx, nbins), nbins) for dx in (0, -1, 1)]
+    y = div(b - 1, nbins)
+    [bin_index(mod(x + dx, nbins), mod(y + dy, nbins), nbins) for (dx, dy) in ((0, 0), (-1, 1), (0, 1), (1, 1), (-1, 0), (1, 0), (-1, -1), (0, -1), (1, -1))]
+end
+"""s.nn (src/system.jl:109): per time slice, per cell, the particles in it -- rebuilt from the device's bins (list order: ascending index)"""
+function nn_lists(s::System; chain::Integer = 0)
+    w = world(s; chain = chain); nb = getfield(s, :nbins)^getfield(s, :dim)
+    nn = [[Int64[] for _ in 1:nb] for _ in 1:getfield(s, :M)]
+    for (i, p) in enumerate(w), m in 1:getfield(s, :M)
+        p.bins[m] >= 1 && push!(nn[m][p.bins[m]], i)
+    end
+    nn
 end
 update_nnbins!(s::System) = check(s.h, ccall((:pimc_update_nnbins, LIB), Cint, (Ptr{Cvoid},), s.h))
 
@@ -292,6 +333,29 @@ function subcycle(p::Vector{Worldline}, n::Int64)::Tuple{Int64,Vector{Int64}}   
     return length(cycle), cycle
 end
 pcycle(j::Int64, pol::Vector{Int64}, Npol::Int64, M::Int64)::Int64 = pol[mod1(1 + floor(Int64, (j - 1) / M), Npol)]  # helper.jl:113-115
-build_prop_int(args...) = error("build_prop_int (QuadGK/Bessel table construction, src/propagator.jl:35-89) is host-side and out of scope of the " *
-                                "B200 path: build it with the reference package and pass the closure as `propint`")
+# ---- pair propagator (src/propagator.jl:34-89): table built by the library's host code, csrc/pimc_propint.cu --------------
+"""What `build_prop_int` returns: callable like the reference's closure `prop_int(r1_rel, r2_rel, τ)`, and carrying the sampled
+term table (`terms` of src/propagator.jl:80) that `System(...; interactions = true, propint)` hands to the device."""
+struct PropInt <: Function
+    tab::Matrix{Float64}; lo::Float64; hi::Float64
+end
+function build_prop_int(L::Float64, g0::Float64, τ::Float64; Δ::Integer = 600)::PropInt
+    tab = Matrix{Float64}(undef, Δ, Δ); lo = Ref(0.0); hi = Ref(0.0)
+    check(C_NULL, ccall((:pimc_build_prop_table, LIB), Cint, (Float64, Float64, Float64, Int32, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+                        L, g0, τ, Δ, tab, lo, hi))
+    PropInt(tab, lo[], hi[])
+end
+function (p::PropInt)(r1_rel::AbstractVector{Float64}, r2_rel::AbstractVector{Float64}, τ::Float64)::Float64
+    out = Ref(0.0); a = Vector{Float64}(r1_rel); b = Vector{Float64}(r2_rel)
+    check(C_NULL, ccall((:pimc_prop_int, LIB), Cint, (Ptr{Float64}, Int32, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ref{Float64}),
+                        p.tab, size(p.tab, 1), p.lo, p.hi, a, b, length(a), τ, out))
+    out[]
+end
+function determine_nnrange(p::PropInt, τ::Float64, a::Float64, b::Float64)::Float64   # src/system.jl:10-15
+    out = Ref(0.0)
+    rc = ccall((:pimc_determine_nnrange, LIB), Cint, (Ptr{Float64}, Int32, Float64, Float64, Float64, Float64, Float64, Ref{Float64}),
+               p.tab, size(p.tab, 1), p.lo, p.hi, τ, a, b, out)
+    rc == 0 || error("determine_nnrange: no sign change of propint - 0.999 on (r_min, b)")
+    out[]
+end
 end # module

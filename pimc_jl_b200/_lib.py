@@ -18,6 +18,7 @@ SCHED_FAITHFUL, SCHED_SWEEP = 0, 1
 OPT_SWEEP_IMPL = 1
 OPT_FAITHFUL_IMPL = 2
 OPT_FUSE_ENERGY = 3
+OPT_ISWEEP = 4
 COMPAT_PAIR_BYVALUE, COMPAT_SWAP_SIGN, COMPAT_DENSITY_SHIFT, COMPAT_SWAP_STALE_LINK, COMPAT_ALL = 1, 2, 4, 8, 15
 
 f64p = C.POINTER(C.c_double)
@@ -69,6 +70,9 @@ SIGNATURES = {
     "pimc_set_paths": (C.c_int, [_vp, _i32, _i32, f64p, i64p]),
     "pimc_get_scalars": (C.c_int, [_vp, f64p, i64p]),
     "pimc_set_iter": (C.c_int, [_vp, _u64]),
+    "pimc_state_size": (C.c_int, [_vp, i64p]),
+    "pimc_get_state": (C.c_int, [_vp, _vp, _i64]),
+    "pimc_set_state": (C.c_int, [_vp, _vp, _i64]),
     "pimc_distance": (C.c_int, [_i64, f64p, f64p, _d, f64p]),
     "pimc_teleport": (C.c_int, [_i64, f64p, _d, f64p]),
     "pimc_lnK": (C.c_int, [_i64, f64p, f64p, _i32, _d, _d, _d, f64p]),
@@ -95,6 +99,9 @@ SIGNATURES = {
     "pimc_density_create": (C.c_int, [_vp, _i64, i32p]),
     "pimc_density_measure": (C.c_int, [_vp, _i32]),
     "pimc_density_read": (C.c_int, [_vp, _i32, f64p, i64p, f64p]),
+    "pimc_build_prop_table": (C.c_int, [_d, _d, _d, _i32, f64p, f64p, f64p]),
+    "pimc_prop_int": (C.c_int, [f64p, _i32, _d, _d, f64p, f64p, _i32, _d, f64p]),
+    "pimc_determine_nnrange": (C.c_int, [f64p, _i32, _d, _d, _d, _d, _d, f64p]),
     "pimc_run": (C.c_int, [_vp, _i64, i32p, i64p, _i32, i32p, _i32, i32p, _i32, _i32, C.POINTER(RunStats)]),
 }
 

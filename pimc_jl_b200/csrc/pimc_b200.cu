@@ -253,7 +253,8 @@ struct pimc_handle {
     long long en_cap[PIMC_MAXE];
     long long en_count[PIMC_MAXE];   // samples every Energy object holds (its own count, measurement.jl:119-120)
     unsigned char *mdone;            // [C] per-chain flag: Energy of the current measurement evaluated inside the sweep launch
-    int opt_fuse_energy;
+    int opt_fuse_energy, opt_isweep;
+    int *nw_head, *nw_next;          // second cell list over proposed positions (optimistic sweep of interacting worldlines), lazily allocated
     unsigned long long *dstats;
     std::vector<void *> allocs;
     long long de_ndata[PIMC_MAXD];
@@ -357,7 +358,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr;
     memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
     int rc = PIMC_OK;
@@ -375,7 +376,11 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     h->r_a = cfg->r_a;
     if (h->r_a == 0.0) {
         if (!cfg->interactions) h->r_a = cfg->L / 4; // system.jl:22-24
-        else { snprintf(g_err, sizeof g_err, "interactions with r_a == 0 need determine_nnrange (Optim/Roots, system.jl:10-15): out of scope, pass r_a"); pimc_destroy(h); return PIMC_ERR_UNSUPPORTED; }
+        else {   // init_int (system.jl:29-31): the cut-off comes from the propagator itself, determine_nnrange(propint, tau, 1e-20, L)
+            if (!cfg->tab || cfg->tab_n < 2) { snprintf(g_err, sizeof g_err, "interactions = true needs the pair-propagator table (pimc_build_prop_table)"); pimc_destroy(h); return PIMC_ERR_INVALID; }
+            if (pimc_determine_nnrange(cfg->tab, cfg->tab_n, cfg->tab_lo, cfg->tab_hi, S.tau, 1e-20, cfg->L, &h->r_a) != PIMC_OK) {
+                snprintf(g_err, sizeof g_err, "determine_nnrange: no sign change of propint - 0.999 on (r_min, L) (Roots.find_zero would throw, system.jl:14)"); pimc_destroy(h); return PIMC_ERR_STATE; }
+        }
     }
     S.nbins = (int)floor((2 * cfg->L) / h->r_a); if (S.nbins < 1) S.nbins = 1; // system.jl:81
     S.ncell = cfg->dim == 2 ? S.nbins * S.nbins : S.nbins;
@@ -393,7 +398,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
         CKC(cudaMemcpy(t, cfg->tab, sizeof(double) * cfg->tab_n * cfg->tab_n, cudaMemcpyHostToDevice));
         S.tab = t; S.tab_n = cfg->tab_n; S.tab_lo = cfg->tab_lo; S.tab_hi = cfg->tab_hi;
     }
-    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 16)); RCC(dalloc(h, &h->dS, 1));
+    RCC(dalloc(h, &h->dT, 1)); RCC(dalloc(h, &h->dstats, 32)); RCC(dalloc(h, &h->dS, 1));
     {   // table of the division-free log of the Gaussian transform (include/pimc_rng.h), filled with IEEE operations on the host
         double htab[2 * PIMC_LOGTAB_N]; pimc_logtab_fill(htab);
         double *dl; RCC(dalloc(h, &dl, 2 * PIMC_LOGTAB_N));
@@ -429,6 +434,7 @@ extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
     if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FAITHFUL_IMPL && value >= 0 && value <= 1) { h->opt_faithful_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FUSE_ENERGY && value >= 0 && value <= 1) { h->opt_fuse_energy = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_ISWEEP && value >= 0 && value <= 1) { h->opt_isweep = (int)value; return PIMC_OK; }
     SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
 }
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
@@ -861,7 +867,7 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         const long long cnt = h->en_count[P.en_id[i]];
         if (cnt + nmeas > h->T.en[P.en_id[i]].cap) { SETERR(h, "Energy buffer of %lld entries would overflow (%lld + %lld)", (long long)h->T.en[P.en_id[i]].cap, cnt, nmeas); return PIMC_ERR_STATE; }
     }
-    CK(h, cudaMemsetAsync(h->dstats, 0, 16 * sizeof(unsigned long long), h->stream));
+    CK(h, cudaMemsetAsync(h->dstats, 0, 32 * sizeof(unsigned long long), h->stream));
     // FAITHFUL: warp 0 owns the proposal; large chains get three more warps for the estimators (Energy / Density stream N*M beads)
     int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? (S.need_cells ? PIMC_CELLS_THREADS : 64) : 32);
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
@@ -899,8 +905,48 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     const bool batched_ok = sched == PIMC_SCHED_SWEEP && !S.need_cells && S.M <= 256 && smem_rs <= 200 * 1024 && smem_cs <= 200 * 1024;
     bool batched = batched_ok && (h->opt_sweep_impl >= 2 || (h->opt_sweep_impl == 0 && (size_t)S.C * S.N * S.M >= (size_t)1 << 20));
     if (h->opt_sweep_impl >= 2 && sched == PIMC_SCHED_SWEEP && !batched_ok) { SETERR(h, "per-iteration sweep kernels need independent worldlines and M <= %d", 256); return PIMC_ERR_UNSUPPORTED; }
+    // optimistic-parallel sweep of interacting worldlines (pimc_isweep.cuh): the hard core is the only coupling between the proposals of a
+    // sweep when the pair action does not enter ReshapeLinear / centre-of-mass moves (the reference as shipped, compat PAIR_BYVALUE)
+    const bool pair_in_moves = S.interactions && !(S.compat & PIMC_COMPAT_PAIR_BYVALUE);
+    const bool isweep = sched == PIMC_SCHED_SWEEP && S.need_cells && S.a > 0.0 && !pair_in_moves && h->opt_isweep != 0 && h->opt_faithful_impl == 0 &&
+                        S.M <= 256 && S.N <= 8192 && isw_rs_smem_bytes(S.N, S.M) <= 200 * 1024;
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    if (n > 0 && !batched) {
+    if (n > 0 && isweep) {
+        if (!h->nw_head) {
+            int rc = dalloc(h, &h->nw_head, (size_t)S.C * S.ncell * S.M); if (rc) return rc;
+            rc = dalloc(h, &h->nw_next, (size_t)S.C * S.N * S.M); if (rc) return rc;
+            CK(h, cudaMemset(h->nw_head, 0xFF, sizeof(int) * (size_t)S.C * S.ncell * S.M));
+        }
+        bool has_rs = false, has_com = false, has_swap = false;
+        for (int i = 0; i < nupd; ++i) { int k = h->T.upd[update_ids[i]].kind; has_rs |= k == PIMC_UPD_RESHAPE_LINEAR; has_swap |= k == PIMC_UPD_RESHAPE_SWAP; has_com |= (k == PIMC_UPD_SINGLE_COM || k == PIMC_UPD_POLYMER_COM); }
+        ISweepParams IP; memset(&IP, 0, sizeof IP);
+        SweepParams &SP = IP.sp;
+        SP.nupd = nupd; SP.stats = h->dstats; SP.Sg = h->dS;
+        pimc_roundkeys_make(S.seed, &SP.rk);
+        for (int i = 0; i < nupd; ++i) { SP.kind[i] = h->T.upd[update_ids[i]].kind; SP.vmax[i] = h->T.upd[update_ids[i]].vmax; SP.upd_id[i] = P.upd_id[i]; SP.w[i] = P.w[i]; IP.upd[i] = h->T.upd[update_ids[i]]; }
+        IP.nw_head = h->nw_head; IP.nw_next = h->nw_next; IP.prof = P.prof;
+        Sweep2Params SW; memset(&SW, 0, sizeof SW);
+        for (int i = 0; i < nupd; ++i) SW.upd[i] = h->T.upd[update_ids[i]];
+        if (has_swap && faithful_scratch_doubles(S.N, S.M) * sizeof(double) > 160 * 1024) {
+            if (!h->fscr) { int rc = dalloc(h, &h->fscr, (size_t)S.C * faithful_scratch_doubles(S.N, S.M)); if (rc) return rc; }
+            SW.fscr = h->fscr;
+        }
+        MeasParams MP; memset(&MP, 0, sizeof MP);
+        MP.nen = nen; MP.nde = nde;
+        for (int i = 0; i < nen; ++i) { MP.en_id[i] = P.en_id[i]; MP.en_k0[i] = P.en_k0[i]; }
+        for (int i = 0; i < nde; ++i) MP.de_id[i] = P.de_id[i];
+        for (long long it = 0; it < n; ++it) {
+            SP.iter = h->iter + (unsigned long long)it;
+            if (has_rs || has_com) { CK(h, pimc_launch_isweep(S.C, h->stream, S, IP, has_rs, has_com)); LAUNCHED(); launches += (has_rs ? 1 : 0) + (has_com ? 1 : 0); if (has_rs && has_com) LAUNCHED(); }
+            if (has_swap) { SW.sp = SP; CK(h, pimc_launch_iswap(S.C, h->stream, S, h->dT, SW)); LAUNCHED(); launches++; }
+            const long long ctrv = h->Nctr + it + 1;
+            if (nen + nde > 0 && ctrv % h->cfg.Ncycle == 0) {
+                MP.ord = ctrv / h->cfg.Ncycle - 1;
+                CK(h, pimc_launch_measure(S.C, h->stream, S, h->dT, MP, nullptr)); LAUNCHED(); launches++;
+            }
+        }
+    }
+    if (n > 0 && !batched && !isweep) {
         CK(h, pimc_launch_run(S.need_cells != 0, S.C, threads, smem, h->stream, S, h->dT, P));
         LAUNCHED(); launches++;
     }
@@ -939,8 +985,16 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     float ms = 0; CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    unsigned long long st[16]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
-    if (P.prof && n > 0) {
+    unsigned long long st[32]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
+    if (P.prof && n > 0 && isweep) {
+        const double sw = (double)st[4 + 9] / S.N > 0 ? (double)st[4 + 9] / S.N : 1.0;   // chain-sweeps executed
+        fprintf(stderr, "[pimc prof] isweep %.3f ms, %lld iterations x %d chains, %.0f chain-sweeps, %.2f replays per chain-sweep; cycles per chain-sweep", ms, (long long)n, S.C, sw, (double)st[4 + 8] / sw);
+        const char *ph[6] = { "setup", "P1", "P3", "P4", "P5", "book" };
+        fprintf(stderr, " reshape:"); for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f", ph[i], (double)st[4 + i] / sw);
+        fprintf(stderr, " | com:"); for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f", ph[i], (double)st[4 + 10 + i] / sw);
+        fprintf(stderr, "  (each divided by ALL chain-sweeps)\n");
+    }
+    if (P.prof && n > 0 && !isweep) {
         const char *kn[4] = { "ReshapeLinear", "ReshapeSwap", "SingleCOM", "PolymerCOM" };
         fprintf(stderr, "[pimc prof] k_run %.3f ms, %lld iterations x %d chains; mean cycles per proposal:", ms, (long long)n, S.C);
         for (int k = 0; k < 4; ++k) if (st[4 + 4 + k]) fprintf(stderr, " %s %.0f (x%llu)", kn[k], (double)st[4 + k] / (double)st[4 + 4 + k], st[4 + 4 + k]);
@@ -960,5 +1014,108 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
             pimc_update_get(h, update_ids[i], -1, nullptr, nullptr, nullptr, nullptr, &a, nullptr); acc += a; }
         stats->accepted = acc; // cumulative over the life of the update objects
     }
+    return PIMC_OK;
+}
+
+// ---- checkpoint / resume: the complete chain state as one host blob ----
+// The reference's savetools (examples/tools/savetools.jl:4-34) write the paths only, so a reloaded Julia run restarts its step adaptation and
+// counters.  A resumed run here continues bit for bit: positions, permutation, the CACHED link actions (stale links of compat B14 included),
+// cell lists with their list order and multiplicities (B13), iteration counter of the addressed RNG, measurement cadence, every update
+// object's adaptive variable / counters / acceptance window, every estimator's accumulators.
+struct StateHeader {
+    unsigned long long magic; int version, dim, M, N, C, need_cells, ncell, nupd, nen, nde; unsigned chain_offset; unsigned long long seed;
+    unsigned long long iter; long long N_MC, Nctr;
+    long long en_count[PIMC_MAXE], en_cap[PIMC_MAXE], de_ndata[PIMC_MAXD], de_nbins[PIMC_MAXD];
+    int upd_kind[PIMC_MAXU], upd_ring_words[PIMC_MAXU]; long long upd_adj[PIMC_MAXU], upd_range[PIMC_MAXU];
+    double upd_vmin[PIMC_MAXU], upd_vmax[PIMC_MAXU], upd_minacc[PIMC_MAXU], upd_maxacc[PIMC_MAXU];
+};
+#define PIMC_STATE_MAGIC 0x50494d4342323030ull   /* "PIMCB200" */
+struct Seg { void *p; size_t bytes; };
+static std::vector<Seg> state_segments(pimc_handle *h)
+{
+    DevSys &S = h->S; const size_t C = S.C, nb = C * S.N * S.M;
+    std::vector<Seg> v;
+    v.push_back({ S.r, nb * S.dim * sizeof(double) }); v.push_back({ S.Vl, nb * sizeof(double) }); v.push_back({ S.next, C * S.N * sizeof(int) });
+    if (S.need_cells) {
+        v.push_back({ S.bins, nb * sizeof(*S.bins) }); v.push_back({ S.cell_head, C * S.M * S.ncell * sizeof(int) });
+        v.push_back({ S.cell_next, C * S.M * S.N * sizeof(int) }); v.push_back({ S.mult, nb * sizeof(*S.mult) });
+    }
+    for (int i = 0; i < h->nupd; ++i) {
+        UpdDev &U = h->T.upd[i];
+        v.push_back({ U.var, C * 8 }); v.push_back({ U.tries, C * 8 }); v.push_back({ U.accepted, C * 8 }); v.push_back({ U.tries_var, C * 8 });
+        v.push_back({ U.bead_moves, C * 8 }); v.push_back({ U.ring_head, C * 4 }); v.push_back({ U.ring_len, C * 4 }); v.push_back({ U.ring_sum, C * 4 });
+        v.push_back({ U.ring, C * (size_t)U.ring_words * 4 });
+    }
+    for (int i = 0; i < h->nen; ++i) {
+        EnDev &E = h->T.en[i]; const size_t rows = (size_t)(h->en_count[i] < E.cap ? h->en_count[i] : E.cap);
+        v.push_back({ E.E, rows * C * 8 }); v.push_back({ E.Ev, rows * C * 8 }); v.push_back({ E.acc, C * 5 * 8 });
+    }
+    for (int i = 0; i < h->nde; ++i) { DeDev &D = h->T.de[i]; v.push_back({ D.dens, (S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins) * 8 }); }
+    return v;
+}
+static void state_header(pimc_handle *h, StateHeader *H)
+{
+    memset(H, 0, sizeof *H);
+    DevSys &S = h->S;
+    H->magic = PIMC_STATE_MAGIC; H->version = 1; H->dim = S.dim; H->M = S.M; H->N = S.N; H->C = S.C; H->need_cells = S.need_cells; H->ncell = S.ncell;
+    H->nupd = h->nupd; H->nen = h->nen; H->nde = h->nde; H->chain_offset = S.chain_offset; H->seed = S.seed;
+    H->iter = h->iter; H->N_MC = h->N_MC; H->Nctr = h->Nctr;
+    for (int i = 0; i < h->nen; ++i) { H->en_count[i] = h->en_count[i]; H->en_cap[i] = h->T.en[i].cap; }
+    for (int i = 0; i < h->nde; ++i) { H->de_ndata[i] = h->de_ndata[i]; H->de_nbins[i] = h->T.de[i].nbins; }
+    for (int i = 0; i < h->nupd; ++i) {
+        const UpdDev &U = h->T.upd[i];
+        H->upd_kind[i] = U.kind; H->upd_ring_words[i] = U.ring_words; H->upd_adj[i] = U.adj; H->upd_range[i] = U.range;
+        H->upd_vmin[i] = U.vmin; H->upd_vmax[i] = U.vmax; H->upd_minacc[i] = U.minacc; H->upd_maxacc[i] = U.maxacc;
+    }
+}
+extern "C" int pimc_state_size(pimc_handle *h, int64_t *bytes)
+{
+    if (!h || !bytes) return PIMC_ERR_INVALID;
+    size_t n = sizeof(StateHeader);
+    for (const Seg &s : state_segments(h)) n += (s.bytes + 7) & ~(size_t)7;
+    *bytes = (int64_t)n; return PIMC_OK;
+}
+extern "C" int pimc_get_state(pimc_handle *h, void *buf, int64_t cap)
+{
+    if (!h || !buf) return PIMC_ERR_INVALID;
+    int64_t need; pimc_state_size(h, &need);
+    if (cap < need) { SETERR(h, "state buffer of %lld bytes, %lld needed", (long long)cap, (long long)need); return PIMC_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    StateHeader H; state_header(h, &H);
+    char *p = (char *)buf; memcpy(p, &H, sizeof H); p += sizeof H;
+    for (const Seg &s : state_segments(h)) {
+        if (s.bytes) CK(h, cudaMemcpy(p, s.p, s.bytes, cudaMemcpyDeviceToHost));
+        p += (s.bytes + 7) & ~(size_t)7;
+    }
+    return PIMC_OK;
+}
+extern "C" int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes)
+{
+    if (!h || !buf || bytes < (int64_t)sizeof(StateHeader)) return PIMC_ERR_INVALID;
+    StateHeader H; memcpy(&H, buf, sizeof H);
+    DevSys &S = h->S;
+    if (H.magic != PIMC_STATE_MAGIC || H.version != 1) { SETERR(h, "not a pimc_b200 state blob (magic / version)"); return PIMC_ERR_INVALID; }
+    if (H.dim != S.dim || H.M != S.M || H.N != S.N || H.C != S.C || H.need_cells != S.need_cells || H.ncell != S.ncell || H.seed != S.seed || H.chain_offset != S.chain_offset) {
+        SETERR(h, "state blob belongs to another System (dim/M/N/chains/cells/seed/chain_offset differ)"); return PIMC_ERR_STATE; }
+    if (H.nupd != h->nupd || H.nen != h->nen || H.nde != h->nde) { SETERR(h, "state blob holds %d/%d/%d update/Energy/Density objects, the handle %d/%d/%d: create the same objects in the same order first", H.nupd, H.nen, H.nde, h->nupd, h->nen, h->nde); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->nupd; ++i) if (H.upd_kind[i] != h->T.upd[i].kind || H.upd_range[i] != h->T.upd[i].range) { SETERR(h, "update object %d differs in kind or window range", i); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->nen; ++i) if (H.en_cap[i] != h->T.en[i].cap) { SETERR(h, "Energy object %d differs in capacity", i); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->nde; ++i) if (H.de_nbins[i] != h->T.de[i].nbins) { SETERR(h, "Density object %d differs in nbins", i); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->iter = H.iter; h->N_MC = H.N_MC; h->Nctr = H.Nctr;
+    for (int i = 0; i < h->nen; ++i) h->en_count[i] = H.en_count[i];
+    for (int i = 0; i < h->nde; ++i) h->de_ndata[i] = H.de_ndata[i];
+    for (int i = 0; i < h->nupd; ++i) { UpdDev &U = h->T.upd[i]; U.adj = H.upd_adj[i]; U.vmin = H.upd_vmin[i]; U.vmax = H.upd_vmax[i]; U.minacc = H.upd_minacc[i]; U.maxacc = H.upd_maxacc[i]; }
+    int64_t need; pimc_state_size(h, &need);   // after en_count is restored: the Energy segments hold the rows taken so far
+    if (bytes < need) { SETERR(h, "state blob truncated (%lld of %lld bytes)", (long long)bytes, (long long)need); return PIMC_ERR_INVALID; }
+    const char *p = (const char *)buf + sizeof H;
+    for (const Seg &s : state_segments(h)) {
+        if (s.bytes) CK(h, cudaMemcpy(s.p, p, s.bytes, cudaMemcpyHostToDevice));
+        p += (s.bytes + 7) & ~(size_t)7;
+    }
+    int rc = sync_tables(h); if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
     return PIMC_OK;
 }

@@ -250,6 +250,52 @@ __global__ void __launch_bounds__(256, 3) k_run(const __grid_constant__ DevSys S
 __global__ void __launch_bounds__(PIMC_CELLS_THREADS, 8) k_run_cells(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ RunParams P) { d_run_body<true>(S, T, P); }
 
 
+// The swap move of the per-iteration path for interacting systems (optimistic sweeps, pimc_isweep.cuh): one proposal per chain and
+// iteration (reshape.jl:123-283) by the warp-cooperative body -- sampleparticles table, hard-core bridges, pair sums through the cell
+// list, commit with cell-list surgery.  Shared memory: the proposal scratch of pimc_faithful.cuh.
+__global__ void __launch_bounds__(32) k_iswap(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
+{
+    extern __shared__ double smem[];
+    const SweepParams &P = P2.sp;
+    const int c = blockIdx.x, N = S.N, M = S.M, lane = threadIdx.x;
+    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
+    const pimc_u4 di = f_draw(st, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_sample_weighted(P.w, P.nupd, pimc_u01_co(di.w[0], di.w[1]));
+    if (P.kind[pick] != PIMC_UPD_RESHAPE_SWAP) return;
+    const UpdDev &U = P2.upd[pick];
+    double *fscr = P2.fscr ? P2.fscr + (size_t)c * faithful_scratch_doubles(N, M) : smem;
+    int f = 3; unsigned long long beads = 0;
+    if (N > 1) {
+        const int var = (int)U.var[c];
+        const pimc_u4 dt = f_draw(st, 0, PIMC_K_TASK, 0, 0), dm = f_draw(st, 0, PIMC_K_TASK, 0, 1), dsw = f_draw(st, 0, PIMC_K_SWAP, 0, 0);
+        const int j0 = 1 + (int)pimc_index(dt.w[1], (uint32_t)M);
+        const int mm = 2 + (int)pimc_index(dt.w[2], (uint32_t)(var - 1));
+        const int m = (int)U.vmax < mm ? (int)U.vmax : mm;
+        const int n1 = (int)pimc_index(dsw.w[0], (uint32_t)N);
+        const int n2 = d_sample_partner_w(S, c, n1, j0, m, pimc_u01_co(dsw.w[2], dsw.w[3]), fscr);
+        if (n1 != n2) {   // n1 == n2: early return without queue!(counter_var) (reshape.jl:134-136)
+            GSrc g1, g2; g1.xi = nullptr; g1.st = st; g1.slot = 0; g1.kind = PIMC_K_BRIDGE; g1.tab = S.logtab; g2 = g1; g2.kind = PIMC_K_BRIDGE2;
+            const int r = d_reshape_swap_w(S, c, n1, n2, j0, m, g1, g2, pimc_u01_co(dm.w[0], dm.w[1]), fscr + ((N + 1) & ~1));
+            f = r == 1 ? 1 : 0; beads = 2ull * (unsigned long long)(m - 1);
+        }
+    }
+    if (lane != 0) return;
+    RingReg R; R.head = U.ring_head[c]; R.len = U.ring_len[c]; R.sum = U.ring_sum[c]; R.tries = U.tries_var[c];   // apply! (simulation.jl:19-27)
+    U.tries[c] += 1;
+    if (f != 3) { U.accepted[c] += f; d_ring_push(U, c, R, f); }
+    U.ring_head[c] = R.head; U.ring_len[c] = R.len; U.ring_sum[c] = R.sum; U.tries_var[c] = R.tries;
+    U.bead_moves[c] += (long long)beads;
+    if ((R.tries % U.adj) == 0) d_adjust(U, c, R);
+    if (P.stats) { atomicAdd(P.stats + 0, 1ull); atomicAdd(P.stats + 2, beads); }
+}
+cudaError_t pimc_launch_iswap(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P)
+{
+    size_t smem = P.fscr ? 16 : faithful_scratch_doubles(S.N, S.M) * sizeof(double);
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k_iswap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    k_iswap<<<grid, 32, smem, st>>>(S, dT, P);
+    return cudaGetLastError();
+}
+
 cudaError_t pimc_launch_run(bool cells, int grid, int threads, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const RunParams &P)
 {
     if (smem > 48 * 1024) {

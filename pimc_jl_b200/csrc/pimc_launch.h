@@ -25,12 +25,29 @@ struct MeasParams { int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC_MAXE]; i
 // on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).
 // fuse: the sweep launch of a measurement iteration also evaluates the Energy functor for the chains whose picked update streamed
 // every worldline anyway (centre-of-mass sweep of a chain without exchange cycles); mdone[c] = 1 tells k_measure to skip that chain.
-struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; };
+struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; double *fscr; };
 
 __host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
 __host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }
 #define FA_ARR 6
 __host__ __device__ inline size_t faithful_scratch_doubles(int N, int M) { return (size_t)((N + 1) & ~1) + 2 * FA_ARR * (size_t)(M + 1); }
+
+// ---- optimistic-parallel sweep of interacting worldlines (pimc_isweep.cuh) ----
+#define ISW_THREADS 256
+#define ISW_RARR 5
+struct ISweepParams {
+    SweepParams sp;
+    UpdDev upd[PIMC_MAXU];
+    int *nw_head;               // [C][ncell][M] lists over the PROPOSED positions (prop), all -1 between launches
+    int *nw_next;               // [C][N][M]
+    unsigned long long *prof;   // [16] phase cycle counters / replay counts (PIMC_PROF), or null
+};
+
+// shared-memory layout of both kernels: flag[N] | stat[N] | mlen[N] | prev[N] | lead[N] | per-warp rows
+__host__ __device__ inline size_t isw_fixed_bytes(int N) { return (((size_t)N + 15) & ~(size_t)15) + (size_t)N * (4 + 2 + 2 + 4) + 64; }
+__host__ __device__ inline size_t isw_rs_smem_bytes(int N, int M) { return isw_fixed_bytes(N) + (size_t)(ISW_THREADS / 32) * ISW_RARR * (M + 2) * sizeof(double); }
+
+__host__ __device__ inline size_t isw_com_smem_bytes(int N) { return isw_fixed_bytes(N) + 40 * sizeof(double); }
 
 #ifndef PIMC_CELLS_THREADS
 #define PIMC_CELLS_THREADS 128
@@ -41,3 +58,5 @@ cudaError_t pimc_launch_run(bool cells, int grid, int threads, size_t smem, cuda
 cudaError_t pimc_launch_sweep(int grid, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
 cudaError_t pimc_launch_swap_iter(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
 cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const MeasParams &P, const unsigned char *mdone);
+cudaError_t pimc_launch_isweep(int grid, cudaStream_t st, const DevSys &S, const ISweepParams &P, bool has_rs, bool has_com);
+cudaError_t pimc_launch_iswap(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);

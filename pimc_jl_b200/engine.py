@@ -71,6 +71,18 @@ class Engine:
     def set_iter(self, it):
         self._ck(self.lib.pimc_set_iter(self.h, it))
 
+    def get_state(self):
+        """the complete chain state as one uint8 array (pimc_get_state): resumes bit for bit through set_state"""
+        n = C.c_int64()
+        self._ck(self.lib.pimc_state_size(self.h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._ck(self.lib.pimc_get_state(self.h, buf.ctypes.data_as(C.c_void_p), n.value))
+        return buf
+
+    def set_state(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._ck(self.lib.pimc_set_state(self.h, buf.ctypes.data_as(C.c_void_p), buf.size))
+
     def paths(self, chain0=0, nchains=None, want=("r", "V", "bins", "next")):
         nc = self.C - chain0 if nchains is None else nchains
         r = np.zeros((nc, self.N, self.dim, self.M)) if "r" in want else None

@@ -16,8 +16,37 @@ import numpy as np
 from . import _lib as _L
 from . import engine as _eng
 from .engine import Engine
-from . import propint as _propint
-from .propint import build_prop_int, determine_nnrange  # noqa: F401  (src/propagator.jl:79-89, src/system.jl:10-15)
+import ctypes as _C
+
+
+def build_prop_int(L, g0, tau, delta=600):
+    """build_prop_int(L, g0, tau) (src/propagator.jl:79-89): the `propint` argument of System(...; interactions=true) -- the sampled term
+    table of prop_rel_interpolate_terms, built by the library's host code (pimc_build_prop_table, csrc/pimc_propint.cu)"""
+    tab = np.zeros((delta, delta), order="F")
+    lo, hi = _C.c_double(), _C.c_double()
+    _L.check(_L.load().pimc_build_prop_table(float(L), float(g0), float(tau), int(delta), tab.ctypes.data_as(_L.f64p), _C.byref(lo), _C.byref(hi)))
+    return PropInt(tab=tab, lo=lo.value, hi=hi.value, g0=float(g0), tau=float(tau))
+
+
+class PropInt(dict):
+    """what build_prop_int returns: the table, callable like the reference's closure prop_int(r1_rel, r2_rel, tau)"""
+
+    def __call__(self, r1_rel, r2_rel, tau):
+        r1, r2 = np.atleast_1d(np.asarray(r1_rel, dtype=np.float64)), np.atleast_1d(np.asarray(r2_rel, dtype=np.float64))
+        out = _C.c_double()
+        _L.check(_L.load().pimc_prop_int(self["tab"].ctypes.data_as(_L.f64p), self["tab"].shape[0], self["lo"], self["hi"],
+                                         r1.ctypes.data_as(_L.f64p), r2.ctypes.data_as(_L.f64p), len(r1), float(tau), _C.byref(out)))
+        return out.value
+
+
+def determine_nnrange(propint, tau, a, b):
+    """determine_nnrange(propint, tau, a, b) (src/system.jl:10-15)"""
+    out = _C.c_double()
+    tab = np.asfortranarray(propint["tab"], dtype=np.float64)
+    rc = _L.load().pimc_determine_nnrange(tab.ctypes.data_as(_L.f64p), tab.shape[0], propint["lo"], propint["hi"], float(tau), float(a), float(b), _C.byref(out))
+    if rc != 0:
+        raise ValueError("determine_nnrange: no sign change of propint - 0.999 on (r_min, b) (Roots.find_zero would throw)")
+    return out.value
 
 L25 = [2.214297435588181, 0.9272952180016122, -0.6435011087932844, 0.6435011087932844, -2.498091544796509, 3.141592653589793,
        2.498091544796509, 0, 1.5707963267948966, -2.2142974355881813, -1.5707963267948968, -0.9272952180016123]
@@ -260,8 +289,7 @@ class System:                       # src/system.jl:93-168
             if propint is None or not isinstance(propint, dict):
                 raise TypeError("interactions=True needs propint = dict(tab=..., lo=..., hi=...) (the sampled term table of build_prop_int)")
             tab, tab_lo, tab_hi = propint["tab"], propint["lo"], propint["hi"]
-            if r_a == 0.0:   # init_int (src/system.jl:29-31): the cut-off comes from the propagator itself
-                r_a = _propint.determine_nnrange(propint, (1.0 / T) / M, 1e-20, L)
+            # r_a == 0: init_int (src/system.jl:29-31) takes the cut-off from the propagator itself; pimc_create does (pimc_determine_nnrange)
         self.engine = Engine(_L.make_potential(**spec), dim=dim, M=M, N=N, chains=cnt, chain_offset=off, mu=mu, L_=L, T=T, lam=lam,
                              interactions=interactions, g=g, r_a=r_a, Ncycle=length_measurement_cycle, compat=compat, seed=seed,
                              tab=tab, tab_lo=tab_lo or 0.0, tab_hi=tab_hi or 1.0, device=device)

@@ -72,24 +72,21 @@ def info_updates(updates):
     return "\n".join(out)
 
 
-def checkpoint(s, path, updates=()):
-    """All chains of this rank: worldlines, permutation, iteration counter, measurement counters, adaptive variables."""
+def checkpoint(s, path):
+    """Complete state of all chains of this rank (pimc_get_state): worldlines, permutation, cached link actions, cell lists, RNG iteration
+    counter, measurement cadence, every update object's adaptive variable / counters / acceptance window, estimator accumulators.
+    The reference's savetools (examples/tools/savetools.jl:4-34) write the paths only."""
     e = s.engine
-    r, _, _, nxt = e.paths(want=("r", "next"))
-    sc = e.scalars()
-    var = np.array([[e.update_get(u.id, c)["var"] for c in range(e.C)] for _, u in updates]) if updates else np.zeros((0, e.C))
-    np.savez_compressed(path, r=r, next=nxt, iter=sc["iter"], N_MC=sc["N_MC"], Nctr=sc["Nctr"], var=var,
-                        shape=np.array([e.C, e.N, e.dim, e.M]))
+    path = str(path) if str(path).endswith(".npz") else str(path) + ".npz"
+    np.savez_compressed(path, state=e.get_state(), shape=np.array([e.C, e.N, e.dim, e.M]))
     return path
 
 
 def restore(s, path):
-    """Puts the worldlines / permutation back and re-arms the Philox iteration counter; the link cache and the cell lists are rebuilt by
-    the library (pimc_set_paths).  Returns the saved adaptive variables (one row per update) for the caller to re-create its updates with."""
+    """Puts a checkpoint back into a System built with the same arguments and the same update / Energy / Density objects created in the same
+    order; the run then continues bit for bit (tests/test_gpu_api.py::test_checkpoint_restore_continues_bit_for_bit)."""
     z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
     e = s.engine
     if tuple(z["shape"]) != (e.C, e.N, e.dim, e.M):
         raise ValueError(f"checkpoint shape {tuple(z['shape'])} does not match this System {(e.C, e.N, e.dim, e.M)}")
-    e.set_paths(z["r"], z["next"])
-    e.set_iter(int(z["iter"]))
-    return z["var"]
+    e.set_state(z["state"])

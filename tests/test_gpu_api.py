@@ -131,27 +131,72 @@ def test_debug_exports():
 
 
 @pytest.mark.gpu
-def test_checkpoint_restore_and_save_tools(tmp_path):
-    """State checkpoint / restore: a restored System continues bit for bit; save_paths / save_density write the
-    reference's CSV layouts (examples/tools/savetools.jl)."""
+@pytest.mark.parametrize("variant", ["free-sweep", "free-faithful", "interacting-as-shipped", "interacting-intended"])
+def test_checkpoint_restore_continues_bit_for_bit(tmp_path, variant):
+    """State checkpoint / restore (pimc_get_state / pimc_set_state): run 30, checkpoint, run 20 -> A; a FRESH System with the same
+    objects, restore, run 20 -> B; A == B bit for bit: positions, cached link actions (stale links of compat B14 after swaps included),
+    permutation, cells, every update object's variable / counters / acceptance window, Energy series, density counters, N_MC."""
+    from pimc_jl_b200 import tools
+    import pimc_jl_b200.pimc as P
+    from pimc_jl_b200 import _lib as L
+    kw = dict(dV="identity", dim=2, M=16, N=6, L=4.0, T=1.0, lam=0.5, length_measurement_cycle=3, chains=3, seed=21)
+    kw["schedule"] = "faithful" if variant == "free-faithful" else "sweep"
+    if variant.startswith("interacting"):
+        from test_gpu_parity import synthetic_table
+        tab, lo, hi = synthetic_table()
+        kw.update(interactions=True, g=3.0, r_a=1.0, propint=dict(tab=tab, lo=lo, hi=hi), M=12, N=9, L=3.0, T=0.5,
+                  compat=L.COMPAT_ALL if variant.endswith("as-shipped") else 0)
+
+    def build():
+        s = P.System(P.harmonic(), **kw)
+        o = dict(adj=3, range=7)                                # short windows: ring wrap-around and adjust! both happen within 50 iterations
+        ups = [(1, P.SingleCenterOfMass(s, 0.6, **o)), (1, P.ReshapeLinear(s, 6, **o)), (1, P.ReshapeSwapLinear(s, 6, **o)),
+               (3, P.PolymerCenterOfMass(s, 0.3, **o))]
+        return s, ups, P.Energy(s, 200), P.Density(s, nbins=16)
+
+    def snapshot(s, ups, en, de):
+        e = s.engine
+        out = list(e.paths()) + [e.scalars()["iter"], e.scalars()["N_MC"], e.scalars()["Nctr"]]
+        for _, u in ups:
+            for c in range(e.C):
+                g = e.update_get(u.id, c)
+                out += [g["var"], g["tries"], g["tries_var"], g["accepted"], g["bead_moves"], g["acc_window"]]
+        for c in range(e.C):
+            out += list(e.energy_read(en.id, c)[:2])
+        out.append(e.density_read(de.id, 16)[0])
+        return out
+
+    s, ups, en, de = build()
+    P.run_b(s, 30, ups, Zmeasurements=[en, de])
+    ck = tools.checkpoint(s, str(tmp_path / "ck"))
+    mid = snapshot(s, ups, en, de)
+    P.run_b(s, 20, ups, Zmeasurements=[en, de])
+    A = snapshot(s, ups, en, de)
+    assert not np.array_equal(mid[0], A[0])
+    s2, ups2, en2, de2 = build()
+    P.run_b(s2, 7, ups2, Zmeasurements=[en2, de2])          # a different history that the restore must wipe out completely
+    tools.restore(s2, ck)
+    for a, b in zip(mid, snapshot(s2, ups2, en2, de2)):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+    P.run_b(s2, 20, ups2, Zmeasurements=[en2, de2])
+    B = snapshot(s2, ups2, en2, de2)
+    for k, (a, b) in enumerate(zip(A, B)):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
+    # a blob of another System / other objects is refused
+    s3 = P.System(P.harmonic(), **{**kw, "seed": 22})
+    with pytest.raises(L.PimcError):
+        tools.restore(s3, ck)
+
+
+@pytest.mark.gpu
+def test_save_tools(tmp_path):
+    """save_paths / save_density write the reference's CSV layouts (examples/tools/savetools.jl)"""
     from pimc_jl_b200 import tools
     import pimc_jl_b200.pimc as P
     kw = dict(dV="identity", dim=2, M=16, N=6, L=4.0, T=1.0, lam=0.5, length_measurement_cycle=2, chains=3, seed=21, schedule="sweep")
     s = P.System(P.harmonic(), **kw)
     ups = [(1, P.SingleCenterOfMass(s, 1.0)), (1, P.ReshapeLinear(s, 6)), (2, P.ReshapeSwapLinear(s, 6))]
     P.run_b(s, 30, ups)
-    ck = tools.checkpoint(s, str(tmp_path / "ck"), ups)
-    r0, _, _, n0 = s.engine.paths(want=("r", "next"))
-    P.run_b(s, 20, ups)
-    r1, V1, _, n1 = s.engine.paths(want=("r", "V", "next"))
-    assert not np.array_equal(r0, r1)
-    s2 = P.System(P.harmonic(), **kw)
-    var = tools.restore(s2, ck)
-    ups2 = [(1, P.SingleCenterOfMass(s2, 1.0)), (1, P.ReshapeLinear(s2, 6)), (2, P.ReshapeSwapLinear(s2, 6))]
-    assert var.shape == (3, 3)
-    ra, _, _, na = s2.engine.paths(want=("r", "next"))
-    assert np.array_equal(ra, r0) and np.array_equal(na, n0)
-    assert s2.engine.scalars()["iter"] == 30
     path = tools.save_paths(s, str(tmp_path / "paths.csv"))
     tab = np.loadtxt(path, delimiter=",", skiprows=1)
     assert tab.shape == (17, 13) and open(path).readline().startswith("tau,p1 x,p1 y,p2 x")
@@ -208,3 +253,51 @@ def test_full_size_properties_c2_and_c5():
     e3.run(60, ups3, sched=L.SCHED_SWEEP)
     r3 = e3.paths(want=("r",))[0]
     assert np.array_equal(r3, r[448:512])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sched", [0, 1], ids=["faithful", "sweep"])
+def test_c_driver_example_density_srl_lattice(oracle, tmp_path, sched):
+    """examples/density_SRL_lattice.jl through the C ABI from a plain C program (tests/c/example_density_srl_lattice.c: the call sequence the
+    Julia shim issues for that script, scaled down in n / times): build_prop_int -> System(interactions = true, propint) WITHOUT g and r_a
+    (=> a = 0, r_a from determine_nnrange inside pimc_create) -> updates -> Density -> thermalise -> measure until N_MC >= n * times ->
+    read the density.  The histogram must equal the oracle's on the same seed, integer for integer."""
+    import math
+    import os
+    import subprocess
+    import ctypes as C
+    from pimc_jl_b200 import _lib as L
+    ob = oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, out = str(tmp_path / "example_srl"), str(tmp_path / "dens.bin")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "c", "example_density_srl_lattice.c"),
+                           "-L" + os.path.join(root, "pimc_jl_b200"), "-lpimc_b200", "-lm", "-Wl,-rpath," + os.path.join(root, "pimc_jl_b200")])
+    g, V0, n, times = 2.0, 6.0, 30, 3
+    res = subprocess.run([exe, str(g), str(V0), str(n), str(times), out, str(sched)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    words = res.stdout.split()
+    info = {words[i]: float(words[i + 1]) for i in range(0, len(words), 2)}
+    dens = np.fromfile(out).reshape(500, 500, order="F")
+    Lb, M, N, T = 8.0, 200, 20, 0.2
+    assert info["a"] == 0.0 and info["N_MC"] >= n * times and info["ndata"] == info["N_MC"] * M and dens.sum() == info["ndata"] * N
+    # the same run on the oracle: table from the same host code, r_a as pimc_create derived it
+    lib = L.load()
+    tab = np.zeros((600, 600), order="F")
+    lo, hi = C.c_double(), C.c_double()
+    tau = 1.0 / (T * M)
+    assert lib.pimc_build_prop_table(math.ceil(math.sqrt(2) * Lb), g, tau, 600, tab.ctypes.data_as(L.f64p), C.byref(lo), C.byref(hi)) == 0
+    ra = C.c_double()
+    assert lib.pimc_determine_nnrange(tab.ctypes.data_as(L.f64p), 600, lo.value, hi.value, tau, 1e-20, Lb, C.byref(ra)) == 0
+    assert ra.value == info["r_a"] and info["nbins"] == math.floor(2 * Lb / ra.value)
+    import bench
+    s = ob.System(ob.make_potential(**bench._LAT), dim=2, M=M, N=N, L=Lb, T=T, lam=1.0 / math.pi ** 2, Ncycle=3, seed=0x5EEDB200, chain=0,
+                  interactions=True, g=0.0, r_a=ra.value, tab=tab, tab_lo=lo.value, tab_hi=hi.value)
+    assert s.a == 0.0
+    ups = [(1, ob.Update(s, ob.UPD_SINGLE_COM, 1.0)), (1, ob.Update(s, ob.UPD_RESHAPE_LINEAR, 5)), (1, ob.Update(s, ob.UPD_RESHAPE_SWAP, 20))]
+    de = ob.Density(s, 500)
+    osched = ob.SCHED_FAITHFUL if sched == 0 else ob.SCHED_SWEEP_SEQ
+    s.run(n * times, ups, sched=osched)
+    while s.scalars()["N_MC"] < n * times:
+        s.run(n, ups, densities=[de], sched=osched)
+    assert s.scalars()["N_MC"] == info["N_MC"]
+    assert np.array_equal(de.read()[0], dens)
