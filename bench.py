@@ -179,6 +179,7 @@ def main():
               "schedule": "sweep (every worldline of a chain proposes per iteration)" if not faithful else "reference (one proposal per chain and iteration)",
               "iters_per_step": args.iters, "measure": f"{wl['measure'].capitalize()} every {wl['Ncycle']} iterations",
               "interactions": bool(wl.get("interactions")),
+              "e2e_pipeline": "two Systems of chains/2 on two streams / host threads: copies of one half overlap the moves of the other",
               "l2": f"state ({wl['chains']} chains x {wl['N'] * wl['M'] * 24 // 1024} KiB) larger than L2"}
 
     if args.impl == "reference":
@@ -206,7 +207,7 @@ def main():
     import numpy as np
     import torch
     import pimc_jl_b200 as pj
-    from pimc_jl_b200 import _lib as L
+    from pimc_jl_b200 import _lib as L, engine as eng
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -219,6 +220,14 @@ def main():
     e = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
                   T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
     SCHED = L.SCHED_FAITHFUL if faithful else L.SCHED_SWEEP
+
+    def attach_comm(engine_):
+        """multi-GPU inside the library: ncclCommInitRank on this engine's handle; the 128-byte id travels through torch.distributed (plumbing)"""
+        ids = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        engine_.comm_init(world, rank, ids[0])
+    if dist is not None:
+        attach_comm(e)
     if args.faithful_impl:
         e.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
     use_density = wl["measure"] == "density"
@@ -231,20 +240,16 @@ def main():
     e.set_stream(stream.cuda_stream)
     e.run(args.therm, ups, sched=SCHED)  # thermalisation: adaptive slice count / step settle
 
-    def block_allreduce(n_before):
-        """per-block all-reduce of the estimator accumulators: chain-mean E, Ev of this step's measurements (NCCL)"""
-        if use_density:   # density counters are summed over the GPUs at read-out
-            dens, nd, _ = e.density_read(en, wl["nbins"])
-            blk = torch.from_numpy(dens).cuda()
-            if dist is not None:
-                dist.all_reduce(blk)
-            return blk, nd
-        E, Ev, n = e.energy_read_range(en, n_before, 1 << 20)
-        blk = torch.from_numpy(np.stack([E, Ev])).cuda()
-        if dist is not None:
-            dist.all_reduce(blk)
-            blk /= world
-        return blk, n
+    def block_read(n_before, engine_=None, obj=None):
+        """the step's estimator block.  With N > 1 GPUs the library has all-reduced it itself (ncclAllReduce on its side stream, queued at the
+        end of pimc_run; density counters at read-out): chain-mean E, Ev over ALL ranks' chains / density counters and ndata summed over the ranks"""
+        engine_, obj = engine_ or e, en if obj is None else obj
+        if use_density:
+            dens, nd, _ = engine_.density_read(obj, wl["nbins"])
+            return torch.from_numpy(dens), nd
+        E, Ev, n = engine_.energy_read_range(obj, n_before, 1 << 20)
+        return torch.from_numpy(np.stack([E, Ev])), n
+    block_allreduce = block_read
 
     def barrier():
         if dist is not None:
@@ -285,21 +290,66 @@ def main():
     value = total_bm / (ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----
+    # The public API as a user with pinned host buffers drives it: the batch is held as TWO Systems of chains/2 (two handles, two streams,
+    # two host threads -- the library is synchronous per handle), so the H2D / D2H copies of one half overlap the moves of the other.  Runs
+    # and collective read-outs take turns in a fixed order (A, B, A, B, ...), which keeps the NCCL operations of the two communicators in
+    # the same order on every rank.
     per = wl["N"] * wl["dim"] * wl["M"]
-    host_r = torch.empty((Cc, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
-    e.get_r_into(host_r)
+    halves = []
+    for k in range(2):
+        ck = Cc // 2 + (Cc % 2 if k == 0 else 0)
+        if ck == 0:
+            continue
+        ek = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=ck, chain_offset=rank * Cc + k * (Cc - Cc // 2), L_=wl["L"],
+                       T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
+        if args.faithful_impl:
+            ek.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
+        sk = torch.cuda.Stream()
+        ek.set_stream(sk.cuda_stream)
+        if dist is not None:
+            attach_comm(ek)
+        uk = [(every, ek.update_create(kind[kk], v0)) for kk, every, v0 in wl["updates"]]
+        ok = ek.density_create(wl["nbins"]) if use_density else ek.energy_create(nmeas_total)
+        ek.run(args.therm, uk, sched=SCHED)
+        hk = torch.empty((ck, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
+        ek.get_r_into(hk)
+        halves.append(dict(e=ek, ups=uk, obj=ok, host=hk, stream=sk, mkw=dict(densities=[ok]) if use_density else dict(energies=[ok]), seen=0, bm=0, blk=None))
+    turn = [0]
+    cv = threading.Condition()
+    errors = []
+
+    def half_worker(k):
+        try:
+            torch.cuda.set_device(local_rank)
+            hf = halves[k]
+            for s_ in range(args.steps):
+                hf["e"].set_paths(hf["host"])                          # H2D: this step's worldlines (pinned host memory)
+                with cv:
+                    cv.wait_for(lambda: turn[0] == s_ * len(halves) + k)
+                st_ = hf["e"].run(args.iters, hf["ups"], sched=SCHED, **hf["mkw"])
+                hf["bm"] += st_["bead_moves"]
+                hf["blk"], hf["seen"] = block_read(hf["seen"], hf["e"], hf["obj"])   # the step's result: estimator block, D2H (global over the GPUs)
+                with cv:
+                    turn[0] += 1
+                    cv.notify_all()
+                hf["e"].get_r_into(hf["host"])                         # D2H: updated worldlines
+        except Exception as ex:   # noqa: BLE001
+            errors.append(ex)
+            with cv:
+                turn[0] = 1 << 30
+                cv.notify_all()
     barrier()
     t0 = time.perf_counter()
-    e2e_bm = 0
-    for _ in range(args.steps):
-        e.set_paths(host_r)                                    # H2D: this step's worldlines (pinned host memory)
-        st = e.run(args.iters, ups, sched=SCHED, **mkw)
-        e2e_bm += st["bead_moves"]
-        blk, n_seen = block_allreduce(n_seen)                  # estimator block (all-reduced over GPUs)
-        e.get_r_into(host_r)                                   # D2H: updated worldlines
-        blk_host = blk.cpu()                                   # D2H: the step's result
+    workers = [threading.Thread(target=half_worker, args=(k,)) for k in range(len(halves))]
+    [w.start() for w in workers]
+    [w.join() for w in workers]
     barrier()
     t_e2e = time.perf_counter() - t0
+    if errors:
+        raise errors[0]
+    e2e_bm = sum(hf["bm"] for hf in halves)
+    blk_host = halves[0]["blk"]
+    n_seen_e2e = halves[0]["seen"]
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
     be = torch.tensor([float(e2e_bm)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -308,6 +358,7 @@ def main():
     e2e_val = float(be[0]) / float(te[0])
     h2d = per * Cc * 8
     d2h = per * Cc * 8 + (8 * wl["nbins"] ** wl["dim"] if use_density else 2 * 8 * (args.iters // wl["Ncycle"]))
+    comm_info = e.comm_info()
 
     if rank != 0:
         if dist is not None:
@@ -322,6 +373,29 @@ def main():
     sweep_ms = st_mv["kernel_ms"] / n_launch
     sweep_bytes = st_mv["bead_moves"] * B_ALG / n_launch
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+    # per-family legs (after every timed region; they perturb nothing that is reported above): one update family alone, moves only, and the
+    # estimator launch as the difference between a measured and an unmeasured run of the same moves
+    by_family = {}
+    if not faithful:
+        fam_iters = max(8, args.iters // 4)
+        for (kk, every, v0), (_, uid) in zip(wl["updates"], ups):
+            lf = lib.pimc_launch_count()
+            stf = e.run(fam_iters, [(1, uid)], sched=SCHED)
+            nl = max(1, lib.pimc_launch_count() - lf)
+            if stf["bead_moves"] > 0 and stf["kernel_ms"] > 0:
+                gbs = stf["bead_moves"] * B_ALG / (stf["kernel_ms"] * 1e-3) / 1e9
+                by_family[UPD_NAMES[kk]] = {"bead_moves_per_s": stf["bead_moves"] / (stf["kernel_ms"] * 1e-3), "achieved": gbs, "frac": gbs / hbm,
+                                            "launch_ms": stf["kernel_ms"] / nl, "alg_bytes_per_launch": stf["bead_moves"] * B_ALG / nl}
+        n_it = wl["Ncycle"] * max(4, fam_iters // wl["Ncycle"])
+        st_a = e.run(n_it, ups, sched=SCHED)
+        st_b = e.run(n_it, ups, sched=SCHED, **mkw)
+        nm = max(1, st_b["measurements"])
+        ms_meas = max(0.0, st_b["kernel_ms"] - st_a["kernel_ms"] * (st_b["bead_moves"] / max(1, st_a["bead_moves"]))) / nm
+        bytes_meas = Cc * wl["N"] * wl["M"] * 8.0 * wl["dim"]          # the estimators stream the positions once (16 B per bead at d = 2)
+        if ms_meas > 0:
+            by_family["measure"] = {"launch_ms_marginal": ms_meas, "alg_bytes_per_launch": bytes_meas, "achieved": bytes_meas / (ms_meas * 1e-3) / 1e9,
+                                    "frac": bytes_meas / (ms_meas * 1e-3) / 1e9 / hbm,
+                                    "note": "marginal cost of one measurement event inside the step (fused Energy sums ride on the centre-of-mass sweep)"}
     fp64 = C.c_double(0.0)
     lib.pimc_measure_fp64_peak(C.byref(fp64))
     traffic = None
@@ -334,12 +408,13 @@ def main():
     whole = total_bm / world / (kern_ms * 1e-3)            # moves + estimator kernels, per GPU
     roofline = {"bound": "hbm", "kernel": "k_run" if st_mv["launches"] == 1 else "k_sweep", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json ({how})", "alg_bytes_per_bead_move": B_ALG,
-                "alg_bytes_per_launch": sweep_bytes, "launch_ms": sweep_ms,
+                "alg_bytes_per_launch": sweep_bytes, "launch_ms": sweep_ms, "by_family": by_family,
+                "traffic_source": "committed ncu --set full capture (profiles/traffic.json), not measured in this run" if traffic is not None else None,
                 "step_including_estimator": {"achieved": whole * B_ALG / 1e9, "frac": whole * B_ALG / 1e9 / hbm},
                 "fp64": {"achieved_tflops": achieved * 1e9 / B_ALG * F_ALG / 1e12, "peak_tflops_measured_dfma": fp64.value,
                          "frac": (achieved * 1e9 / B_ALG * F_ALG / 1e12 / fp64.value) if fp64.value else None, "alg_flops_per_bead_move": F_ALG}}
     if use_density:   # sum(dens)/ndata vs N (test/testmeasurements.jl:24-29), chain-summed
-        check = {"density_sum_over_ndata": float(blk_host.sum()) / (n_seen * world) if n_seen else None, "expected": float(wl["N"])}
+        check = {"density_sum_over_ndata": float(blk_host.sum()) / n_seen_e2e if n_seen_e2e else None, "expected": float(wl["N"])}   # both global
     else:
         Em = float(blk_host[0].mean()) if blk_host.numel() else None
         check = {"E_mean_last_block": Em, "E_expected_boltzmannon": wl["dim"] * wl["N"] / 2.0 * wl["T"] if wl["pot"]["kind"] == "zero" else None}
@@ -347,7 +422,9 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_val, "unit": "bead-moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "kernel_ms_per_step": kern_ms / args.steps,
+            "gpu_launches": int(launches), "roofline": roofline,
+            "collective": {"where": "libpimc_b200 (ncclAllReduce on the handle's side stream, queued at the end of pimc_run; density counters at read-out)",
+                           "comm_nranks_seen": comm_info["nranks"], "chains_total": comm_info["chains_total"], "nccl_version": comm_info["nccl_version"]}, "kernel_ms_per_step": kern_ms / args.steps,
             "check": check}
     if not args.no_cpu_baseline:
         it = args.cpu_iters or (150 if not faithful else (wl.get("iters") or (1000 if wl.get("interactions") else 20000)))
@@ -355,6 +432,9 @@ def main():
         line["cpu_baseline"] = {"value": bm / dt, "unit": "bead-moves/s", "cores": ncpu, "kind": "port",
                                 "sample": f"{ncpu} chains (one per host thread) x {it} run! iterations after 60 thermalisation iterations; "
                                           f"oracle port of the reference (C, -O2), not Julia"}
+        # the reference's real execution model (src/ has no threading): one chain on one host thread
+        bm1, dt1 = oracle_arm(wl, 1, it)
+        line["cpu_baseline"]["single_thread"] = {"value": bm1 / dt1, "unit": "bead-moves/s", "cores": 1, "sample": f"1 chain x {it} run! iterations, same port"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

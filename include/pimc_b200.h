@@ -100,9 +100,10 @@ int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run k
 /* PIMC_OPT_FUSE_ENERGY: 1 (default) evaluates the Energy functor inside the sweep launch for chains whose picked update streamed every
  * worldline anyway; 0 always uses the separate estimator launch (A/B, same values to 1e-12) */
 #define PIMC_OPT_FUSE_ENERGY 3
-/* PIMC_OPT_ISWEEP: sweep schedule of interacting worldlines: 1 (default) optimistic-parallel per-iteration kernels where they apply
- * (hard core, pair action not counted in ReshapeLinear / centre-of-mass moves = the reference as shipped); 0 the sequential sweep inside
- * the persistent kernel (A/B: identical trajectories) */
+/* PIMC_OPT_ISWEEP: sweep schedule of interacting worldlines (hard core; pair action not counted in ReshapeLinear / centre-of-mass moves =
+ * the reference as shipped): 1 (default) adaptive -- optimistic-parallel per-iteration kernels, falling back to the sequential sweep inside
+ * the persistent kernel for a few runs whenever most proposals had to be replayed serially (dense clouds); 2 always optimistic;
+ * 0 always sequential.  All three produce identical trajectories. */
 #define PIMC_OPT_ISWEEP 4
 int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */
@@ -179,6 +180,44 @@ int pimc_density_create(pimc_handle *h, int64_t nbins, int32_t *id);
 int pimc_density_measure(pimc_handle *h, int32_t id);                   /* Density functor now, src/measurement.jl:45-55 */
 /* dens: nbins^dim counts (column-major like the Julia array), summed over this handle's chains; ndata likewise */
 int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64_t *ndata, double *bin);
+
+/* ---- estimators the reference lists as TODO (src/measurement.jl:125-127 `#TODO radial distribution`, `#TODO Superfluid Fraction`), written in the
+ *      style of its functors (the CPU checker under tests/ restates the same definitions).  (`#TODO Compressibilty` needs particle-number fluctuations, i.e. the
+ *      grand-canonical worm sector the reference never shipped: not provided.)
+ *  g(r): per measurement, for every slice and every pair i < j, ib = floor(|distance.(r_i, r_j, L)| / (rmax / nbins)); hist[ib] += 1 if
+ *        ib < nbins; ndata += M.   g(r_b) = hist[b] * vol / (ndata * N (N - 1) / 2 * shell_b) at read-out.
+ *  winding: W_k = (1 / 2L) * sum over links of teleport(r_next[k] - r[k], L), an integer for closed paths; superfluid fraction
+ *        rho_s / rho = <W^2> (2L)^2 / (2 dim lambda beta N). ---- */
+int pimc_paircorr_create(pimc_handle *h, int64_t nbins, double rmax, int32_t *id);
+int pimc_paircorr_measure(pimc_handle *h, int32_t id);                                       /* functor call now, every chain */
+int pimc_paircorr_read(pimc_handle *h, int32_t id, double *hist, int64_t *ndata, double *bin); /* summed over chains (and ranks) */
+int pimc_winding_create(pimc_handle *h, int64_t cap, int32_t *id);
+int pimc_winding_now(pimc_handle *h, double *W /* [chains][dim] */);
+/* chain >= 0: out[n][dim] that chain's series; chain = -1: out[n] = mean over this handle's chains of W^2 per measurement */
+int pimc_winding_read(pimc_handle *h, int32_t id, int32_t chain, double *out, int64_t cap, int64_t *n);
+/* run! with the full Zmeasurements list (src/simulation.jl:29-42): pimc_run plus the estimators above, same cadence */
+typedef struct {
+    const int32_t *energy_ids; int32_t nenergy;
+    const int32_t *density_ids; int32_t ndensity;
+    const int32_t *paircorr_ids; int32_t npaircorr;
+    const int32_t *winding_ids; int32_t nwinding;
+} pimc_measurements;
+int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
+                const pimc_measurements *meas, int32_t sched, pimc_run_stats *stats);
+
+/* ---- multi-GPU: chains shard over ranks (one handle per GPU, chain_offset = first global chain id of the shard), no
+ *      data-path collective; the reference's analogue is `pmap` over independent runs (examples/density_SRL_lattice.jl:1-2,46).  With a
+ *      communicator attached the library all-reduces the estimator accumulators itself (NCCL over NVLink, on a side stream: the block
+ *      reduced at the end of pimc_run overlaps the next block's moves) and the read-outs become collective and global:
+ *      pimc_energy_read* with chain = -1 -> mean over the chains of ALL ranks; pimc_density_read -> counters and ndata summed over the ranks.
+ *      Every rank must issue the same read-outs in the same order.  One rank per process (torchrun, MPI, Julia Distributed workers): rank 0
+ *      calls pimc_comm_get_unique_id and ships the 128 bytes to the others, every rank calls pimc_comm_init.  One process, several GPUs:
+ *      pimc_comm_init_all on handles created on different devices, then one host thread per handle. ---- */
+#define PIMC_COMM_ID_BYTES 128
+int pimc_comm_get_unique_id(void *id128);
+int pimc_comm_init(pimc_handle *h, int32_t nranks, int32_t rank, const void *id128);
+int pimc_comm_init_all(pimc_handle **handles, int32_t n);
+int pimc_comm_info(pimc_handle *h, int32_t *nranks, int32_t *rank, int64_t *chains_total, int32_t *nccl_version);
 
 /* ---- pair propagator of interacting Systems: host-side construction, no GPU needed (csrc/pimc_propint.cu) ---- */
 /* prop_rel_interpolate_terms (src/propagator.jl:34-70): the sampled term table on range(1e-20, L, delta)^2 (delta = 600 in the reference),

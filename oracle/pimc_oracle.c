@@ -918,6 +918,54 @@ void ora_energy_now(const ora_system *s, double *E, double *Ev, double *parts)
     *Ev = 1.0 / (2 * s->M) * vkin + 1.0 / (2 * s->M) * vpot;
     if (parts) { parts[0] = link; parts[1] = pot; parts[2] = vkin; }
 }
+/* ---- estimators the reference lists as TODO (measurement.jl:125-127), defined here in the style of its functors ---- */
+/* Radial distribution (`#TODO radial distribution`): histogram of equal-time pair distances.  Per measurement, for every time slice m and every
+ * pair i < j: d = |distance.(r_i[m, :], r_j[m, :], L)| (minimum image, propagator.jl:6-9), ib = floor(d / bin), bin = rmax / nbins;
+ * hist[ib] += 1 when ib < nbins; ndata += M (the convention of Density, measurement.jl:54).  g(r) is the histogram divided by the ideal-gas
+ * count ndata * N(N-1)/2 * shell(r) / vol at read-out. */
+struct ora_paircorr { int64_t nbins; double rmax, bin; double *hist; int64_t ndata; };
+ora_paircorr *ora_paircorr_create(const ora_system *s, int64_t nbins, double rmax)
+{
+    (void)s;
+    ora_paircorr *g = (ora_paircorr *)calloc(1, sizeof *g);
+    g->nbins = nbins; g->rmax = rmax; g->bin = rmax / (double)nbins;
+    g->hist = (double *)calloc((size_t)nbins, sizeof(double));
+    return g;
+}
+void ora_paircorr_destroy(ora_paircorr *g) { if (!g) return; free(g->hist); free(g); }
+void ora_paircorr_measure(ora_paircorr *g, const ora_system *s)
+{
+    for (int64_t m = 1; m <= s->M; ++m)
+        for (int64_t i = 1; i <= s->N; ++i)
+            for (int64_t j = i + 1; j <= s->N; ++j) {
+                double d2 = 0.0;
+                for (int k = 1; k <= s->dim; ++k) { double dr = ora_distance(R_(s, i, m, k), R_(s, j, m, k), s->L); d2 = (k == 1) ? dr * dr : d2 + dr * dr; }
+                const double ib = floor(sqrt(d2) / g->bin);
+                if (ib < (double)g->nbins) g->hist[(int64_t)ib] += 1.0;
+            }
+    g->ndata += s->M;
+}
+int64_t ora_paircorr_read(const ora_paircorr *g, double *hist, double *bin)
+{
+    if (hist) memcpy(hist, g->hist, sizeof(double) * (size_t)g->nbins);
+    if (bin) *bin = g->bin;
+    return g->ndata;
+}
+/* Winding number (`#TODO Superfluid Fraction`): W_k = (1 / 2L) * sum over all links of the minimum-image displacement
+ * teleport(r_next[k] - r[k], L) (propagator.jl:30-32 wraps into [-L, L)); an integer for closed paths.  The superfluid fraction follows at
+ * read-out from <W^2> (2L)^2 / (2 dim lambda beta N) (Pollock & Ceperley 1987). */
+void ora_winding_now(const ora_system *s, double *W)
+{
+    for (int k = 1; k <= s->dim; ++k) {
+        double acc = 0.0;
+        for (int64_t i = 1; i <= s->N; ++i)
+            for (int64_t j = 1; j <= s->M; ++j) {
+                int64_t inext = (j == s->M) ? s->next[i - 1] : i, jnext = mod1(j + 1, s->M);
+                acc += ora_teleport(R_(s, inext, jnext, k) - R_(s, i, j, k), s->L);
+            }
+        W[k - 1] = acc / (2 * s->L);
+    }
+}
 struct ora_density { int64_t nbins; int dim; double bin; double *dens; int64_t ndata; };
 /* measurement.jl:31-38 */
 ora_density *ora_density_create(const ora_system *s, int64_t nbins)

@@ -136,6 +136,14 @@ void ora_density_destroy(ora_density *d);
 void ora_density_measure(ora_density *d, const ora_system *s);
 int64_t ora_density_read(const ora_density *d, double *dens, double *bin);
 
+/* estimators the reference lists as TODO (measurement.jl:125-127): radial distribution and winding number, definitions in pimc_oracle.c */
+typedef struct ora_paircorr ora_paircorr;
+ora_paircorr *ora_paircorr_create(const ora_system *s, int64_t nbins, double rmax);
+void ora_paircorr_destroy(ora_paircorr *g);
+void ora_paircorr_measure(ora_paircorr *g, const ora_system *s);
+int64_t ora_paircorr_read(const ora_paircorr *g, double *hist, double *bin);
+void ora_winding_now(const ora_system *s, double *W /* dim */);
+
 /* ---- driver ---- */
 int ora_run(ora_system *s, int64_t n, ora_update **upd, const int64_t *every, int nupd,
             ora_energy **en, int nen, ora_density **de, int nde, int sched);

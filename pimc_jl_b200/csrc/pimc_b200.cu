@@ -150,6 +150,24 @@ __global__ void k_energy_chain_mean(const double *E, const double *Ev, int C, lo
     __syncthreads();
     if (threadIdx.x == 0) { a = 0.0; b = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += ra[i]; b += rb[i]; } mE[blockIdx.x] = a / C; mEv[blockIdx.x] = b / C; }
 }
+// chain SUMS of a block of measurements, interleaved (E, Ev) per index: the buffer the ranks all-reduce
+__global__ void k_energy_chain_sum(const double *E, const double *Ev, int C, long long k0, double *g)
+{
+    __shared__ double ra[8], rb[8];
+    const long long k = k0 + blockIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { a += E[(size_t)k * C + c]; b += Ev[(size_t)k * C + c]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = a; rb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) { a = 0.0; b = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += ra[i]; b += rb[i]; } g[2 * k] = a; g[2 * k + 1] = b; }
+}
+__global__ void k_energy_global_mean(const double *g, long long k0, long long n, double inv /* total number of chains */, double *oE, double *oEv)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    oE[k] = g[2 * (k0 + k)] / inv; oEv[k] = g[2 * (k0 + k) + 1] / inv;
+}
 __global__ void k_energy_chain_series(const double *E, const double *Ev, int C, int c, long long k0, long long n, double *oE, double *oEv)
 {
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -254,6 +272,8 @@ struct pimc_handle {
     long long en_count[PIMC_MAXE];   // samples every Energy object holds (its own count, measurement.jl:119-120)
     unsigned char *mdone;            // [C] per-chain flag: Energy of the current measurement evaluated inside the sweep launch
     int opt_fuse_energy, opt_isweep;
+    int isw_backoff;                 // runs left on the sequential kernel before the optimistic sweep is probed again (dense regimes: most proposals replay)
+    double isw_replay_frac;          // replays per proposal of the last optimistic run
     int *nw_head, *nw_next;          // second cell list over proposed positions (optimistic sweep of interacting worldlines), lazily allocated
     unsigned long long *dstats;
     std::vector<void *> allocs;
@@ -264,6 +284,15 @@ struct pimc_handle {
     double *fscr;       // HBM scratch for warp-cooperative proposals that do not fit shared memory (lazily allocated)
     cudaEvent_t ev0, ev1;
     int device;
+    PcDev pc[PIMC_MAXP]; long long pc_ndata[PIMC_MAXP]; int npc;      // g(r) objects
+    WiDev wi[PIMC_MAXW]; long long wi_count[PIMC_MAXW]; int nwi;       // winding-number objects
+    // multi-GPU: one rank per handle; estimator blocks are all-reduced on a side stream while the next block's moves run
+    void *comm;                        // ncclComm_t, null = single GPU
+    int nranks, rank; long long chains_total;
+    cudaStream_t cstream; cudaEvent_t cev;
+    double *g_en[PIMC_MAXE];           // [cap][2] chain sums of (E, Ev) per measurement index, all-reduced over the ranks
+    long long g_en_upto[PIMC_MAXE];    // rows of g_en that hold reduced values
+    unsigned long long *g_u64; size_t g_u64_n;   // density read-out staging (counters + ndata)
 };
 static char g_err[512] = "";
 static long long g_launches = 0;
@@ -329,14 +358,141 @@ extern "C" int pimc_measure_fp64_peak(double *tflops)
 }
 extern "C" const char *pimc_last_error(const pimc_handle *h) { return h ? h->err : g_err; }
 
+static void comm_teardown(pimc_handle *h);
 extern "C" void pimc_destroy(pimc_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    comm_teardown(h);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
+}
+
+
+// =====================================================================================================
+// multi-GPU inside the library: chains shard over ranks with no data-path collective (chain_offset makes the result
+// independent of the sharding); the only exchange is the all-reduce of estimator blocks.  NCCL is bound at run time (dlopen of
+// libnccl.so.2: the copy a host process -- torch, MPI.jl -- already mapped is reused), so the library loads on boxes without it.
+// =====================================================================================================
+#include <dlfcn.h>
+#include <nccl.h>
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    ncclResult_t (*GetVersion)(int *);
+    bool ok;
+};
+static NcclApi *nccl_api()
+{
+    static NcclApi api; static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true; api.ok = false;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);        // already mapped by the host process?
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return nullptr;
+#define NSYM(field, name) do { *(void **)(&api.field) = dlsym(lib, name); if (!api.field) return nullptr; } while (0)
+    NSYM(GetUniqueId, "ncclGetUniqueId"); NSYM(CommInitRank, "ncclCommInitRank"); NSYM(CommInitAll, "ncclCommInitAll"); NSYM(CommDestroy, "ncclCommDestroy");
+    NSYM(AllReduce, "ncclAllReduce"); NSYM(GetErrorString, "ncclGetErrorString"); NSYM(GetVersion, "ncclGetVersion");
+#undef NSYM
+    api.ok = true; return &api;
+}
+#define NK(h, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { SETERR(h, "NCCL error %s at %s:%d (%s)", nccl_api()->GetErrorString(r_), __FILE__, __LINE__, #call); return PIMC_ERR_CUDA; } } while (0)
+
+static void comm_teardown(pimc_handle *h)
+{
+    if (h->comm && nccl_api()) { cudaStreamSynchronize(h->cstream); nccl_api()->CommDestroy((ncclComm_t)h->comm); }
+    h->comm = nullptr;
+    if (h->cstream) cudaStreamDestroy(h->cstream);
+    if (h->cev) cudaEventDestroy(h->cev);
+    h->cstream = nullptr; h->cev = nullptr;
+}
+static int comm_finish_init(pimc_handle *h, ncclComm_t comm, int nranks, int rank)
+{
+    h->comm = comm; h->nranks = nranks; h->rank = rank;
+    CK(h, cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    CK(h, cudaEventCreateWithFlags(&h->cev, cudaEventDisableTiming));
+    // total number of chains over the ranks (shards may be uneven): first collective of the communicator
+    if (h->g_u64_n < 4) { int rc = dalloc(h, &h->g_u64, 4); if (rc) return rc; h->g_u64_n = 4; }
+    unsigned long long c = (unsigned long long)h->S.C;
+    CK(h, cudaMemcpyAsync(h->g_u64, &c, 8, cudaMemcpyHostToDevice, h->cstream));
+    NK(h, nccl_api()->AllReduce(h->g_u64, h->g_u64, 1, ncclUint64, ncclSum, comm, h->cstream));
+    CK(h, cudaMemcpyAsync(&c, h->g_u64, 8, cudaMemcpyDeviceToHost, h->cstream));
+    CK(h, cudaStreamSynchronize(h->cstream));
+    h->chains_total = (long long)c;
+    for (int i = 0; i < h->nen; ++i) h->g_en_upto[i] = 0;
+    return PIMC_OK;
+}
+extern "C" int pimc_comm_get_unique_id(void *id128)
+{
+    if (!id128) return PIMC_ERR_INVALID;
+    NcclApi *a = nccl_api(); if (!a) { snprintf(g_err, sizeof g_err, "libnccl.so.2 not found (dlopen)"); return PIMC_ERR_UNSUPPORTED; }
+    static_assert(sizeof(ncclUniqueId) == PIMC_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id; ncclResult_t r = a->GetUniqueId(&id);
+    if (r != ncclSuccess) { snprintf(g_err, sizeof g_err, "ncclGetUniqueId: %s", a->GetErrorString(r)); return PIMC_ERR_CUDA; }
+    memcpy(id128, &id, sizeof id); return PIMC_OK;
+}
+extern "C" int pimc_comm_init(pimc_handle *h, int32_t nranks, int32_t rank, const void *id128)
+{
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PIMC_ERR_INVALID;
+    if (h->comm) { SETERR(h, "communicator already initialised"); return PIMC_ERR_STATE; }
+    NcclApi *a = nccl_api(); if (!a) { SETERR(h, "libnccl.so.2 not found (dlopen)"); return PIMC_ERR_UNSUPPORTED; }
+    CK(h, cudaSetDevice(h->device));
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    ncclComm_t comm; NK(h, a->CommInitRank(&comm, nranks, id, rank));
+    return comm_finish_init(h, comm, nranks, rank);
+}
+// one process, n handles on n different devices (the ncclCommInitAll form of SURVEY 8e).  Afterwards every handle must be driven from its
+// own host thread (a collective read-out blocks until all ranks have issued it).
+extern "C" int pimc_comm_init_all(pimc_handle **hs, int32_t n)
+{
+    if (!hs || n < 1 || n > 64) return PIMC_ERR_INVALID;
+    NcclApi *a = nccl_api(); if (!a) { SETERR(hs[0], "libnccl.so.2 not found (dlopen)"); return PIMC_ERR_UNSUPPORTED; }
+    int devs[64]; ncclComm_t comms[64];
+    for (int i = 0; i < n; ++i) { if (!hs[i] || hs[i]->comm) return PIMC_ERR_STATE; devs[i] = hs[i]->device; for (int k = 0; k < i; ++k) if (devs[k] == devs[i]) { SETERR(hs[0], "handles %d and %d share device %d", k, i, devs[i]); return PIMC_ERR_INVALID; } }
+    NK(hs[0], a->CommInitAll(comms, n, devs));
+    // the first collective (chain count) is issued for every rank before any of them is waited for
+    for (int i = 0; i < n; ++i) {
+        pimc_handle *h = hs[i];
+        CK(h, cudaSetDevice(h->device));
+        h->comm = comms[i]; h->nranks = n; h->rank = i;
+        CK(h, cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->cev, cudaEventDisableTiming));
+        if (h->g_u64_n < 4) { int rc = dalloc(h, &h->g_u64, 4); if (rc) return rc; h->g_u64_n = 4; }
+    }
+    long long tot = 0; for (int i = 0; i < n; ++i) tot += hs[i]->S.C;
+    for (int i = 0; i < n; ++i) { hs[i]->chains_total = tot; for (int k = 0; k < hs[i]->nen; ++k) hs[i]->g_en_upto[k] = 0; }
+    return PIMC_OK;
+}
+extern "C" int pimc_comm_info(pimc_handle *h, int32_t *nranks, int32_t *rank, int64_t *chains_total, int32_t *nccl_version)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    if (nranks) *nranks = h->nranks; if (rank) *rank = h->rank; if (chains_total) *chains_total = h->chains_total;
+    if (nccl_version) { int v = 0; if (h->comm && nccl_api()) nccl_api()->GetVersion(&v); *nccl_version = v; }
+    return PIMC_OK;
+}
+// rows [from, to) of Energy object id: chain sums, then all-reduce over the ranks, on the side stream behind everything queued on the run
+// stream so far.  Returns immediately: the next block's moves overlap the reduction.
+static int comm_reduce_energy(pimc_handle *h, int id, long long from, long long to)
+{
+    if (!h->comm || to <= from) return PIMC_OK;
+    EnDev &E = h->T.en[id];
+    if (!h->g_en[id]) { int rc = dalloc(h, &h->g_en[id], (size_t)2 * E.cap); if (rc) return rc; }
+    if (to > E.cap) to = E.cap;
+    if (to <= from) return PIMC_OK;
+    CK(h, cudaEventRecord(h->cev, h->stream));
+    CK(h, cudaStreamWaitEvent(h->cstream, h->cev, 0));
+    k_energy_chain_sum<<<(int)(to - from), 256, 0, h->cstream>>>(E.E, E.Ev, h->S.C, from, h->g_en[id]); LAUNCHED();
+    CK(h, cudaGetLastError());
+    NK(h, nccl_api()->AllReduce(h->g_en[id] + 2 * from, h->g_en[id] + 2 * from, (size_t)(2 * (to - from)), ncclDouble, ncclSum, (ncclComm_t)h->comm, h->cstream));
+    h->g_en_upto[id] = to;
+    return PIMC_OK;
 }
 
 static int sync_tables(pimc_handle *h) { CK(h, cudaMemcpyAsync(h->dT, &h->T, sizeof(DevTables), cudaMemcpyHostToDevice, h->stream)); return PIMC_OK; }
@@ -358,9 +514,12 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr; h->isw_backoff = 0; h->isw_replay_frac = 0.0;
     memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
+    h->npc = h->nwi = 0; memset(h->pc_ndata, 0, sizeof h->pc_ndata); memset(h->wi_count, 0, sizeof h->wi_count);
+    h->comm = nullptr; h->nranks = 1; h->rank = 0; h->chains_total = cfg->chains; h->cstream = nullptr; h->cev = nullptr; h->g_u64 = nullptr; h->g_u64_n = 0;
+    memset(h->g_en, 0, sizeof h->g_en); memset(h->g_en_upto, 0, sizeof h->g_en_upto);
     int rc = PIMC_OK;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); pimc_destroy(h); return PIMC_ERR_CUDA; } } while (0)
 #define RCC(call) do { rc = (call); if (rc != PIMC_OK) { snprintf(g_err, sizeof g_err, "%s", h->err); pimc_destroy(h); return rc; } } while (0)
@@ -434,7 +593,7 @@ extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
     if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FAITHFUL_IMPL && value >= 0 && value <= 1) { h->opt_faithful_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FUSE_ENERGY && value >= 0 && value <= 1) { h->opt_fuse_energy = (int)value; return PIMC_OK; }
-    if (option == PIMC_OPT_ISWEEP && value >= 0 && value <= 1) { h->opt_isweep = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_ISWEEP && value >= 0 && value <= 2) { h->opt_isweep = (int)value; h->isw_backoff = 0; return PIMC_OK; }
     SETERR(h, "unknown option %d / value %lld", option, (long long)value); return PIMC_ERR_INVALID;
 }
 extern "C" int pimc_set_iter(pimc_handle *h, uint64_t iter) { if (!h) return PIMC_ERR_INVALID; h->iter = iter; return PIMC_OK; }
@@ -776,7 +935,12 @@ extern "C" int pimc_energy_read_range(pimc_handle *h, int32_t id, int32_t chain,
     long long m = avail - start; if (m > count) m = count;
     if (m <= 0 || (!E && !Ev)) return PIMC_OK;
     TmpBuf t; double *a = t.up((double *)nullptr, m), *b = t.up((double *)nullptr, m); if (!a || !b) return PIMC_ERR_NOMEM;
-    if (chain < 0) k_energy_chain_mean<<<(int)m, 256, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, start, a, b);
+    if (chain < 0 && h->comm) {   // mean over the chains of ALL ranks (collective: every rank reads the same range); blocks reduced at the end of pimc_run are ready
+        if (h->g_en_upto[id] < avail) { rc = comm_reduce_energy(h, id, h->g_en_upto[id], avail); if (rc) return rc; }
+        CK(h, cudaStreamSynchronize(h->cstream));
+        k_energy_global_mean<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->g_en[id], start, m, (double)h->chains_total, a, b);
+    }
+    else if (chain < 0) k_energy_chain_mean<<<(int)m, 256, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, start, a, b);
     else k_energy_chain_series<<<(int)((m + 127) / 128), 128, 0, h->stream>>>(h->T.en[id].E, h->T.en[id].Ev, h->S.C, chain, start, m, a, b);
     LAUNCHED();
     CK(h, cudaGetLastError()); CK(h, cudaStreamSynchronize(h->stream));
@@ -827,9 +991,29 @@ extern "C" int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64
         // read-out buffer kept with the handle: a cudaMalloc / cudaFree pair per block costs a device-wide synchronisation each
         if (h->dens_out_n < sz) { double *o2 = nullptr; int rc = dalloc(h, &o2, sz); if (rc) return rc; h->dens_out = o2; h->dens_out_n = sz; }
         double *o = h->dens_out;
-        k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(D.dens, sz, o); LAUNCHED(); CK(h, cudaGetLastError());
+        const unsigned long long *src = D.dens;
+        if (h->comm) {   // counters summed over the ranks (collective); the local counters stay local
+            if (h->g_u64_n < sz + 1) { int rc = dalloc(h, &h->g_u64, sz + 1); if (rc) return rc; h->g_u64_n = sz + 1; }
+            CK(h, cudaMemcpyAsync(h->g_u64, D.dens, sz * 8, cudaMemcpyDeviceToDevice, h->cstream));
+            const unsigned long long nd = (unsigned long long)h->de_ndata[id];
+            CK(h, cudaMemcpyAsync(h->g_u64 + sz, &nd, 8, cudaMemcpyHostToDevice, h->cstream));
+            NK(h, nccl_api()->AllReduce(h->g_u64, h->g_u64, sz + 1, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->cstream));
+            CK(h, cudaStreamSynchronize(h->cstream));
+            src = h->g_u64;
+        }
+        k_dens_to_double<<<grid_for(sz, 256), 256, 0, h->stream>>>(src, sz, o); LAUNCHED(); CK(h, cudaGetLastError());
         CK(h, cudaStreamSynchronize(h->stream));
         CK(h, cudaMemcpy(dens, o, sz * sizeof(double), cudaMemcpyDeviceToHost));
+        if (h->comm && ndata) { unsigned long long nd; CK(h, cudaMemcpy(&nd, h->g_u64 + sz, 8, cudaMemcpyDeviceToHost)); *ndata = (int64_t)nd; ndata = nullptr; }
+    }
+    else if (h->comm && ndata) {   // ndata alone: still the global count
+        if (h->g_u64_n < 4) { int rc = dalloc(h, &h->g_u64, 4); if (rc) return rc; h->g_u64_n = 4; }
+        unsigned long long nd = (unsigned long long)h->de_ndata[id];
+        CK(h, cudaMemcpyAsync(h->g_u64, &nd, 8, cudaMemcpyHostToDevice, h->cstream));
+        NK(h, nccl_api()->AllReduce(h->g_u64, h->g_u64, 1, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->cstream));
+        CK(h, cudaMemcpyAsync(&nd, h->g_u64, 8, cudaMemcpyDeviceToHost, h->cstream));
+        CK(h, cudaStreamSynchronize(h->cstream));
+        *ndata = (int64_t)nd; ndata = nullptr;
     }
     if (ndata) *ndata = h->de_ndata[id];
     if (bin) *bin = D.bin;
@@ -837,8 +1021,10 @@ extern "C" int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64
 }
 
 // ---- run! ----
-extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
-                        const int32_t *energy_ids, int32_t nen, const int32_t *density_ids, int32_t nde, int32_t sched, pimc_run_stats *stats)
+// force_cadence: the measurement cadence (N_MC / Nctr, simulation.jl:31-32 retry cap) runs although neither Energy nor Density is listed --
+// pimc_run_ex drives the remaining estimators between segments
+static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
+                    const int32_t *energy_ids, int32_t nen, const int32_t *density_ids, int32_t nde, int32_t sched, bool force_cadence, pimc_run_stats *stats)
 {
     if (!h) return PIMC_ERR_INVALID;
     if (n < 0 || nupd < 1 || nupd > PIMC_MAXU || nen < 0 || nen > PIMC_MAXE || nde < 0 || nde > PIMC_MAXD || !update_ids || !every) { SETERR(h, "pimc_run: bad arguments"); return PIMC_ERR_INVALID; }
@@ -860,9 +1046,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     }
     for (int i = 0; i < nde; ++i) { if (density_ids[i] < 0 || density_ids[i] >= h->nde) { SETERR(h, "bad density id"); return PIMC_ERR_INVALID; } P.de_id[i] = density_ids[i]; }
     P.Nctr0 = h->Nctr; P.N_MC0 = h->N_MC; P.Ncycle = h->cfg.Ncycle; P.stats = h->dstats;
-    S.ctr = (nen + nde == 0) ? 10000 : 1000; // simulation.jl:31-32
+    const bool cadence = force_cadence || nen + nde > 0;
+    S.ctr = cadence ? 1000 : 10000; // simulation.jl:31-32
     // energy overflow: the reference errors when the pre-sized vector is full (measurement.jl:119-120); every Energy object counts its own samples
-    const long long nmeas = (nen + nde > 0) ? (h->Nctr + n) / h->cfg.Ncycle : 0;
+    const long long nmeas = cadence ? (h->Nctr + n) / h->cfg.Ncycle : 0;
     for (int i = 0; i < nen; ++i) {
         const long long cnt = h->en_count[P.en_id[i]];
         if (cnt + nmeas > h->T.en[P.en_id[i]].cap) { SETERR(h, "Energy buffer of %lld entries would overflow (%lld + %lld)", (long long)h->T.en[P.en_id[i]].cap, cnt, nmeas); return PIMC_ERR_STATE; }
@@ -908,8 +1095,12 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     // optimistic-parallel sweep of interacting worldlines (pimc_isweep.cuh): the hard core is the only coupling between the proposals of a
     // sweep when the pair action does not enter ReshapeLinear / centre-of-mass moves (the reference as shipped, compat PAIR_BYVALUE)
     const bool pair_in_moves = S.interactions && !(S.compat & PIMC_COMPAT_PAIR_BYVALUE);
-    const bool isweep = sched == PIMC_SCHED_SWEEP && S.need_cells && S.a > 0.0 && !pair_in_moves && h->opt_isweep != 0 && h->opt_faithful_impl == 0 &&
-                        S.M <= 256 && S.N <= 8192 && isw_rs_smem_bytes(S.N, S.M) <= 200 * 1024;
+    const bool isweep_ok = sched == PIMC_SCHED_SWEEP && S.need_cells && S.a > 0.0 && !pair_in_moves && h->opt_isweep != 0 && h->opt_faithful_impl == 0 &&
+                           S.M <= 256 && S.N <= 8192 && isw_rs_smem_bytes(S.N, S.M) <= 200 * 1024;
+    // both paths execute the same sequential definition bit for bit, so the choice is free: option 1 = adaptive (after a run in which more
+    // than 30 % of the proposals had to be replayed serially the next 7 runs take the persistent sequential kernel), option 2 = always optimistic
+    bool isweep = isweep_ok;
+    if (isweep_ok && h->opt_isweep == 1 && n > 0 && h->isw_backoff > 0) { isweep = false; h->isw_backoff -= 1; }
     CK(h, cudaEventRecord(h->ev0, h->stream));
     if (n > 0 && isweep) {
         if (!h->nw_head) {
@@ -986,6 +1177,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     CK(h, cudaStreamSynchronize(h->stream));
     float ms = 0; CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     unsigned long long st[32]; CK(h, cudaMemcpy(st, h->dstats, sizeof st, cudaMemcpyDeviceToHost));
+    if (n > 0 && isweep && st[13] > 0) {
+        h->isw_replay_frac = (double)st[12] / (double)st[13];
+        if (h->opt_isweep == 1 && h->isw_replay_frac > 0.30) h->isw_backoff = 7;
+    }
     if (P.prof && n > 0 && isweep) {
         const double sw = (double)st[4 + 9] / S.N > 0 ? (double)st[4 + 9] / S.N : 1.0;   // chain-sweeps executed
         fprintf(stderr, "[pimc prof] isweep %.3f ms, %lld iterations x %d chains, %.0f chain-sweeps, %.2f replays per chain-sweep; cycles per chain-sweep", ms, (long long)n, S.C, sw, (double)st[4 + 8] / sw);
@@ -1001,8 +1196,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
         fprintf(stderr, "; per iteration: bookkeeping %.0f, estimators %.0f\n", (double)st[4 + 8] / ((double)n * S.C), (double)st[4 + 9] / ((double)n * S.C));
     }
     h->iter += (unsigned long long)n;
-    if (nen + nde > 0) {
+    if (cadence) {
         h->N_MC += nmeas; h->Nctr = (h->Nctr + n) % h->cfg.Ncycle;
+        // per-block all-reduce of the Energy accumulators, queued on the side stream: it overlaps the next block's moves
+        for (int i = 0; i < nen && h->comm; ++i) if (h->g_en_upto[P.en_id[i]] == h->en_count[P.en_id[i]]) { int rc = comm_reduce_energy(h, P.en_id[i], h->en_count[P.en_id[i]], h->en_count[P.en_id[i]] + nmeas); if (rc) return rc; }
         for (int i = 0; i < nen; ++i) h->en_count[P.en_id[i]] += nmeas;
         for (int i = 0; i < nde; ++i) h->de_ndata[P.de_id[i]] += nmeas * (long long)S.M * S.C;
     }
@@ -1016,6 +1213,142 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
     }
     return PIMC_OK;
 }
+extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
+                        const int32_t *energy_ids, int32_t nen, const int32_t *density_ids, int32_t nde, int32_t sched, pimc_run_stats *stats)
+{
+    return run_core(h, n, update_ids, every, nupd, energy_ids, nen, density_ids, nde, sched, false, stats);
+}
+
+// ---- estimators the reference lists as TODO (measurement.jl:125-127): g(r) and winding number ----
+extern "C" int pimc_paircorr_create(pimc_handle *h, int64_t nbins, double rmax, int32_t *id)
+{
+    if (!h || !id || nbins < 1 || !(rmax > 0)) return PIMC_ERR_INVALID;
+    if (h->npc >= PIMC_MAXP) { SETERR(h, "at most %d pair-correlation objects per handle", PIMC_MAXP); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    PcDev &G = h->pc[h->npc]; G.nbins = nbins; G.rmax = rmax; G.bin = rmax / (double)nbins;
+    int TS, sh; if (pimc_paircorr_smem(h->S, G, &TS, &sh) > 200 * 1024) { SETERR(h, "pair correlation: N = %d does not fit the shared-memory tile", h->S.N); return PIMC_ERR_UNSUPPORTED; }
+    int rc = dalloc(h, &G.hist, (size_t)nbins); if (rc) return rc;
+    h->pc_ndata[h->npc] = 0;
+    *id = h->npc++;
+    return PIMC_OK;
+}
+extern "C" int pimc_paircorr_measure(pimc_handle *h, int32_t id)
+{
+    if (!h || id < 0 || id >= h->npc) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, pimc_launch_paircorr(h->S.C, h->stream, h->S, h->pc[id])); LAUNCHED();
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->pc_ndata[id] += (long long)h->S.M * h->S.C;
+    return PIMC_OK;
+}
+// hist: nbins pair counts summed over this handle's chains (over all ranks with a communicator attached); ndata likewise
+extern "C" int pimc_paircorr_read(pimc_handle *h, int32_t id, double *hist, int64_t *ndata, double *bin)
+{
+    if (!h || id < 0 || id >= h->npc) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    PcDev &G = h->pc[id]; const size_t sz = (size_t)G.nbins;
+    long long nd = h->pc_ndata[id];
+    std::vector<unsigned long long> tmp(sz + 1);
+    if (h->comm) {
+        if (h->g_u64_n < sz + 1) { int rc = dalloc(h, &h->g_u64, sz + 1); if (rc) return rc; h->g_u64_n = sz + 1; }
+        CK(h, cudaMemcpyAsync(h->g_u64, G.hist, sz * 8, cudaMemcpyDeviceToDevice, h->cstream));
+        const unsigned long long ndu = (unsigned long long)nd;
+        CK(h, cudaMemcpyAsync(h->g_u64 + sz, &ndu, 8, cudaMemcpyHostToDevice, h->cstream));
+        NK(h, nccl_api()->AllReduce(h->g_u64, h->g_u64, sz + 1, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->cstream));
+        CK(h, cudaMemcpyAsync(tmp.data(), h->g_u64, (sz + 1) * 8, cudaMemcpyDeviceToHost, h->cstream));
+        CK(h, cudaStreamSynchronize(h->cstream));
+        nd = (long long)tmp[sz];
+    } else CK(h, cudaMemcpy(tmp.data(), G.hist, sz * 8, cudaMemcpyDeviceToHost));
+    if (hist) for (size_t i = 0; i < sz; ++i) hist[i] = (double)tmp[i];
+    if (ndata) *ndata = nd;
+    if (bin) *bin = G.bin;
+    return PIMC_OK;
+}
+extern "C" int pimc_winding_create(pimc_handle *h, int64_t cap, int32_t *id)
+{
+    if (!h || !id || cap < 1) return PIMC_ERR_INVALID;
+    if (h->nwi >= PIMC_MAXW) { SETERR(h, "at most %d winding objects per handle", PIMC_MAXW); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    WiDev &W = h->wi[h->nwi]; W.cap = cap;
+    int rc = dalloc(h, &W.W, (size_t)cap * h->S.dim * h->S.C); if (rc) return rc;
+    h->wi_count[h->nwi] = 0;
+    *id = h->nwi++;
+    return PIMC_OK;
+}
+// winding number of the CURRENT configuration of every chain: W[chains][dim]
+extern "C" int pimc_winding_now(pimc_handle *h, double *W)
+{
+    if (!h || !W) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    const int C = h->S.C, dim = h->S.dim;
+    TmpBuf t; WiDev tmp; tmp.cap = 1; tmp.W = t.up((double *)nullptr, (size_t)dim * C); if (!tmp.W) return PIMC_ERR_NOMEM;
+    CK(h, pimc_launch_winding(C, h->stream, h->S, tmp, 0)); LAUNCHED();
+    CK(h, cudaStreamSynchronize(h->stream));
+    std::vector<double> w((size_t)dim * C);
+    CK(h, cudaMemcpy(w.data(), tmp.W, sizeof(double) * w.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < C; ++c) for (int k = 0; k < dim; ++k) W[(size_t)c * dim + k] = w[(size_t)k * C + c];
+    return PIMC_OK;
+}
+// series of one chain: W[n][dim] (chain >= 0), or with chain = -1 the chain-mean of W^2 = sum_k W_k^2 per measurement: W2[n] (local chains)
+extern "C" int pimc_winding_read(pimc_handle *h, int32_t id, int32_t chain, double *out, int64_t cap, int64_t *n)
+{
+    if (!h || id < 0 || id >= h->nwi || chain < -1 || chain >= h->S.C || cap < 0) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const long long cnt = h->wi_count[id]; if (n) *n = cnt;
+    long long m = cnt < h->wi[id].cap ? cnt : h->wi[id].cap; if (m > cap) m = cap;
+    if (m <= 0 || !out) return PIMC_OK;
+    const int C = h->S.C, dim = h->S.dim;
+    std::vector<double> w((size_t)m * dim * C);
+    CK(h, cudaMemcpy(w.data(), h->wi[id].W, sizeof(double) * w.size(), cudaMemcpyDeviceToHost));
+    for (long long k = 0; k < m; ++k) {
+        if (chain >= 0) for (int d = 0; d < dim; ++d) out[k * dim + d] = w[((size_t)k * dim + d) * C + chain];
+        else { double s2 = 0.0; for (int c = 0; c < C; ++c) for (int d = 0; d < dim; ++d) { const double v = w[((size_t)k * dim + d) * C + c]; s2 += v * v; } out[k] = s2 / C; }
+    }
+    return PIMC_OK;
+}
+
+// run! with the full estimator list.  Energy / Density are evaluated inside the run kernels; the estimators above are launched between
+// segments of the run that end on a measurement event (same cadence: measurement_Z_sector, measurement.jl:1-17).
+extern "C" int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
+                           const pimc_measurements *meas, int32_t sched, pimc_run_stats *stats)
+{
+    if (!h) return PIMC_ERR_INVALID;
+    pimc_measurements none; memset(&none, 0, sizeof none);
+    const pimc_measurements &Z = meas ? *meas : none;
+    if (Z.npaircorr < 0 || Z.npaircorr > PIMC_MAXP || Z.nwinding < 0 || Z.nwinding > PIMC_MAXW) { SETERR(h, "pimc_run_ex: bad estimator counts"); return PIMC_ERR_INVALID; }
+    for (int i = 0; i < Z.npaircorr; ++i) if (Z.paircorr_ids[i] < 0 || Z.paircorr_ids[i] >= h->npc) { SETERR(h, "bad pair-correlation id"); return PIMC_ERR_INVALID; }
+    for (int i = 0; i < Z.nwinding; ++i) if (Z.winding_ids[i] < 0 || Z.winding_ids[i] >= h->nwi) { SETERR(h, "bad winding id"); return PIMC_ERR_INVALID; }
+    const int nextra = Z.npaircorr + Z.nwinding;
+    if (nextra == 0) return run_core(h, n, update_ids, every, nupd, Z.energy_ids, Z.nenergy, Z.density_ids, Z.ndensity, sched, false, stats);
+    {   // winding series overflow: like Energy, the pre-sized vector must hold every sample of this run
+        const long long nmeas = (h->Nctr + n) / h->cfg.Ncycle;
+        for (int i = 0; i < Z.nwinding; ++i) if (h->wi_count[Z.winding_ids[i]] + nmeas > h->wi[Z.winding_ids[i]].cap) { SETERR(h, "winding buffer would overflow"); return PIMC_ERR_STATE; }
+    }
+    pimc_run_stats tot; memset(&tot, 0, sizeof tot);
+    long long remaining = n;
+    while (remaining > 0) {
+        const long long to_event = h->cfg.Ncycle - h->Nctr, seg = remaining < to_event ? remaining : to_event;
+        pimc_run_stats st; memset(&st, 0, sizeof st);
+        int rc = run_core(h, seg, update_ids, every, nupd, Z.energy_ids, Z.nenergy, Z.density_ids, Z.ndensity, sched, true, &st);
+        if (rc) return rc;
+        tot.iterations += st.iterations; tot.proposals += st.proposals; tot.bead_moves += st.bead_moves; tot.measurements += st.measurements;
+        tot.launches += st.launches; tot.kernel_ms += st.kernel_ms; tot.accepted = st.accepted;
+        if (seg == to_event) {          // a measurement event ends this segment
+            cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+            CK(h, cudaEventRecord(e0, h->stream));
+            for (int i = 0; i < Z.npaircorr; ++i) { CK(h, pimc_launch_paircorr(h->S.C, h->stream, h->S, h->pc[Z.paircorr_ids[i]])); LAUNCHED(); tot.launches++; h->pc_ndata[Z.paircorr_ids[i]] += (long long)h->S.M * h->S.C; }
+            for (int i = 0; i < Z.nwinding; ++i) { const int id = Z.winding_ids[i]; CK(h, pimc_launch_winding(h->S.C, h->stream, h->S, h->wi[id], h->wi_count[id])); LAUNCHED(); tot.launches++; h->wi_count[id] += 1; }
+            CK(h, cudaEventRecord(e1, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+            float ms = 0; CK(h, cudaEventElapsedTime(&ms, e0, e1)); tot.kernel_ms += ms;
+        }
+        remaining -= seg;
+    }
+    if (stats) *stats = tot;
+    return PIMC_OK;
+}
 
 // ---- checkpoint / resume: the complete chain state as one host blob ----
 // The reference's savetools (examples/tools/savetools.jl:4-34) write the paths only, so a reloaded Julia run restarts its step adaptation and
@@ -1023,9 +1356,10 @@ extern "C" int pimc_run(pimc_handle *h, int64_t n, const int32_t *update_ids, co
 // cell lists with their list order and multiplicities (B13), iteration counter of the addressed RNG, measurement cadence, every update
 // object's adaptive variable / counters / acceptance window, every estimator's accumulators.
 struct StateHeader {
-    unsigned long long magic; int version, dim, M, N, C, need_cells, ncell, nupd, nen, nde; unsigned chain_offset; unsigned long long seed;
+    unsigned long long magic; int version, dim, M, N, C, need_cells, ncell, nupd, nen, nde, npc, nwi; unsigned chain_offset; unsigned long long seed;
     unsigned long long iter; long long N_MC, Nctr;
     long long en_count[PIMC_MAXE], en_cap[PIMC_MAXE], de_ndata[PIMC_MAXD], de_nbins[PIMC_MAXD];
+    long long pc_ndata[PIMC_MAXP], pc_nbins[PIMC_MAXP], wi_count[PIMC_MAXW], wi_cap[PIMC_MAXW];
     int upd_kind[PIMC_MAXU], upd_ring_words[PIMC_MAXU]; long long upd_adj[PIMC_MAXU], upd_range[PIMC_MAXU];
     double upd_vmin[PIMC_MAXU], upd_vmax[PIMC_MAXU], upd_minacc[PIMC_MAXU], upd_maxacc[PIMC_MAXU];
 };
@@ -1051,13 +1385,17 @@ static std::vector<Seg> state_segments(pimc_handle *h)
         v.push_back({ E.E, rows * C * 8 }); v.push_back({ E.Ev, rows * C * 8 }); v.push_back({ E.acc, C * 5 * 8 });
     }
     for (int i = 0; i < h->nde; ++i) { DeDev &D = h->T.de[i]; v.push_back({ D.dens, (S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins) * 8 }); }
+    for (int i = 0; i < h->npc; ++i) v.push_back({ h->pc[i].hist, (size_t)h->pc[i].nbins * 8 });
+    for (int i = 0; i < h->nwi; ++i) { const size_t rows = (size_t)(h->wi_count[i] < h->wi[i].cap ? h->wi_count[i] : h->wi[i].cap); v.push_back({ h->wi[i].W, rows * S.dim * C * 8 }); }
     return v;
 }
 static void state_header(pimc_handle *h, StateHeader *H)
 {
     memset(H, 0, sizeof *H);
     DevSys &S = h->S;
-    H->magic = PIMC_STATE_MAGIC; H->version = 1; H->dim = S.dim; H->M = S.M; H->N = S.N; H->C = S.C; H->need_cells = S.need_cells; H->ncell = S.ncell;
+    H->magic = PIMC_STATE_MAGIC; H->version = 2; H->npc = h->npc; H->nwi = h->nwi;
+    for (int i = 0; i < h->npc; ++i) { H->pc_ndata[i] = h->pc_ndata[i]; H->pc_nbins[i] = h->pc[i].nbins; }
+    for (int i = 0; i < h->nwi; ++i) { H->wi_count[i] = h->wi_count[i]; H->wi_cap[i] = h->wi[i].cap; } H->dim = S.dim; H->M = S.M; H->N = S.N; H->C = S.C; H->need_cells = S.need_cells; H->ncell = S.ncell;
     H->nupd = h->nupd; H->nen = h->nen; H->nde = h->nde; H->chain_offset = S.chain_offset; H->seed = S.seed;
     H->iter = h->iter; H->N_MC = h->N_MC; H->Nctr = h->Nctr;
     for (int i = 0; i < h->nen; ++i) { H->en_count[i] = h->en_count[i]; H->en_cap[i] = h->T.en[i].cap; }
@@ -1095,9 +1433,12 @@ extern "C" int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes)
     if (!h || !buf || bytes < (int64_t)sizeof(StateHeader)) return PIMC_ERR_INVALID;
     StateHeader H; memcpy(&H, buf, sizeof H);
     DevSys &S = h->S;
-    if (H.magic != PIMC_STATE_MAGIC || H.version != 1) { SETERR(h, "not a pimc_b200 state blob (magic / version)"); return PIMC_ERR_INVALID; }
+    if (H.magic != PIMC_STATE_MAGIC || H.version != 2) { SETERR(h, "not a pimc_b200 state blob (magic / version)"); return PIMC_ERR_INVALID; }
     if (H.dim != S.dim || H.M != S.M || H.N != S.N || H.C != S.C || H.need_cells != S.need_cells || H.ncell != S.ncell || H.seed != S.seed || H.chain_offset != S.chain_offset) {
         SETERR(h, "state blob belongs to another System (dim/M/N/chains/cells/seed/chain_offset differ)"); return PIMC_ERR_STATE; }
+    if (H.npc != h->npc || H.nwi != h->nwi) { SETERR(h, "state blob holds %d/%d pair-correlation/winding objects, the handle %d/%d", H.npc, H.nwi, h->npc, h->nwi); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->npc; ++i) if (H.pc_nbins[i] != h->pc[i].nbins) { SETERR(h, "pair-correlation object %d differs in nbins", i); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->nwi; ++i) if (H.wi_cap[i] != h->wi[i].cap) { SETERR(h, "winding object %d differs in capacity", i); return PIMC_ERR_STATE; }
     if (H.nupd != h->nupd || H.nen != h->nen || H.nde != h->nde) { SETERR(h, "state blob holds %d/%d/%d update/Energy/Density objects, the handle %d/%d/%d: create the same objects in the same order first", H.nupd, H.nen, H.nde, h->nupd, h->nen, h->nde); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->nupd; ++i) if (H.upd_kind[i] != h->T.upd[i].kind || H.upd_range[i] != h->T.upd[i].range) { SETERR(h, "update object %d differs in kind or window range", i); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->nen; ++i) if (H.en_cap[i] != h->T.en[i].cap) { SETERR(h, "Energy object %d differs in capacity", i); return PIMC_ERR_STATE; }
@@ -1105,8 +1446,10 @@ extern "C" int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes)
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
     h->iter = H.iter; h->N_MC = H.N_MC; h->Nctr = H.Nctr;
-    for (int i = 0; i < h->nen; ++i) h->en_count[i] = H.en_count[i];
+    for (int i = 0; i < h->nen; ++i) { h->en_count[i] = H.en_count[i]; h->g_en_upto[i] = 0; }
     for (int i = 0; i < h->nde; ++i) h->de_ndata[i] = H.de_ndata[i];
+    for (int i = 0; i < h->npc; ++i) h->pc_ndata[i] = H.pc_ndata[i];
+    for (int i = 0; i < h->nwi; ++i) h->wi_count[i] = H.wi_count[i];
     for (int i = 0; i < h->nupd; ++i) { UpdDev &U = h->T.upd[i]; U.adj = H.upd_adj[i]; U.vmin = H.upd_vmin[i]; U.vmax = H.upd_vmax[i]; U.minacc = H.upd_minacc[i]; U.maxacc = H.upd_maxacc[i]; }
     int64_t need; pimc_state_size(h, &need);   // after en_count is restored: the Energy segments hold the rows taken so far
     if (bytes < need) { SETERR(h, "state blob truncated (%lld of %lld bytes)", (long long)bytes, (long long)need); return PIMC_ERR_INVALID; }

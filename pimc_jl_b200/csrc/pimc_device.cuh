@@ -56,6 +56,11 @@ struct UpdDev {
 struct EnDev { double *E, *Ev; long long cap; double *acc; /* [C][5] n, sumE, sumE2, sumEv, sumEv2 */ };
 struct DeDev { unsigned long long *dens; long long nbins; double bin; };
 struct DevTables { UpdDev upd[PIMC_MAXU]; EnDev en[PIMC_MAXE]; DeDev de[PIMC_MAXD]; };
+// estimators the reference lists as TODO (measurement.jl:125-127); passed to their kernels by value
+#define PIMC_MAXP 4
+#define PIMC_MAXW 4
+struct PcDev { unsigned long long *hist; long long nbins; double rmax, bin; };   // g(r): counts per radial bin, all chains of the handle
+struct WiDev { double *W; long long cap; };                                      // winding series W[cap][dim][C]
 
 struct RunParams {
     long long n;

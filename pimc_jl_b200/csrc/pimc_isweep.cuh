@@ -343,7 +343,7 @@ __device__ __forceinline__ void d_isw_commit_rebuild(const DevSys &S, int c, int
     for (int i = warp; i < nsl; i += NW) { int sl = sl0 + i; if (sl >= M) sl -= M; d_rebuild_slice(S, c, sl); }
 }
 
-__global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_reshape(const __grid_constant__ DevSys S, const __grid_constant__ ISweepParams P)
+__global__ void __launch_bounds__(ISW_THREADS, 4) k_isweep_reshape(const __grid_constant__ DevSys S, const __grid_constant__ ISweepParams P)
 {
     extern __shared__ double smd[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = ISW_THREADS / 32;
@@ -406,15 +406,14 @@ __global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_reshape(const __grid_
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&stat[n], ISW_DIRTY);
     }
     ISW_TICK(2);
-    // ---- P4: dirty proposals in index order against the sequential state ----
-    for (int cur = 0;;) {
-        __syncthreads();
-        int d = cur;
-        while (d < N && (stat[d] & (ISW_DIRTY | ISW_DONE)) != ISW_DIRTY) ++d;
-        if (d >= N) break;
-        if (warp == 0) {
+    // ---- P4: dirty proposals in index order against the sequential state, all on warp 0 (no CTA barrier per replay; the scan of `stat`
+    //      and the replay must not race: a replay sets DONE on its own slot and DIRTY on higher ones) ----
+    __syncthreads();
+    if (warp == 0) {
+        for (int d = 0; d < N; ++d) {
+            if ((stat[d] & (ISW_DIRTY | ISW_DONE)) != ISW_DIRTY) continue;                // warp-uniform (one shared-memory word)
             const int m = mlen[d];
-            if (stat[d] & ISW_INS) d_isw_rs_link(S, P, c, d, m, first, rows, R1, false);     // its tentative rows leave NW
+            if (stat[d] & ISW_INS) d_isw_rs_link(S, P, c, d, m, first, rows, R1, false);  // its tentative rows leave NW
             __syncwarp();
             const int acc = d_isw_rs_replay(S, P, X, st, c, d, m, first, rows, R1);
             unsigned s = ISW_PROP | ISW_DIRTY | ISW_DONE;
@@ -429,10 +428,11 @@ __global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_reshape(const __grid_
             }
             __syncwarp();
             if (lane == 0) { stat[d] = s; s_nrep += 1; }
-            __threadfence_block();
+            __syncwarp();
         }
-        cur = d + 1;
     }
+    __threadfence_block();
+    __syncthreads();
     ISW_TICK(3);
     // ---- P5: commit ----
     const int nsl = s_maxm;                                                               // rows t = 0 .. maxm - 1 can change
@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_reshape(const __grid_
     __syncthreads();
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.sp.stats, s_pre);
     ISW_TICK(5);
-    if (P.prof && tid == 0) { for (int i = 0; i < 6; ++i) atomicAdd(P.prof + i, pacc[i]); atomicAdd(P.prof + 8, (unsigned long long)s_nrep); atomicAdd(P.prof + 9, (unsigned long long)N); }
+    if (P.prof && tid == 0) for (int i = 0; i < 6; ++i) atomicAdd(P.prof + i, pacc[i]);
+    if (tid == 0) { atomicAdd(P.sp.stats + 12, (unsigned long long)s_nrep); atomicAdd(P.sp.stats + 13, (unsigned long long)N); }   // replay rate: the host's dispatch heuristic
 }
 
 // =====================================================================================================================
@@ -531,7 +532,7 @@ static __device__ __noinline__ int d_isw_com_replay(const DevSys &S, const ISwee
 }
 
 template <int KM>
-__global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_com(const __grid_constant__ DevSys S, const __grid_constant__ ISweepParams P)
+__global__ void __launch_bounds__(ISW_THREADS, 4) k_isweep_com(const __grid_constant__ DevSys S, const __grid_constant__ ISweepParams P)
 {
     extern __shared__ double smd[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = ISW_THREADS / 32;
@@ -707,5 +708,6 @@ __global__ void __launch_bounds__(ISW_THREADS, 2) k_isweep_com(const __grid_cons
     __syncthreads();
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.sp.stats, s_pre);
     ISW_TICK(5);
-    if (P.prof && tid == 0) { for (int i = 0; i < 6; ++i) atomicAdd(P.prof + 10 + i, pacc[i]); atomicAdd(P.prof + 8, (unsigned long long)s_nrep); atomicAdd(P.prof + 9, (unsigned long long)N); }
+    if (P.prof && tid == 0) for (int i = 0; i < 6; ++i) atomicAdd(P.prof + 10 + i, pacc[i]);
+    if (tid == 0) { atomicAdd(P.sp.stats + 12, (unsigned long long)s_nrep); atomicAdd(P.sp.stats + 13, (unsigned long long)N); }
 }

@@ -4,7 +4,8 @@
 typedef void (*sweep_fn)(const DevSys, const DevTables *, const Sweep2Params);
 typedef void (*meas_fn)(const DevSys, const DevTables *, const MeasParams, const unsigned char *);
 
-template <int POT> static sweep_fn pick_sweep(int KM) { return KM <= 1 ? k_sweep<POT, 1> : KM <= 2 ? k_sweep<POT, 2> : KM <= 4 ? k_sweep<POT, 4> : k_sweep<POT, 8>; }
+template <int POT, bool FUSE> static sweep_fn pick_sweep(int KM) { return KM <= 1 ? k_sweep<POT, 1, FUSE> : KM <= 2 ? k_sweep<POT, 2, FUSE> : KM <= 4 ? k_sweep<POT, 4, FUSE> : k_sweep<POT, 8, FUSE>; }
+template <int POT> static sweep_fn pick_sweep(int KM, bool fuse) { return fuse ? pick_sweep<POT, true>(KM) : pick_sweep<POT, false>(KM); }
 template <int POT> static meas_fn pick_meas(int KM)
 {
     return KM <= 1 ? k_measure<POT, 1> : KM <= 2 ? k_measure<POT, 2> : KM <= 4 ? k_measure<POT, 4> : KM <= 8 ? k_measure<POT, 8> : k_measure<POT, 0>;
@@ -13,14 +14,15 @@ template <int POT> static meas_fn pick_meas(int KM)
 cudaError_t pimc_launch_sweep(int grid, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P)
 {
     const int KM = (S.M + 31) / 32, pk = S.pot.kind;
-    sweep_fn k = pk == PIMC_POT_ZERO ? pick_sweep<PIMC_POT_ZERO>(KM) : (pk == PIMC_POT_HARMONIC ? pick_sweep<PIMC_POT_HARMONIC>(KM) : pick_sweep<PIMC_POT_LATTICE>(KM));
-    static sweep_fn configured[16]; static int nconf = 0;
+    const bool fuse = P.fuse != 0;
+    sweep_fn k = pk == PIMC_POT_ZERO ? pick_sweep<PIMC_POT_ZERO>(KM, fuse) : (pk == PIMC_POT_HARMONIC ? pick_sweep<PIMC_POT_HARMONIC>(KM, fuse) : pick_sweep<PIMC_POT_LATTICE>(KM, fuse));
+    static sweep_fn configured[32]; static int nconf = 0;
     bool seen = false; for (int i = 0; i < nconf; ++i) seen |= configured[i] == k;
     if (!seen) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (nconf < 16) configured[nconf++] = k;
+        if (nconf < 32) configured[nconf++] = k;
     }
     k<<<grid, SWEEP_THREADS, smem, st>>>(S, dT, P);
     return cudaGetLastError();

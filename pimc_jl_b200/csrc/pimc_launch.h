@@ -33,7 +33,7 @@ __host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_
 __host__ __device__ inline size_t faithful_scratch_doubles(int N, int M) { return (size_t)((N + 1) & ~1) + 2 * FA_ARR * (size_t)(M + 1); }
 
 // ---- optimistic-parallel sweep of interacting worldlines (pimc_isweep.cuh) ----
-#define ISW_THREADS 256
+#define ISW_THREADS 128
 #define ISW_RARR 5
 struct ISweepParams {
     SweepParams sp;
@@ -58,5 +58,8 @@ cudaError_t pimc_launch_run(bool cells, int grid, int threads, size_t smem, cuda
 cudaError_t pimc_launch_sweep(int grid, size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
 cudaError_t pimc_launch_swap_iter(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
 cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const MeasParams &P, const unsigned char *mdone);
+size_t pimc_paircorr_smem(const DevSys &S, const PcDev &G, int *TS, int *smem_hist);
+cudaError_t pimc_launch_paircorr(int grid, cudaStream_t st, const DevSys &S, const PcDev &G);
+cudaError_t pimc_launch_winding(int grid, cudaStream_t st, const DevSys &S, const WiDev &W, long long k);
 cudaError_t pimc_launch_isweep(int grid, cudaStream_t st, const DevSys &S, const ISweepParams &P, bool has_rs, bool has_com);
 cudaError_t pimc_launch_iswap(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);

@@ -383,9 +383,12 @@ __device__ __forceinline__ void d_pcom_cycles(const DevSys &S, const SweepParams
 }
 
 // KM = ceil(M / 32) <= 8: the worldline lives in registers (KM beads per lane), one read and one write of HBM per bead.
-template <int POT, int KM, int TH = SWEEP_THREADS>
+// FUSE: this launch belongs to a measurement iteration -- the Energy functor (measurement.jl:92-122) of the chain is accumulated on the
+// fly from the final rows every proposal already holds in registers (one read of HBM serves the move and the estimator); chains with
+// exchange cycles (whose members this sweep does not stream) leave mdone[c] = 0 and are measured by k_measure.
+template <int POT, int KM, bool FUSE, int TH = SWEEP_THREADS>
 __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &U, const SweepParams &P, const pimc_stream &st,
-                                                 const int pick)
+                                                 const int pick, const Sweep2Params &P2, const DevTables *__restrict__ T)
 {
     extern __shared__ double sm[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TH / 32;
@@ -421,6 +424,8 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
     int it = 0;
     if (use_tma && warp < N) issue(warp, 0);
     unsigned long long my_beads = 0;
+    double e_link = 0.0, e_pot = 0.0, e_vkin = 0.0; int e_cyc = 0;   // FUSE: lane partials of the Energy sums of this warp's worldlines
+    const int dvk = S.pot.dv_kind;
     // groups of 32 proposals per warp: lane l draws the displacement of the l-th proposal of the group (one Philox per lane
     // instead of one per warp and proposal); the proposals themselves run one after the other, lanes striding the slices
     for (int g0 = warp; g0 < N; g0 += NW * 32) {
@@ -443,7 +448,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
             }
             const int nx = nextc[n];
             const bool single = nx == n;
-            if (!single) continue;              // members of exchange cycles: PolymerCOM moves them below, SingleCOM never (com.jl:139-141)
+            if (!single) { if (FUSE) e_cyc = 1; continue; }   // members of exchange cycles: PolymerCOM moves them below, SingleCOM never (com.jl:139-141)
             double *rx = S.r + RIDX(S, c, n, 0, 0), *ry = rx + M, *vl = S.Vl + VIDX(S, c, n, 0);
             double x[KM], y[KM], v[KM], wi = 0.0, wu = 0.0;
 #pragma unroll
@@ -504,6 +509,58 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
                     if (j < M) { rx[j] = x[k]; if (dim > 1) ry[j] = y[k]; vl[j] = v[k]; }
                 }
             }
+            if (FUSE) {
+                if (!acc) {                      // rejected: the worldline stays where it was (rows still staged / cached)
+#pragma unroll
+                    for (int k = 0; k < KM; ++k) {
+                        const int j = lane + 32 * k;
+                        const double *sx = stage0 + (size_t)stg * rows * M;
+                        x[k] = j < M ? (use_tma ? sx[j] : rx[j]) : 0.0;
+                        y[k] = (dim > 1 && j < M) ? (use_tma ? sx[M + j] : ry[j]) : 0.0;
+                    }
+                }
+                const double x00 = __shfl_sync(0xffffffffu, x[0], 0), y00 = __shfl_sync(0xffffffffu, y[0], 0);   // closed worldline: last link ends on bead 0
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                    const int j = lane + 32 * k;
+                    double bx = __shfl_down_sync(0xffffffffu, x[k], 1), by = __shfl_down_sync(0xffffffffu, y[k], 1);
+                    const double nbx = __shfl_sync(0xffffffffu, x[(k + 1 < KM) ? k + 1 : k], 0), nby = __shfl_sync(0xffffffffu, y[(k + 1 < KM) ? k + 1 : k], 0);
+                    if (lane == 31) { bx = nbx; by = nby; }
+                    if (j == M - 1) { bx = x00; by = y00; }
+                    if (j < M) {
+                        const double ax = x[k], ay = y[k];
+                        double ddx = fabs(ax - bx); { const double alt = twoL - ddx; ddx = alt < ddx ? alt : ddx; }
+                        double d2 = ddx * ddx;
+                        if (dim > 1) { double ddy = fabs(ay - by); const double alt = twoL - ddy; ddy = alt < ddy ? alt : ddy; d2 = d2 + ddy * ddy; }
+                        e_link += d2;
+                        if (dvk == PIMC_DV_IDENTITY) { double q = ax * ax; if (dim > 1) q = q + ay * ay; e_vkin += q; }   // r . dV(r), measurement.jl:105
+                        else if (dvk != PIMC_DV_ZERO) e_vkin += d_rdv(S.pot, ax, ay, dim);
+                    }
+                }
+                // sum over the links of V(a) + V(b) = (sum of the link actions) / (-tau / 2): the cached ones if rejected, the new ones if accepted
+                if (POT != PIMC_POT_ZERO && lane == 0) e_pot += (acc ? wu : wi) / mht;
+            }
+        }
+    }
+    if (FUSE) {
+        __shared__ double s_en[3 * (TH / 32)];
+        e_link = warp_sum(e_link); e_pot = warp_sum(e_pot); e_vkin = warp_sum(e_vkin);
+        const int anycyc = __syncthreads_or(e_cyc);
+        if (lane == 0) { s_en[warp] = e_link; s_en[NW + warp] = e_pot; s_en[2 * NW + warp] = e_vkin; }
+        __syncthreads();
+        if (tid == 0 && !anycyc) {
+            double link = 0.0, pot = 0.0, vkin = 0.0;
+            for (int i = 0; i < NW; ++i) { link += s_en[i]; pot += s_en[NW + i]; vkin += s_en[2 * NW + i]; }
+            const double E = (double)(S.dim * S.N) / (2 * S.tau) - 1 / (4 * S.lambda * (S.tau * S.tau) * S.M) * link + 1.0 / (2 * S.M) * pot;
+            const double Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
+            for (int e = 0; e < P2.mp.nen; ++e) {
+                const EnDev &En = T->en[P2.mp.en_id[e]];
+                const long long k = P2.mp.en_k0[e] + P2.mp.ord;
+                if (k < En.cap) { En.E[(size_t)k * S.C + c] = E; En.Ev[(size_t)k * S.C + c] = Ev; }
+                double *a = En.acc + (size_t)c * 5;
+                a[0] += 1.0; a[1] += E; a[2] += E * E; a[3] += Ev; a[4] += Ev * Ev;
+            }
+            P2.mdone[c] = 1;
         }
     }
     if (polymer) {                              // whole-cycle moves of the exchange cycles, all warps together (staging area reused)
@@ -516,7 +573,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
 }
 
 // One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
-template <int POT, int KM>
+template <int POT, int KM, bool FUSE>
 __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(const __grid_constant__ DevSys S, const DevTables *__restrict__ T,
                                                                                                    const __grid_constant__ Sweep2Params P2)
 {
@@ -527,7 +584,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
     const int pick = d_pick_update(P, di);
     const int kind = P.kind[pick];
     if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM>(S, P2.upd[pick], P, st, pick);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, FUSE>(S, P2.upd[pick], P, st, pick, P2, T);
 }
 
 // The swap move stays one proposal per chain and iteration (reshape.jl:123-283): one warp per chain.  Everything that touches

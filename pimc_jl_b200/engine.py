@@ -16,6 +16,13 @@ def _f(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def comm_unique_id():
+    """128 bytes of an ncclUniqueId (pimc_comm_get_unique_id); rank 0 creates it and ships it to the other ranks"""
+    buf = (C.c_ubyte * 128)()
+    L.check(L.load().pimc_comm_get_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
+
+
 class Engine:
     def __init__(self, pot=None, dim=2, M=100, N=2, chains=1, chain_offset=0, mu=0.0, L_=4.0, T=1.0, lam=1.0,
                  interactions=False, g=0.0, r_a=0.0, Ncycle=10, compat=L.COMPAT_ALL, init=True, seed=0x5EEDB200,
@@ -70,6 +77,16 @@ class Engine:
 
     def set_iter(self, it):
         self._ck(self.lib.pimc_set_iter(self.h, it))
+
+    def comm_init(self, nranks, rank, unique_id):
+        """attach an NCCL communicator (pimc_comm_init): estimator read-outs with chain = -1 / density_read become global and collective"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.pimc_comm_init(self.h, nranks, rank, C.cast(buf, C.c_void_p)))
+
+    def comm_info(self):
+        nr, rk, ver, tot = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        self._ck(self.lib.pimc_comm_info(self.h, C.byref(nr), C.byref(rk), C.byref(tot), C.byref(ver)))
+        return dict(nranks=nr.value, rank=rk.value, chains_total=tot.value, nccl_version=ver.value)
 
     def get_state(self):
         """the complete chain state as one uint8 array (pimc_get_state): resumes bit for bit through set_state"""
@@ -217,7 +234,7 @@ class Engine:
         self._ck(self.lib.pimc_density_read(self.h, did, _p(dens), C.byref(nd), C.byref(b)))
         return dens.reshape(shape, order="F"), nd.value, b.value
 
-    def run(self, n, updates, energies=(), densities=(), sched=L.SCHED_FAITHFUL):
+    def run(self, n, updates, energies=(), densities=(), sched=L.SCHED_FAITHFUL, paircorrs=(), windings=()):
         """updates: [(every, update_id)] ; returns RunStats as dict"""
         nu = len(updates)
         ids = (C.c_int32 * nu)(*[u for _, u in updates])
@@ -225,8 +242,46 @@ class Engine:
         en = (C.c_int32 * max(1, len(energies)))(*energies)
         de = (C.c_int32 * max(1, len(densities)))(*densities)
         st = L.RunStats()
-        self._ck(self.lib.pimc_run(self.h, n, ids, ev, nu, en, len(energies), de, len(densities), sched, C.byref(st)))
+        if not paircorrs and not windings:
+            self._ck(self.lib.pimc_run(self.h, n, ids, ev, nu, en, len(energies), de, len(densities), sched, C.byref(st)))
+        else:
+            pc = (C.c_int32 * max(1, len(paircorrs)))(*paircorrs)
+            wi = (C.c_int32 * max(1, len(windings)))(*windings)
+            z = L.Measurements(C.cast(en, L.i32p), len(energies), C.cast(de, L.i32p), len(densities), C.cast(pc, L.i32p), len(paircorrs),
+                               C.cast(wi, L.i32p), len(windings))
+            self._ck(self.lib.pimc_run_ex(self.h, n, ids, ev, nu, C.byref(z), sched, C.byref(st)))
         return {k: getattr(st, k) for k, _ in L.RunStats._fields_}
+
+    # ---- estimators the reference lists as TODO (measurement.jl:125-127) ----
+    def paircorr_create(self, nbins, rmax):
+        i = C.c_int32()
+        self._ck(self.lib.pimc_paircorr_create(self.h, nbins, float(rmax), C.byref(i)))
+        return i.value
+
+    def paircorr_measure(self, pid):
+        self._ck(self.lib.pimc_paircorr_measure(self.h, pid))
+
+    def paircorr_read(self, pid, nbins):
+        hist, nd, b = np.zeros(nbins), C.c_int64(), C.c_double()
+        self._ck(self.lib.pimc_paircorr_read(self.h, pid, _p(hist), C.byref(nd), C.byref(b)))
+        return hist, nd.value, b.value
+
+    def winding_create(self, cap):
+        i = C.c_int32()
+        self._ck(self.lib.pimc_winding_create(self.h, cap, C.byref(i)))
+        return i.value
+
+    def winding_now(self):
+        W = np.zeros((self.C, self.dim))
+        self._ck(self.lib.pimc_winding_now(self.h, _p(W)))
+        return W
+
+    def winding_read(self, wid, chain=-1):
+        n = C.c_int64()
+        self._ck(self.lib.pimc_winding_read(self.h, wid, chain, None, 0, C.byref(n)))
+        out = np.zeros((max(1, n.value), self.dim)) if chain >= 0 else np.zeros(max(1, n.value))
+        self._ck(self.lib.pimc_winding_read(self.h, wid, chain, _p(out), n.value, C.byref(n)))
+        return out[:n.value], n.value
 
 
 # ---- stateless device hooks ----

@@ -263,6 +263,65 @@ class Density:                      # src/measurement.jl:31-55
         s.engine.density_measure(self.id)
 
 
+class PairCorrelation:              # `#TODO radial distribution` (src/measurement.jl:125), in the style of Density
+    """g(r) from equal-time pair distances: PairCorrelation(s; nbins=200, rmax=s.L); .hist (raw pair counts), .ndata, .g (normalised)"""
+
+    def __init__(self, s, nbins=200, rmax=None):
+        self.s, self.nbins, self.rmax = s, nbins, float(s.L if rmax is None else rmax)
+        self.bin = self.rmax / nbins
+        self.id = s.engine.paircorr_create(nbins, self.rmax)
+
+    def _read(self):
+        h, nd, _ = self.s.engine.paircorr_read(self.id, self.nbins)   # global over the ranks when the library communicator is attached
+        return h, nd
+
+    @property
+    def hist(self):
+        return self._read()[0]
+
+    @property
+    def ndata(self):
+        return self._read()[1]
+
+    @property
+    def r(self):
+        return (np.arange(self.nbins) + 0.5) * self.bin
+
+    @property
+    def g(self):
+        h, nd = self._read()
+        edges = np.arange(self.nbins + 1) * self.bin
+        shell = np.pi * (edges[1:] ** 2 - edges[:-1] ** 2) if self.s.dim == 2 else 2 * self.bin * np.ones(self.nbins)
+        ideal = nd * self.s.N * (self.s.N - 1) / 2.0 * shell / self.s.vol
+        return h / np.maximum(ideal, 1e-300)
+
+    def __call__(self, s):
+        s.engine.paircorr_measure(self.id)
+
+
+class Winding:                      # `#TODO Superfluid Fraction` (src/measurement.jl:126), in the style of Energy
+    """winding number per measurement: .W2 (chain-mean of W^2 per measurement), .series(chain), .superfluid_fraction()"""
+
+    def __init__(self, s, n=20_000):
+        self.s, self.n = s, n
+        self.id = s.engine.winding_create(n)
+
+    @property
+    def W2(self):
+        return self.s.engine.winding_read(self.id, -1)[0]
+
+    def series(self, chain=0):
+        return self.s.engine.winding_read(self.id, chain)[0]
+
+    def superfluid_fraction(self):
+        """rho_s / rho = <W^2> (2L)^2 / (2 dim lambda beta N)  (Pollock & Ceperley, PRB 36, 8343)"""
+        w2 = self.W2
+        return float(np.mean(w2)) * (2 * self.s.L) ** 2 / (2 * self.s.dim * self.s.lam * self.s.beta * self.s.N) if len(w2) else float("nan")
+
+    def __call__(self, s):
+        return s.engine.winding_now()
+
+
 class System:                       # src/system.jl:93-168
     def __init__(self, potential, dV="zero", dim=2, M=100, N=2, mu=0.0, L=4.0, T=1.0, lam=1.0, interactions=False, propint=None,
                  g=0.0, r_a=0.0, length_measurement_cycle=10, measure_scheme="c", chains=None, seed=None, compat=_L.COMPAT_ALL,
@@ -330,8 +389,10 @@ def run_b(s, n, updates, Zmeasurements=()):
     """run!(s, n, updates; Zmeasurements) -- src/simulation.jl:29-42, on every chain."""
     en = [m.id for m in Zmeasurements if isinstance(m, Energy)]
     de = [m.id for m in Zmeasurements if isinstance(m, Density)]
+    pc = [m.id for m in Zmeasurements if isinstance(m, PairCorrelation)]
+    wi = [m.id for m in Zmeasurements if isinstance(m, Winding)]
     sched = _L.SCHED_SWEEP if s.schedule == "sweep" else _L.SCHED_FAITHFUL
-    return s.engine.run(n, [(every, u.id) for every, u in updates], energies=en, densities=de, sched=sched)
+    return s.engine.run(n, [(every, u.id) for every, u in updates], energies=en, densities=de, sched=sched, paircorrs=pc, windings=wi)
 
 
 def apply_b(s, f):

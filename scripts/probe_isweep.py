@@ -15,7 +15,7 @@ print(f"create {time.time() - t0:.2f}s  a={e.a} nbins={e.nbins}", flush=True)
 e.set_option(L.OPT_ISWEEP, isw)
 kind = {"com": L.UPD_SINGLE_COM, "reshape": L.UPD_RESHAPE_LINEAR, "swap": L.UPD_RESHAPE_SWAP, "pcom": L.UPD_POLYMER_COM}
 ups = [(every, e.update_create(kind[k], v0)) for k, every, v0 in wl["updates"] if upds is None or k in upds]
-for rep in range(3):
+for rep in range(4):
     t0 = time.time()
     st = e.run(iters, ups, sched=L.SCHED_SWEEP)
     print(f"run {rep}: {time.time() - t0:.3f}s kernel {st['kernel_ms']:.2f} ms, {st['bead_moves']} bead moves -> {st['bead_moves'] / st['kernel_ms'] * 1e3:.3e}/s, launches {st['launches']}", flush=True)

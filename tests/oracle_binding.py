@@ -89,6 +89,9 @@ def lib():
             "ora_energy_read": (i64, [vp, f64p, f64p, i64]), "ora_energy_now": (None, [vp, f64p, f64p, f64p]),
             "ora_density_create": (vp, [vp, i64]), "ora_density_destroy": (None, [vp]),
             "ora_density_measure": (None, [vp, vp]), "ora_density_read": (i64, [vp, f64p, f64p]),
+            "ora_paircorr_create": (vp, [vp, i64, d]), "ora_paircorr_destroy": (None, [vp]),
+            "ora_paircorr_measure": (None, [vp, vp]), "ora_paircorr_read": (i64, [vp, f64p, f64p]),
+            "ora_winding_now": (None, [vp, f64p]),
             "ora_run": (C.c_int, [vp, i64, C.POINTER(vp), i64p, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.c_int]),
         }
         for name, (res, args) in sig.items():
@@ -176,6 +179,32 @@ class Density:
             lib().ora_density_destroy(self.h)
         except Exception:
             pass
+
+
+class PairCorrelation:
+    def __init__(self, system, nbins, rmax):
+        self.nbins = nbins
+        self.h = lib().ora_paircorr_create(system.h, nbins, float(rmax))
+
+    def measure(self, system):
+        lib().ora_paircorr_measure(self.h, system.h)
+
+    def read(self):
+        hist, b = np.zeros(self.nbins), C.c_double()
+        nd = lib().ora_paircorr_read(self.h, _p(hist), C.byref(b))
+        return hist, nd, b.value
+
+    def __del__(self):
+        try:
+            lib().ora_paircorr_destroy(self.h)
+        except Exception:
+            pass
+
+
+def winding_now(system):
+    W = np.zeros(system.dim)
+    lib().ora_winding_now(system.h, _p(W))
+    return W
 
 
 class System:

@@ -279,7 +279,8 @@ def test_c_driver_example_density_srl_lattice(oracle, tmp_path, sched):
     info = {words[i]: float(words[i + 1]) for i in range(0, len(words), 2)}
     dens = np.fromfile(out).reshape(500, 500, order="F")
     Lb, M, N, T = 8.0, 200, 20, 0.2
-    assert info["a"] == 0.0 and info["N_MC"] >= n * times and info["ndata"] == info["N_MC"] * M and dens.sum() == info["ndata"] * N
+    # (the histogram drops bin 0 of either axis as shipped, compat B5 / measurement.jl:48-50, so its sum is a little below ndata * N)
+    assert info["a"] == 0.0 and info["N_MC"] >= n * times and info["ndata"] == info["N_MC"] * M and 0.9 * info["ndata"] * N < dens.sum() <= info["ndata"] * N
     # the same run on the oracle: table from the same host code, r_a as pimc_create derived it
     lib = L.load()
     tab = np.zeros((600, 600), order="F")
@@ -301,3 +302,33 @@ def test_c_driver_example_density_srl_lattice(oracle, tmp_path, sched):
         s.run(n, ups, densities=[de], sched=osched)
     assert s.scalars()["N_MC"] == info["N_MC"]
     assert np.array_equal(de.read()[0], dens)
+
+
+@pytest.mark.gpu
+def test_library_communicator_single_rank():
+    """pimc_comm_* with one rank (NCCL bound at run time): the global read-outs -- chain-mean Energy reduced per block on the side stream,
+    density counters and ndata all-reduced at read-out -- equal the local ones; per-chain series stay local.  (The 2-rank run is
+    scripts/comm_2gpu.py, executed with gpurun --gpus 2; the world-size-2 host logic is covered on CPU by tests/test_multi_rank_cpu.py.)"""
+    import pimc_jl_b200 as pj
+    from pimc_jl_b200 import _lib as L, engine
+    kw = dict(dim=2, M=16, N=5, T=1.0, lam=0.5, Ncycle=2, seed=5, chains=6, L_=4.0)
+    out = []
+    for with_comm in (False, True):
+        e = pj.Engine(pj.make_potential("harmonic", "identity"), device=0, **kw)
+        if with_comm:
+            e.comm_init(1, 0, engine.comm_unique_id())
+            info = e.comm_info()
+            assert info["nranks"] == 1 and info["rank"] == 0 and info["chains_total"] == 6 and info["nccl_version"] > 20000
+        ups = [(1, e.update_create(L.UPD_SINGLE_COM, 1.0)), (1, e.update_create(L.UPD_RESHAPE_LINEAR, 6))]
+        en, de = e.energy_create(64), e.density_create(16)
+        for _ in range(3):   # three blocks: each is reduced at the end of its pimc_run
+            e.run(10, ups, energies=[en], densities=[de], sched=L.SCHED_SWEEP)
+        E, Ev, n = e.energy_read(en, -1)
+        per_chain = np.stack([e.energy_read(en, c)[0] for c in range(6)])
+        d, nd, _ = e.density_read(de, 16)
+        blk = e.energy_read_range(en, 5, 5)
+        out.append((E, Ev, n, per_chain, d, nd, blk[0]))
+    (E0, Ev0, n0, pc0, d0, nd0, b0), (E1, Ev1, n1, pc1, d1, nd1, b1) = out
+    assert n0 == n1 == 15 and np.array_equal(pc0, pc1) and np.array_equal(d0, d1) and nd0 == nd1
+    assert np.allclose(E0, E1, rtol=1e-14, atol=0) and np.allclose(Ev0, Ev1, rtol=1e-14, atol=0) and np.allclose(b0, b1, rtol=1e-14, atol=0)
+    assert np.allclose(E1, pc1.mean(axis=0), rtol=1e-13)

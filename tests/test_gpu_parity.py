@@ -697,3 +697,65 @@ def test_golden_vectors():
         assert np.array_equal(dens, gold[key]) and nd == M
     V, _ = eng.potential_eval(gold["lat_pts"], pj.make_potential(**lat))
     assert close(V, gold["lat_V"], 1e-12, 1e-13)
+
+
+@pytest.mark.parametrize("cfg,nb,rmax", [
+    (dict(pot="harmonic", dim=2, M=20, N=13, L=3.0, T=0.6, lam=0.5, Ncycle=3), 40, 3.0),
+    (dict(pot="zero", dim=2, M=33, N=70, L=4.0, T=1.0, lam=1.0, Ncycle=2), 9000, 5.0),     # > 8192 bins: global-atomic path; odd M: ragged last tile
+    (dict(pot="sin2", dim=1, M=16, N=9, L=2.0, T=1.0, lam=0.5, Ncycle=4), 16, 1.5),
+], ids=["trap2d", "free2d-many-bins", "1d"])
+def test_paircorr_and_winding_vs_oracle(oracle, cfg, nb, rmax):
+    """the estimators the reference lists as TODO (measurement.jl:125-127): g(r) pair counts integer for integer and winding numbers against
+    the oracle's definitions, (i) as functors on the current configuration, (ii) inside run! with swaps (pimc_run_ex: same cadence as
+    Energy / Density, which are measured alongside and must not change), (iii) on a hand-made winding worldline."""
+    ob = oracle
+    chains = 3
+    e, os_ = make_pair(ob, cfg, chains=chains, seed=77)
+    spec = [(1, L.UPD_SINGLE_COM, 0.5), (1, L.UPD_RESHAPE_LINEAR, 6), (1, L.UPD_RESHAPE_SWAP, 6)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    pc, wi, en = e.paircorr_create(nb, rmax), e.winding_create(64), e.energy_create(64)
+    opc = [ob.PairCorrelation(s, nb, rmax) for s in os_]
+    oen = [ob.Energy(64) for _ in os_]
+    # (i) functor calls
+    e.paircorr_measure(pc)
+    for g, s in zip(opc, os_):
+        g.measure(s)
+    h, nd, b = e.paircorr_read(pc, nb)
+    assert np.array_equal(h, sum(g.read()[0] for g in opc)) and nd == chains * cfg["M"] and b == rmax / nb and h.sum() > 0
+    assert np.allclose(e.winding_now(), np.stack([ob.winding_now(s) for s in os_]), atol=1e-12)
+    # (ii) inside run!, 41 iterations: the cadence counter carries over between the two calls
+    nC = cfg["Ncycle"]
+    for n_it in (23, 18):
+        e.run(n_it, ge, energies=[en], paircorrs=[pc], windings=[wi], sched=L.SCHED_SWEEP)
+    Wo = [[] for _ in os_]
+    for c, (s, ups, g, eo) in enumerate(zip(os_, oo, opc, oen)):
+        done = 0
+        while done < 41:
+            seg = min(nC - s.scalars()["Nctr"], 41 - done)
+            s.run(seg, ups, energies=[eo], sched=ob.SCHED_SWEEP)
+            done += seg
+            if s.scalars()["Nctr"] == 0:
+                g.measure(s)
+                Wo[c].append(ob.winding_now(s))
+    _sync_paths(e, os_)
+    h, nd, _ = e.paircorr_read(pc, nb)
+    nm = 41 // nC
+    assert np.array_equal(h, sum(g.read()[0] for g in opc)) and nd == chains * cfg["M"] * (1 + nm)
+    scale = cfg["dim"] * cfg["N"] / (2 * os_[0].tau)
+    for c in range(chains):
+        Wg, n = e.winding_read(wi, c)
+        assert n == nm and np.allclose(Wg, np.array(Wo[c]), atol=1e-9) and np.array_equal(np.rint(Wg), np.rint(np.array(Wo[c])))
+        E, _, ne = e.energy_read(en, c)
+        assert ne == nm and np.all(np.abs(E - oen[c].read()[0]) <= 1e-12 * scale)
+    W2, n = e.winding_read(wi, -1)
+    assert n == nm and np.allclose(W2, np.mean([(np.array(w) ** 2).sum(axis=1) for w in Wo], axis=0), atol=1e-9)
+    # (iii) one worldline wrapped once around x
+    r, _, _, nxt = e.paths()
+    M, Lb = cfg["M"], cfg["L"]
+    r[1, 2, 0, :] = -Lb + (np.arange(M) + 0.5) * (2 * Lb / M)
+    e.set_paths(r, nxt)
+    os_[1].set_paths(r[1], nxt[1])
+    W = e.winding_now()
+    assert np.allclose(W[1], ob.winding_now(os_[1]), atol=1e-9) and np.rint(W[1, 0]) == 1 + np.rint(Wo[1][-1][0])
+    with pytest.raises(pj.PimcError):
+        e.run(64 * nC, ge, windings=[wi], sched=L.SCHED_SWEEP)   # more samples than the pre-sized series holds: refused like Energy

@@ -448,3 +448,36 @@ def test_swap_weights_against_numpy(oracle):
         lnk = lambda a, b: -sum(distance_py(a[k], b[k], L) ** 2 for k in range(2)) / (4 * (m * s.tau) * lam)
         ref = [math.exp(lnk(r[n1 - 1, :, j0 - 1], r[endp(i) - 1, :, jm]) + lnk(r[i - 1, :, j0 - 1], r[endp(n1) - 1, :, jm])) for i in range(1, N + 1)]
         assert np.allclose(w, ref, rtol=1e-13, atol=0)
+
+
+def test_paircorr_and_winding_estimators_against_numpy(oracle):
+    ob = oracle
+    """the two estimators the reference lists as TODO (measurement.jl:125-127) as the oracle defines them, against direct numpy evaluations:
+    g(r) pair counts (minimum-image distances, all pairs, all slices) and the winding number (an integer; non-zero for a worldline that
+    wraps the box)"""
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=12, N=7, L=2.0, T=0.7, lam=0.5, seed=3)
+    g = ob.PairCorrelation(s, 25, 2.5)
+    g.measure(s)
+    g.measure(s)
+    hist, nd, b = g.read()
+    r = s.paths()[0]                                        # [N][dim][M]
+    ref = np.zeros(25)
+    for m in range(12):
+        for i in range(7):
+            for j in range(i + 1, 7):
+                d = np.abs(r[i, :, m] - r[j, :, m])
+                d = np.minimum(2 * 2.0 - d, d)
+                ib = math.floor(math.sqrt(d[0] * d[0] + d[1] * d[1]) / (2.5 / 25))
+                if ib < 25:
+                    ref[ib] += 1
+    assert nd == 24 and b == 2.5 / 25 and np.array_equal(hist, 2 * ref) and hist.sum() > 0
+    assert np.allclose(ob.winding_now(s), 0.0, atol=1e-12)  # init_world closes every ring inside the box
+    # a worldline that winds once around x: beads advance by 2L / M per slice and wrap
+    M, L_ = 12, 2.0
+    r2 = r.copy()
+    x = -L_ + (np.arange(M) + 0.5) * (2 * L_ / M)
+    r2[3, 0, :] = x
+    r2[3, 1, :] = 0.25
+    s.set_paths(r2, s.paths()[3])
+    W = ob.winding_now(s)
+    assert abs(W[0] - 1.0) < 1e-12 and abs(W[1]) < 1e-12
