@@ -296,11 +296,14 @@ def main():
     # the same order on every rank.
     per = wl["N"] * wl["dim"] * wl["M"]
     halves = []
-    for k in range(2):
-        ck = Cc // 2 + (Cc % 2 if k == 0 else 0)
+    # the two parts are sized to whole waves of the sweep kernel (one CTA per chain, 148 SMs x 4 resident CTAs, 3 beyond M = 128), so
+    # that splitting the batch does not add a partly filled wave
+    wave = 148 * (4 if wl["M"] <= 128 else 3)
+    cA = Cc - Cc // 2 if Cc < 2 * wave else min(Cc - 1, ((Cc // 2 + wave - 1) // wave) * wave)
+    for k, ck in enumerate((cA, Cc - cA)):
         if ck == 0:
             continue
-        ek = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=ck, chain_offset=rank * Cc + k * (Cc - Cc // 2), L_=wl["L"],
+        ek = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=ck, chain_offset=rank * Cc + k * cA, L_=wl["L"],
                        T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
         if args.faithful_impl:
             ek.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)

@@ -97,8 +97,9 @@ int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run k
 #define PIMC_OPT_SWEEP_IMPL 1
 /* PIMC_OPT_FAITHFUL_IMPL: proposals of the reference schedule: 0 warp-cooperative (default), 1 one thread per proposal (A/B, same bits) */
 #define PIMC_OPT_FAITHFUL_IMPL 2
-/* PIMC_OPT_FUSE_ENERGY: 1 (default) evaluates the Energy functor inside the sweep launch for chains whose picked update streamed every
- * worldline anyway; 0 always uses the separate estimator launch (A/B, same values to 1e-12) */
+/* PIMC_OPT_FUSE_ENERGY: 1 evaluates the Energy functor inside the sweep launch for chains whose centre-of-mass sweep streams every worldline
+ * anyway; 0 (default) uses the estimator launch.  Same values to 1e-12.  Measured on C2 (profiles/r02_summary.md): the fused sums push the
+ * HBM-bound centre-of-mass sweep over its issue budget and cost more than the TMA-fed estimator pass they save. */
 #define PIMC_OPT_FUSE_ENERGY 3
 /* PIMC_OPT_ISWEEP: sweep schedule of interacting worldlines (hard core; pair action not counted in ReshapeLinear / centre-of-mass moves =
  * the reference as shipped): 1 (default) adaptive -- optimistic-parallel per-iteration kernels, falling back to the sequential sweep inside

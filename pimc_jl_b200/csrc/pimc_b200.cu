@@ -318,6 +318,28 @@ static void pot_to_dev(const pimc_potential *p, PotDev *d)
     d->kind = p->kind; d->dv_kind = p->dv_kind; d->k = p->k; d->depth = p->depth; d->scale = p->scale; d->sgn = p->sgn;
     d->nang = p->nang; d->helical = p->helical;
     for (int i = 0; i < p->nang && i < PIMC_MAX_ANGLES; ++i) { d->ang[i] = p->ang[i]; d->sn[i] = sin(p->ang[i]); d->cs[i] = cos(p->ang[i]); }
+    // commensurate projections?  base = (smallest non-zero |projection|) / q for the smallest q in 1..8 that makes every projection an integer
+    // multiple <= PIMC_FAST_NMAX of it (to 1e-12); PIMC_NO_FAST_LATTICE=1 keeps the one-sincos-per-beam evaluation (A/B)
+    d->fast = 0;
+    if (p->kind == PIMC_POT_LATTICE && p->nang > 0 && !getenv("PIMC_NO_FAST_LATTICE")) {
+        auto fit = [&](const double *v, signed char *m, double *base, int *nmax) {
+            double mn = 0.0;
+            for (int i = 0; i < p->nang; ++i) { const double a = fabs(v[i]); if (a > 1e-12 && (mn == 0.0 || a < mn)) mn = a; }
+            if (mn == 0.0) { for (int i = 0; i < p->nang; ++i) m[i] = 0; *base = 0.0; *nmax = 0; return true; }
+            for (int q = 1; q <= 8; ++q) {
+                const double b = mn / q; bool ok = true; int mx = 0;
+                for (int i = 0; i < p->nang && ok; ++i) {
+                    const double r = v[i] / b, n = nearbyint(r);
+                    if (fabs(r - n) > 1e-12 * (fabs(r) + 1.0) || fabs(n) > PIMC_FAST_NMAX) ok = false;
+                    else { m[i] = (signed char)n; if (abs((int)n) > mx) mx = abs((int)n); }
+                }
+                if (ok) { *base = b; *nmax = mx; return true; }
+            }
+            return false;
+        };
+        double bx, by; int nx, ny;
+        if (fit(d->sn, d->mx, &bx, &nx) && fit(d->cs, d->my, &by, &ny)) { d->fast = 1; d->bx = bx * p->scale; d->by = by * p->scale; d->nmx = nx; d->nmy = ny; }
+    }
 }
 static int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 
@@ -514,7 +536,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 1; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr; h->isw_backoff = 0; h->isw_replay_frac = 0.0;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 0; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr; h->isw_backoff = 0; h->isw_replay_frac = 0.0;
     memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
     h->npc = h->nwi = 0; memset(h->pc_ndata, 0, sizeof h->pc_ndata); memset(h->wi_count, 0, sizeof h->wi_count);

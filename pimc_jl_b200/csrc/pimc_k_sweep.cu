@@ -1,4 +1,5 @@
 // pimc_k_sweep.cu -- per-iteration throughput kernels of the SWEEP schedule for independent worldlines (k_sweep, k_swap_iter, k_measure).
+#include <cstdlib>
 #include "pimc_sweep.cuh"
 
 typedef void (*sweep_fn)(const DevSys, const DevTables *, const Sweep2Params);
@@ -38,6 +39,15 @@ cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, cons
 {
     const int KM = (S.M + 31) / 32, pk = S.pot.kind;
     meas_fn k = pk == PIMC_POT_ZERO ? pick_meas<PIMC_POT_ZERO>(KM) : (pk == PIMC_POT_HARMONIC ? pick_meas<PIMC_POT_HARMONIC>(KM) : pick_meas<PIMC_POT_LATTICE>(KM));
-    k<<<grid, 256, 0, st>>>(S, dT, P, mdone);
+    // Energy pass fed by TMA (even M, register-resident variants): 2 mbarriers + 2 stages of dim rows per warp
+    MeasParams Q = P;
+    Q.tma = (P.nen > 0 && KM <= 8 && (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr) ? 1 : 0;
+    const size_t smem = Q.tma ? (size_t)8 * 16 + (size_t)8 * 2 * S.dim * S.M * sizeof(double) : 0;
+    if (smem > 48 * 1024) {
+        static meas_fn configured[16]; static int nconf = 0;
+        bool seen = false; for (int i = 0; i < nconf; ++i) seen |= configured[i] == k;
+        if (!seen) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; if (nconf < 16) configured[nconf++] = k; }
+    }
+    k<<<grid, 256, smem, st>>>(S, dT, Q, mdone);
     return cudaGetLastError();
 }

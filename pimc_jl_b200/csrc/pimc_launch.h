@@ -19,7 +19,7 @@ struct SweepParams {
 // measurement_Z_sector (measurement.jl:1-17) for every chain at one cadence hit.  ord = 0-based ordinal of this measurement within
 // the current run; Energy object e stores it at index en_k0[e] + ord (its OWN count, like the reference's findfirst(ismissing, ...),
 // measurement.jl:119-120).
-struct MeasParams { int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC_MAXE]; int nde; int de_id[PIMC_MAXD]; long long ord; };
+struct MeasParams { int tma; int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC_MAXE]; int nde; int de_id[PIMC_MAXD]; long long ord; };
 
 // The update descriptors travel by value in the kernel parameters (constant bank): no dependent global loads of T->upd[...]
 // on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).

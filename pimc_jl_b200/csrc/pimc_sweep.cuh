@@ -13,6 +13,13 @@
 
 // staged rows per batch: runtime (Sweep2Params::cap), sized by the host from the shared-memory budget
 #define SWEEP_TBMAX 256   // tasks per batch
+#ifndef SWEEP_UNROLL_A
+#define SWEEP_UNROLL_A 1  // rows per thread in flight in phase A (Gaussians); A/B knob, see profiles/
+#endif
+#ifndef SWEEP_UNROLL_C
+#define SWEEP_UNROLL_C 1  // rows per thread in flight in phase C (teleport, potential)
+#endif
+static constexpr int kSweepUnrollA = SWEEP_UNROLL_A, kSweepUnrollC = SWEEP_UNROLL_C;
 #ifdef EXP_TIMING
 #define TICK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
 #else
@@ -133,6 +140,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
 #ifdef EXP_SKIP_A
             for (int s = tid; s < B; s += SWEEP_THREADS) { const int q = map[s], row = s - t_off[q], mq = t_m[q]; if (row >= 1 && row < mq) { xs[s] = 0.0; ys[s] = 0.0; } }
 #else
+#pragma unroll kSweepUnrollA
             for (int s = tid; s < B; s += SWEEP_THREADS) {
                 const int q = map[s], row = s - t_off[q], mq = t_m[q];
                 if (row >= 1 && row < mq) {
@@ -184,6 +192,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
             TICK(2);
             // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
 #ifndef EXP_SKIP_C
+#pragma unroll kSweepUnrollC
             for (int s = tid; s < B; s += SWEEP_THREADS) {
                 double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
                 xs[s] = x;
@@ -828,18 +837,93 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
         *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
     }
 }
+// TMA-fed variant (even M): every warp keeps the NEXT worldline's rows in flight (cp.async.bulk into its own two-stage shared-memory ring,
+// completion on an mbarrier) while it reduces the current one -- bytes in flight without registers; the permutation entry of the next
+// worldline is fetched one step ahead.  Same sums as d_energy_block_reg.
+template <int POT, int KM>
+__device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, double *red, double *E, double *Ev, char *dyn)
+{
+    const int M = S.M, N = S.N, dim = S.dim, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double twoL = 2 * S.L;
+    const double *rc = S.r + (size_t)c * N * dim * M;
+    const int *nextc = S.next + (size_t)c * N;
+    const int dvk = S.pot.dv_kind;
+    const uint32_t row_bytes = (uint32_t)M * 8u;
+    unsigned long long *mbar = (unsigned long long *)dyn + warp * 2;
+    double *stage0 = (double *)(dyn + nw * 16) + (size_t)warp * 2 * dim * M;
+    const uint32_t bar_u = d_smem_u32(mbar), stage_u = d_smem_u32(stage0);
+    auto issue = [&](int n_, int stg) {
+        if (lane == 0) {
+            const uint32_t b = bar_u + 8u * stg;
+            d_mbar_expect_tx(b, (uint32_t)dim * row_bytes);
+            d_bulk_g2s(stage_u + (uint32_t)stg * dim * row_bytes, rc + (size_t)(n_ * dim) * M, (uint32_t)dim * row_bytes, b);
+        }
+    };
+    if (lane == 0) { d_mbar_init(bar_u, 1); d_mbar_init(bar_u + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    double link = 0.0, pot = 0.0, vkin = 0.0;
+    int it = 0;
+    if (warp < N) issue(warp, 0);
+    int nx = warp < N ? nextc[warp] : 0;
+    for (int n = warp; n < N; n += nw) {
+        const int stg = it & 1; const uint32_t par = (uint32_t)(it >> 1) & 1u; ++it;
+        __syncwarp();                                   // every lane is done with the other stage
+        if (n + nw < N) issue(n + nw, stg ^ 1);
+        const int nx_next = n + nw < N ? nextc[n + nw] : 0;
+        // first bead of the next particle of the cycle (the worldline's own bead 0 when it is closed on itself)
+        double x0n = 0.0, y0n = 0.0;
+        if (nx != n) { const double *qx = rc + (size_t)(nx * dim) * M; x0n = qx[0]; y0n = dim > 1 ? qx[M] : 0.0; }
+        d_mbar_wait(bar_u + 8u * stg, par);
+        const double *sx = stage0 + (size_t)stg * dim * M;
+        double x[KM], y[KM];
+#pragma unroll
+        for (int k = 0; k < KM; ++k) { const int j = lane + 32 * k; x[k] = j < M ? sx[j] : 0.0; y[k] = (dim > 1 && j < M) ? sx[M + j] : 0.0; }
+        if (nx == n) { x0n = __shfl_sync(0xffffffffu, x[0], 0); y0n = __shfl_sync(0xffffffffu, y[0], 0); }
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+            const int j = lane + 32 * k;
+            double bx = __shfl_down_sync(0xffffffffu, x[k], 1), by = __shfl_down_sync(0xffffffffu, y[k], 1);
+            const double nbx = __shfl_sync(0xffffffffu, x[(k + 1 < KM) ? k + 1 : k], 0), nby = __shfl_sync(0xffffffffu, y[(k + 1 < KM) ? k + 1 : k], 0);
+            if (lane == 31) { bx = nbx; by = nby; }
+            if (j == M - 1) { bx = x0n; by = y0n; }
+            if (j < M) {
+                const double ax = x[k], ay = y[k];
+                double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
+                double d2 = dx * dx;
+                if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
+                link += d2;
+                if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
+                if (dvk == PIMC_DV_IDENTITY) { double q = ax * ax; if (dim > 1) q = q + ay * ay; vkin += q; }   // r . dV(r), measurement.jl:105
+                else if (dvk != PIMC_DV_ZERO) vkin += d_rdv(S.pot, ax, ay, dim);
+            }
+        }
+        nx = nx_next;
+    }
+    link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
+    __syncthreads();
+    if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        link = 0.0; pot = 0.0; vkin = 0.0;
+        for (int i = 0; i < nw; ++i) { link += red[i]; pot += red[32 + i]; vkin += red[64 + i]; }
+        *E = (double)(S.dim * S.N) / (2 * S.tau) - 1 / (4 * S.lambda * (S.tau * S.tau) * S.M) * link + 1.0 / (2 * S.M) * pot;
+        *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
+    }
+}
 template <int POT, int KM>
 __global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
                                                     const unsigned char *__restrict__ mdone)
 {
     __shared__ double red[96];
+    extern __shared__ __align__(16) char dyn_meas[];   // TMA ring of the Energy pass (P.tma), else unused
     const int c = blockIdx.x;
     const bool en_done = mdone && mdone[c];     // Energy of this chain was evaluated inside the sweep launch (fused)
     for (int e = 0; e < P.nen && !en_done; ++e) {
         const EnDev &En = T->en[P.en_id[e]];
         const long long k = P.en_k0[e] + P.ord; // the object's own count (measurement.jl:119-120)
         double E, Ev;
-        if (KM > 0) d_energy_block_reg<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev);
+        if (KM > 0 && P.tma && e == 0) d_energy_block_tma<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev, dyn_meas);
+        else if (KM > 0) d_energy_block_reg<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev);
         else d_energy_block_fast<POT>(S, c, red, &E, &Ev);
         if (threadIdx.x == 0) {
             if (k < En.cap) { En.E[(size_t)k * S.C + c] = E; En.Ev[(size_t)k * S.C + c] = Ev; }

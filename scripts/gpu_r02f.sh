@@ -1,0 +1,18 @@
+#!/bin/bash
+tag=r02f; out=gpurun_out; mkdir -p $out
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -25 > $out/${tag}_tests.log; tail -4 $out/${tag}_tests.log
+b() { name=$1; shift; timeout 600 python bench.py --no-cpu-baseline "$@" > $out/${tag}_bench_$name.json 2> $out/${tag}_bench_$name.err; python scripts/show_bench.py $out/${tag}_bench_$name.json; python - $out/${tag}_bench_$name.json <<'PY'
+import json,sys
+try:
+    j=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); f=j["roofline"]["by_family"]
+    print("   families:", {k: ("%.3e" % v["bead_moves_per_s"] if "bead_moves_per_s" in v else "%.1f us" % (1e3*v["launch_ms_marginal"])) for k,v in f.items()})
+except Exception as ex: print("   no families", ex)
+PY
+tail -2 $out/${tag}_bench_$name.err; }
+b c2
+PIMC_B200_SO=$PWD/pimc_jl_b200/libpimc_b200_uc2.so b c2_uc2 --steps 2
+PIMC_B200_SO=$PWD/pimc_jl_b200/libpimc_b200_ua2c2.so b c2_ua2c2 --steps 2
+b c4 --workload c4 --steps 3
+PIMC_NO_FAST_LATTICE=1 b c4_slow --workload c4 --steps 3
+b c3i --workload c3i --sched sweep --steps 3
+b c4i --workload c4i --sched sweep --steps 3

@@ -533,7 +533,7 @@ def test_baseline_shapes_batched_kernels_vs_oracle(oracle, name):
 
 def test_c2_default_dispatch_at_bench_scale_vs_oracle(oracle):
     """C2 with 128 chains = 2^20 beads: the DEFAULT dispatch (PIMC_OPT_SWEEP_IMPL = 0) picks the per-iteration kernels exactly as in bench.py;
-    Energy fused into the sweep launch (default) and the separate estimator launch give the oracle's values; spot-checked chains vs oracle."""
+    Energy fused into the sweep launch (option) and the separate estimator launch (default) give the oracle's values; spot-checked chains vs oracle."""
     ob = oracle
     cfg, spec, measure, n_it = BASELINE_SHAPES["C2"]
     out = []
@@ -737,7 +737,7 @@ def test_paircorr_and_winding_vs_oracle(oracle, cfg, nb, rmax):
             if s.scalars()["Nctr"] == 0:
                 g.measure(s)
                 Wo[c].append(ob.winding_now(s))
-    _sync_paths(e, os_)
+    _sync_paths(e, os_, exact_v=cfg["pot"] in ("zero", "harmonic"))
     h, nd, _ = e.paircorr_read(pc, nb)
     nm = 41 // nC
     assert np.array_equal(h, sum(g.read()[0] for g in opc)) and nd == chains * cfg["M"] * (1 + nm)
