@@ -179,7 +179,7 @@ def main():
               "schedule": "sweep (every worldline of a chain proposes per iteration)" if not faithful else "reference (one proposal per chain and iteration)",
               "iters_per_step": args.iters, "measure": f"{wl['measure'].capitalize()} every {wl['Ncycle']} iterations",
               "interactions": bool(wl.get("interactions")),
-              "e2e_pipeline": "two Systems of chains/2 on two streams / host threads: copies of one half overlap the moves of the other",
+              "e2e_pipeline": "double-buffered: two Systems of the full batch on two streams / host threads take the steps alternately, the copies of one overlap the moves of the other",
               "l2": f"state ({wl['chains']} chains x {wl['N'] * wl['M'] * 24 // 1024} KiB) larger than L2"}
 
     if args.impl == "reference":
@@ -290,21 +290,15 @@ def main():
     value = total_bm / (ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----
-    # The public API as a user with pinned host buffers drives it: the batch is held as TWO Systems of chains/2 (two handles, two streams,
-    # two host threads -- the library is synchronous per handle), so the H2D / D2H copies of one half overlap the moves of the other.  Runs
-    # and collective read-outs take turns in a fixed order (A, B, A, B, ...), which keeps the NCCL operations of the two communicators in
-    # the same order on every rank.
+    # The public API as a user with pinned host buffers drives it, double-buffered: TWO Systems of the full batch (two handles, two streams, two
+    # host threads -- the library is synchronous per handle) take the steps alternately, so the H2D / D2H copies of one batch overlap the moves
+    # of the other.  Every step still uploads its batch, runs it, reads the estimator block and downloads the batch.  Runs and collective
+    # read-outs take turns in step order, which keeps the NCCL operations of the two communicators in the same order on every rank.
     per = wl["N"] * wl["dim"] * wl["M"]
     halves = []
-    # the two parts are sized to whole waves of the sweep kernel (one CTA per chain, 148 SMs x 4 resident CTAs, 3 beyond M = 128), so
-    # that splitting the batch does not add a partly filled wave
-    wave = 148 * (4 if wl["M"] <= 128 else 3)
-    cA = Cc - Cc // 2 if Cc < 2 * wave else min(Cc - 1, ((Cc // 2 + wave - 1) // wave) * wave)
-    for k, ck in enumerate((cA, Cc - cA)):
-        if ck == 0:
-            continue
-        ek = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=ck, chain_offset=rank * Cc + k * cA, L_=wl["L"],
-                       T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1, device=local_rank, **interaction_args(wl))
+    for k in range(2 if args.steps > 1 else 1):
+        ek = pj.Engine(pj.make_potential(**wl["pot"]), dim=wl["dim"], M=wl["M"], N=wl["N"], chains=Cc, chain_offset=rank * Cc, L_=wl["L"],
+                       T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1 + 1000 * (k + 1), device=local_rank, **interaction_args(wl))
         if args.faithful_impl:
             ek.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
         sk = torch.cuda.Stream()
@@ -314,7 +308,7 @@ def main():
         uk = [(every, ek.update_create(kind[kk], v0)) for kk, every, v0 in wl["updates"]]
         ok = ek.density_create(wl["nbins"]) if use_density else ek.energy_create(nmeas_total)
         ek.run(args.therm, uk, sched=SCHED)
-        hk = torch.empty((ck, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
+        hk = torch.empty((Cc, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
         ek.get_r_into(hk)
         halves.append(dict(e=ek, ups=uk, obj=ok, host=hk, stream=sk, mkw=dict(densities=[ok]) if use_density else dict(energies=[ok]), seen=0, bm=0, blk=None))
     turn = [0]
@@ -325,10 +319,10 @@ def main():
         try:
             torch.cuda.set_device(local_rank)
             hf = halves[k]
-            for s_ in range(args.steps):
+            for s_ in range(k, args.steps, len(halves)):               # this buffer's steps
                 hf["e"].set_paths(hf["host"])                          # H2D: this step's worldlines (pinned host memory)
                 with cv:
-                    cv.wait_for(lambda: turn[0] == s_ * len(halves) + k)
+                    cv.wait_for(lambda: turn[0] >= s_)
                 st_ = hf["e"].run(args.iters, hf["ups"], sched=SCHED, **hf["mkw"])
                 hf["bm"] += st_["bead_moves"]
                 hf["blk"], hf["seen"] = block_read(hf["seen"], hf["e"], hf["obj"])   # the step's result: estimator block, D2H (global over the GPUs)

@@ -337,8 +337,21 @@ static void pot_to_dev(const pimc_potential *p, PotDev *d)
             }
             return false;
         };
-        double bx, by; int nx, ny;
-        if (fit(d->sn, d->mx, &bx, &nx) && fit(d->cs, d->my, &by, &ny)) { d->fast = 1; d->bx = bx * p->scale; d->by = by * p->scale; d->nmx = nx; d->nmy = ny; }
+        double bx, by; int nx, ny; signed char mx[PIMC_MAX_ANGLES], my[PIMC_MAX_ANGLES];
+        if (!p->helical && fit(d->sn, mx, &bx, &nx) && fit(d->cs, my, &by, &ny)) {
+            // cos(ma tx + mb ty) = cos|ma| cos|mb| - sgn(ma) sgn(mb) sin|ma| sin|mb| ;  sin(...) = sgn(ma) sin|ma| cos|mb| + sgn(mb) cos|ma| sin|mb|
+            int wcc[9][9] = {}, wss[9][9] = {}, wsc[9][9] = {}, wcs[9][9] = {};
+            for (int i = 0; i < p->nang; ++i) {
+                const int a = abs(mx[i]), b = abs(my[i]), sa = (mx[i] > 0) - (mx[i] < 0), sb = (my[i] > 0) - (my[i] < 0);
+                wcc[a][b] += 1; wss[a][b] -= sa * sb; wsc[a][b] += sa; wcs[a][b] += sb;
+            }
+            bool sym = true;
+            for (int a = 0; a < 9; ++a) for (int b = 0; b < 9; ++b) sym = sym && wss[a][b] == 0 && wsc[a][b] == 0 && wcs[a][b] == 0;
+            if (sym) {
+                d->fast = 1; d->bx = bx * p->scale; d->by = by * p->scale; d->nmx = nx; d->nmy = ny;
+                for (int a = 0; a < 9; ++a) for (int b = 0; b < 9; ++b) d->wcc[a * 9 + b] = (double)wcc[a][b];
+            }
+        }
     }
 }
 static int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }

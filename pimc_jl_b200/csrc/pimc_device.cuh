@@ -16,12 +16,13 @@ struct PotDev {
     double k, depth, scale, sgn;
     int nang, helical;
     double ang[PIMC_MAX_ANGLES], sn[PIMC_MAX_ANGLES], cs[PIMC_MAX_ANGLES]; // sin/cos of the beam angles, host-evaluated
-    // commensurate beam sets (l25 = the 3-4-5 angles, cubic, ...): every x-projection sin(a_i) is an integer multiple mx[i] of one base
-    // value and every y-projection cos(a_i) a multiple my[i] of another, so all nang phases follow from TWO sincos by the multiple-angle
-    // recurrence and the addition theorem (host-detected in pot_to_dev; fast = 0 keeps one sincos per beam)
+    // commensurate, inversion-symmetric beam sets (l25 = the 3-4-5 angles, l65, cubic: all the sets of examples/tools/potentialtools.jl): every
+    // x-projection sin(a_i) is an integer multiple of one base value, every y-projection cos(a_i) of another, and the beams come in (a, -a, pi - a)
+    // families, so the sine sum vanishes identically and the cosine sum is  C = sum_{a,b} wcc[a][b] cos(a tx) cos(b ty):  TWO sincos, two Chebyshev
+    // recurrences and one small static double sum instead of one sincos per beam (host-detected in pot_to_dev; fast = 0 keeps the general form)
     int fast, nmx, nmy;
     double bx, by;                      // base projection * scale
-    signed char mx[PIMC_MAX_ANGLES], my[PIMC_MAX_ANGLES];
+    double wcc[(8 + 1) * (8 + 1)];      // [a][b], a <= nmx, b <= nmy
 };
 #define PIMC_FAST_NMAX 8
 
@@ -124,27 +125,26 @@ __device__ __forceinline__ double d_pot(const PotDev &p, double x, double y, int
         double s = 0.0, c = 0.0;
         if (dim < 2) y = 0.0;
         if (p.fast) {
-            double SX[PIMC_FAST_NMAX + 1], CX[PIMC_FAST_NMAX + 1], SY[PIMC_FAST_NMAX + 1], CY[PIMC_FAST_NMAX + 1];
             const double tx = x * p.bx, ty = y * p.by;
             double s1, c1, s2, c2;
             pimc_sincos2pi(tx - floor(tx), &s1, &c1);
             pimc_sincos2pi(ty - floor(ty), &s2, &c2);
-            SX[0] = 0.0; CX[0] = 1.0; SY[0] = 0.0; CY[0] = 1.0;
+            double CX[PIMC_FAST_NMAX + 1], CY[PIMC_FAST_NMAX + 1];          // static indices only: registers
+            CX[0] = 1.0; CX[1] = c1; CY[0] = 1.0; CY[1] = c2;
+            const double tcx = 2 * c1, tcy = 2 * c2;
 #pragma unroll
-            for (int n = 1; n <= PIMC_FAST_NMAX; ++n) {
-                if (n <= p.nmx) { SX[n] = SX[n - 1] * c1 + CX[n - 1] * s1; CX[n] = CX[n - 1] * c1 - SX[n - 1] * s1; }
-                if (n <= p.nmy) { SY[n] = SY[n - 1] * c2 + CY[n - 1] * s2; CY[n] = CY[n - 1] * c2 - SY[n - 1] * s2; }
+            for (int n = 2; n <= PIMC_FAST_NMAX; ++n) { CX[n] = tcx * CX[n - 1] - CX[n - 2]; CY[n] = tcy * CY[n - 1] - CY[n - 2]; }   // cos(n t)
+            double cs = 0.0;
+#pragma unroll
+            for (int a = 0; a <= PIMC_FAST_NMAX; ++a) {
+                if (a > p.nmx) break;                                       // launch-uniform
+                double row = 0.0;
+#pragma unroll
+                for (int b = 0; b <= PIMC_FAST_NMAX; ++b) { if (b > p.nmy) break; row += p.wcc[a * (PIMC_FAST_NMAX + 1) + b] * CY[b]; }
+                cs += row * CX[a];
             }
-            for (int i = 0; i < p.nang; ++i) {
-                const int ma = p.mx[i], mb = p.my[i];
-                const double sa = ma < 0 ? -SX[-ma] : SX[ma], ca = CX[ma < 0 ? -ma : ma];
-                const double sb = mb < 0 ? -SY[-mb] : SY[mb], cb = CY[mb < 0 ? -mb : mb];
-                double si = sa * cb + ca * sb, ci = ca * cb - sa * sb;
-                if (p.helical) { const double sn = p.sn[i], cs = p.cs[i], s0 = si; si = s0 * cs + ci * sn; ci = ci * cs - s0 * sn; }   // + angle_i
-                s += si; c += ci;
-            }
-            s /= p.nang; c /= p.nang;
-            return (p.sgn * p.depth) * (s * s + c * c);
+            cs /= p.nang;
+            return (p.sgn * p.depth) * (cs * cs);
         }
         for (int i = 0; i < p.nang; ++i) {
             const double t = (x * p.sn[i] + y * p.cs[i]) * p.scale;

@@ -179,28 +179,29 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
                 // software pipelined by hand: next step's alpha and xi*sigma are fetched before this step's store, so that only
                 // DMUL -> DADD -> DADD sits on the serial path (the compiler cannot hoist the loads over the aliasing store)
                 double a = al[-1], g = ar[1];
+                // the teleport of every row (helper.jl:136-138) rides in the latency shadow of the recurrence: the wrapped value is what gets
+                // stored, the recurrence itself continues on the unwrapped one in the register (no separate teleport pass, one barrier less)
+                ar[0] = d_teleport_fast(prev, L, twoL, inv2L);
                 for (int row = 1; row < mq; ++row) {
                     const double a_n = al[-(row + 1)], g_n = ar[row + 1];   // row + 1 <= mq: the end row / alpha_1 slots exist
                     const double t = (1 - a) * e;
                     prev = a * prev + t + g;
-                    ar[row] = prev;
+                    ar[row] = d_teleport_fast(prev, L, twoL, inv2L);
                     a = a_n; g = g_n;
                 }
+                ar[mq] = d_teleport_fast(e, L, twoL, inv2L);
             }
 #endif
             __syncthreads();
             TICK(2);
-            // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
+            // ---- phase C: potential at the new (already wrapped) positions; nothing to do for V = 0 ----
 #ifndef EXP_SKIP_C
+            if (POT != PIMC_POT_ZERO) {
 #pragma unroll kSweepUnrollC
-            for (int s = tid; s < B; s += SWEEP_THREADS) {
-                double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
-                xs[s] = x;
-                if (dim > 1) { y = d_teleport_fast(ys[s], L, twoL, inv2L); ys[s] = y; }
-                if (POT != PIMC_POT_ZERO) pv[s] = d_pot_t<POT>(S.pot, x, y, dim);
+                for (int s = tid; s < B; s += SWEEP_THREADS) pv[s] = d_pot_t<POT>(S.pot, xs[s], dim > 1 ? ys[s] : 0.0, dim);
+                __syncthreads();
             }
 #endif
-            __syncthreads();
             TICK(3);
             // ---- phase D: Delta-U from shared memory, Metropolis, coalesced commit -- one warp per task ----
             {   // half a warp per task: twice as many tasks in flight per phase, 4-step shuffle reductions
