@@ -93,7 +93,9 @@ void pimc_destroy(pimc_handle *h);                                      /* Julia
 const char *pimc_last_error(const pimc_handle *h);                      /* NULL handle: last create error     */
 int  pimc_version(void);
 int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run kernels on this cudaStream_t   */
-/* engine options (no reference counterpart). PIMC_OPT_SWEEP_IMPL: 0 auto, 1 persistent kernel (k_run), 2 per-iteration sweep kernels */
+/* engine options (no reference counterpart). PIMC_OPT_SWEEP_IMPL (sweep schedule, independent worldlines): 0 auto, 1 persistent kernel of the
+ * reference-schedule bodies (k_run), 2 per-iteration sweep kernels (k_sweep + k_swap_iter + k_measure), 3 chain-major persistent sweep kernel
+ * (k_chain: every CTA takes a chain through all iterations of the call; the auto choice for large batches).  Identical trajectories. */
 #define PIMC_OPT_SWEEP_IMPL 1
 /* PIMC_OPT_FAITHFUL_IMPL: proposals of the reference schedule: 0 warp-cooperative (default), 1 one thread per proposal (A/B, same bits) */
 #define PIMC_OPT_FAITHFUL_IMPL 2
@@ -102,9 +104,10 @@ int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run k
  * HBM-bound centre-of-mass sweep over its issue budget and cost more than the TMA-fed estimator pass they save. */
 #define PIMC_OPT_FUSE_ENERGY 3
 /* PIMC_OPT_ISWEEP: sweep schedule of interacting worldlines (hard core; pair action not counted in ReshapeLinear / centre-of-mass moves =
- * the reference as shipped): 1 (default) adaptive -- optimistic-parallel per-iteration kernels, falling back to the sequential sweep inside
- * the persistent kernel for a few runs whenever most proposals had to be replayed serially (dense clouds); 2 always optimistic;
- * 0 always sequential.  All three produce identical trajectories. */
+ * the reference as shipped): 0 (default) the sequential sweep inside the persistent kernel; 2 the optimistic-parallel per-iteration kernels
+ * (pimc_isweep.cuh); 1 adaptive between the two (falls back to the sequential kernel for a few runs whenever more than 30 % of the proposals
+ * had to be replayed serially).  All three produce identical trajectories.  Measured on B200 (profiles/r02_summary.md) the optimistic path
+ * does not yet beat the sequential kernel on C3i / C4i, hence the default. */
 #define PIMC_OPT_ISWEEP 4
 int  pimc_set_option(pimc_handle *h, int32_t option, int64_t value);
 int64_t pimc_launch_count(void);                                        /* kernels launched by this library so far (bench evidence) */

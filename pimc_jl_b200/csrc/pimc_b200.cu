@@ -274,6 +274,7 @@ struct pimc_handle {
     int opt_fuse_energy, opt_isweep;
     int isw_backoff;                 // runs left on the sequential kernel before the optimistic sweep is probed again (dense regimes: most proposals replay)
     double isw_replay_frac;          // replays per proposal of the last optimistic run
+    int *queue;                      // chain queue of the chain-major persistent kernel
     int *nw_head, *nw_next;          // second cell list over proposed positions (optimistic sweep of interacting worldlines), lazily allocated
     unsigned long long *dstats;
     std::vector<void *> allocs;
@@ -549,7 +550,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     pimc_handle *h = new (std::nothrow) pimc_handle();
     if (!h) return PIMC_ERR_NOMEM;
     h->cfg = *cfg; h->err[0] = 0; h->stream = 0; h->iter = 0; h->N_MC = 0; h->Nctr = 0; h->nupd = h->nen = h->nde = 0;
-    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 0; h->opt_isweep = 1; h->nw_head = h->nw_next = nullptr; h->isw_backoff = 0; h->isw_replay_frac = 0.0;
+    h->ev0 = h->ev1 = nullptr; h->dT = nullptr; h->dstats = nullptr; h->opt_sweep_impl = 0; h->opt_faithful_impl = 0; h->fscr = nullptr; h->dens_out = nullptr; h->dens_out_n = 0; h->mdone = nullptr; h->opt_fuse_energy = 0; h->opt_isweep = 0; h->nw_head = h->nw_next = nullptr; h->queue = nullptr; h->isw_backoff = 0; h->isw_replay_frac = 0.0;
     memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
     h->npc = h->nwi = 0; memset(h->pc_ndata, 0, sizeof h->pc_ndata); memset(h->wi_count, 0, sizeof h->wi_count);
@@ -625,7 +626,7 @@ extern "C" int pimc_set_stream(pimc_handle *h, void *s) { if (!h) return PIMC_ER
 extern "C" int pimc_set_option(pimc_handle *h, int32_t option, int64_t value)
 {
     if (!h) return PIMC_ERR_INVALID;
-    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 2) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
+    if (option == PIMC_OPT_SWEEP_IMPL && value >= 0 && value <= 3) { h->opt_sweep_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FAITHFUL_IMPL && value >= 0 && value <= 1) { h->opt_faithful_impl = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_FUSE_ENERGY && value >= 0 && value <= 1) { h->opt_fuse_energy = (int)value; return PIMC_OK; }
     if (option == PIMC_OPT_ISWEEP && value >= 0 && value <= 2) { h->opt_isweep = (int)value; h->isw_backoff = 0; return PIMC_OK; }
@@ -1195,7 +1196,24 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
         // Energy fused into the sweep launch of a measurement iteration (chains whose centre-of-mass sweep streams every worldline anyway)
         const bool fuse_ok = nen > 0 && has_com && h->opt_fuse_energy != 0;
         if (fuse_ok && !h->mdone) { int rc = dalloc(h, &h->mdone, (size_t)S.C); if (rc) return rc; }
-        for (long long it = 0; it < n; ++it) {
+        // chain-major persistent kernel (pimc_chain.cuh): one launch for the whole call, every CTA takes a chain through all n iterations
+        const bool chain_major = h->opt_sweep_impl == 3 || (h->opt_sweep_impl == 0 && getenv("PIMC_NO_CHAIN_MAJOR") == nullptr);
+        if (chain_major) {
+            if (!h->queue) { int rc = dalloc(h, &h->queue, 4); if (rc) return rc; }
+            CK(h, cudaMemsetAsync(h->queue, 0, sizeof(int), h->stream));
+            ChainParams Q; memset(&Q, 0, sizeof Q);
+            SP.iter = h->iter;
+            SP2.sp = SP; SP2.fuse = 0; SP2.mp = MP; SP2.mdone = nullptr;
+            Q.sw = SP2; Q.mp = MP; Q.mp.ord = 0;
+            Q.mp.tma = (nen > 0 && (S.M + 31) / 32 <= 8 && (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr) ? 1 : 0;
+            Q.n = n; Q.Nctr0 = h->Nctr; Q.Ncycle = h->cfg.Ncycle; Q.measure = nen + nde > 0 ? 1 : 0; Q.queue = h->queue;
+            size_t smem_ch = smem_rs > smem_cs ? smem_rs : smem_cs;
+            const size_t smem_sw = has_swap ? swap_smem_bytes(S.N, S.M) : 0, smem_me = Q.mp.tma ? (size_t)8 * 16 + (size_t)8 * 2 * S.dim * S.M * sizeof(double) : 0;
+            if (smem_sw > smem_ch) smem_ch = smem_sw;
+            if (smem_me > smem_ch) smem_ch = smem_me;
+            CK(h, pimc_launch_chain(smem_ch + smem_pad, h->stream, S, h->dT, Q, nullptr)); LAUNCHED(); launches++;
+        }
+        for (long long it = 0; it < n && !chain_major; ++it) {
             SP.iter = h->iter + (unsigned long long)it;
             const long long ctrv = h->Nctr + it + 1;
             const bool meas_now = nen + nde > 0 && ctrv % h->cfg.Ncycle == 0;

@@ -66,52 +66,6 @@ __device__ __forceinline__ void d_nw_remove(const DevSys &S, const ISweepParams 
 __device__ __forceinline__ double d_prop_x(const DevSys &S, int c, int p, int sl) { return S.prop[RIDX(S, c, p, 0, sl)]; }
 __device__ __forceinline__ double d_prop_y(const DevSys &S, int c, int p, int sl) { return S.dim > 1 ? S.prop[RIDX(S, c, p, 1, sl)] : 0.0; }
 
-// ---- register-resident stencil walk.  The generic PIMC_FOR_STENCIL (pimc_device.cuh) keeps the prefetched heads in a local-memory struct and
-// runs one rolled copy of its body (code size of the persistent kernel); here the nine cell indices and list heads live in registers, the
-// head loads are issued together, and a query whose stencil is empty -- the common case in the gases of the examples -- ends after that one
-// round trip.  Visiting order and arithmetic are those of d_find_nn, so the answers are identical.
-struct Stencil9 { int cell[9]; };
-__device__ __forceinline__ void d_stencil9(const DevSys &S, double x, double y, Stencil9 &T)
-{
-    const double inv = 1.0 / S.cellw; const int nb = S.nbins;
-    int ix = d_floor_div(x + S.L, S.cellw, inv); ix = ix < 0 ? 0 : (ix > nb - 1 ? nb - 1 : ix);
-    if (S.dim == 2) {
-        int iy = d_floor_div(y + S.L, S.cellw, inv); iy = iy < 0 ? 0 : (iy > nb - 1 ? nb - 1 : iy);
-        const int xm = d_wrap1(ix - 1, nb), xp = d_wrap1(ix + 1, nb), ym = d_wrap1(iy - 1, nb) * nb, yp = d_wrap1(iy + 1, nb) * nb, y0 = iy * nb;
-        // bin_neighbors order (nearest_neighbours.jl:55-65): (0,0) (-1,1) (0,1) (1,1) (-1,0) (1,0) (-1,-1) (0,-1) (1,-1)
-        T.cell[0] = ix + y0; T.cell[1] = xm + yp; T.cell[2] = ix + yp; T.cell[3] = xp + yp; T.cell[4] = xm + y0; T.cell[5] = xp + y0;
-        T.cell[6] = xm + ym; T.cell[7] = ix + ym; T.cell[8] = xp + ym;
-    } else {
-        T.cell[0] = ix; T.cell[1] = d_wrap1(ix - 1, nb); T.cell[2] = d_wrap1(ix + 1, nb);
-#pragma unroll
-        for (int q = 3; q < 9; ++q) T.cell[q] = -1;
-    }
-}
-// hard-core test against S0 (== d_hardcore_hit): nearest stencil occupant by the periodic metric, then the distance test of helper.jl:167-170
-__device__ __forceinline__ bool d_hc_hit_s0(const DevSys &S, int c, double x, double y, int sl, int exc)
-{
-    Stencil9 T; d_stencil9(S, x, y, T);
-    int h[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) h[q] = T.cell[q] >= 0 ? S.cell_head[HIDX(S, c, sl, T.cell[q])] : -1;
-    bool all_empty = true;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) all_empty = all_empty && h[q] < 0;
-    if (all_empty) return false;
-    int best = -1; double bd = 0.0, bx = 0.0, by = 0.0;
-#pragma unroll
-    for (int q = 0; q < 9; ++q)
-        for (int o = h[q]; o >= 0; o = S.cell_next[NIDX(S, c, sl, o)]) {
-            if (o == exc) continue;
-            const double ox = S.r[RIDX(S, c, o, 0, sl)], oy = S.dim > 1 ? S.r[RIDX(S, c, o, 1, sl)] : 0.0;
-            const double pe = d_peuclid(S, ox, oy, x, y);
-            if (best < 0 || pe < bd) { best = o; bd = pe; bx = ox; by = oy; }
-        }
-    if (best < 0) return false;
-    const double dx = d_distance(x, bx, S.L), dy = S.dim > 1 ? d_distance(y, by, S.L) : 0.0;
-    return d_norm2(dx, dy, S.dim) < S.a;
-}
-
 // NW entries within a(1 + 1e-9) of (x, y) at slice sl.  MODE 0 (validation of proposal n): is there one written by a tentatively accepted
 // proposal k < n?  MODE 1 (after the replay of n): mark every proposal k > n that owns one DIRTY.  Returns the MODE 0 answer.
 template <bool COM, int MODE>
@@ -124,30 +78,6 @@ static __device__ __noinline__ bool d_nw_near(const DevSys &S, const ISweepParam
     if (S.dim > 1) { iya = d_floor_div(y - ap + S.L, S.cellw, inv); iyb = d_floor_div(y + ap + S.L, S.cellw, inv); }
     bool found = false;
     const int nx = min(ixb - ixa + 1, 3), ny = min(iyb - iya + 1, 3);
-    if (nx <= 2 && ny <= 2) {   // a < cell width: at most 2 x 2 cells; their heads are fetched together, empty cells (the common case) cost nothing more
-        int cellq[4], hq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int dx = q & 1, dy = q >> 1;
-            int ix = ixa + dx; ix = ix < 0 ? ix + nb : (ix >= nb ? ix - nb : ix); ix = ix < 0 ? 0 : (ix > nb - 1 ? nb - 1 : ix);
-            int iy = iya + dy; iy = iy < 0 ? iy + nb : (iy >= nb ? iy - nb : iy); iy = iy < 0 ? 0 : (iy > nb - 1 ? nb - 1 : iy);
-            cellq[q] = (dx < nx && dy < ny) ? (S.dim > 1 ? ix + nb * iy : ix) : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hq[q] = cellq[q] >= 0 ? P.nw_head[HIDX(S, c, sl, cellq[q])] : -1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            for (int o = hq[q]; o >= 0; o = P.nw_next[NIDX(S, c, sl, o)]) {
-                int t; const int k = d_is_writer<COM>(X, o, sl, t);
-                if (k < 0 || k == n) continue;
-                if (MODE == 0 ? !(k < n && (X.stat[k] & ISW_ACC)) : !(k > n)) continue;
-                if (d_peuclid(S, d_prop_x(S, c, o, sl), d_prop_y(S, c, o, sl), x, y) < ap) {
-                    if (MODE == 0) return true;
-                    atomicOr(&X.stat[k], ISW_DIRTY);
-                }
-            }
-        return found;
-    }
     for (int dy = 0; dy < ny; ++dy)
         for (int dx = 0; dx < nx; ++dx) {
             int ix = ixa + dx; ix = ix < 0 ? ix + nb : (ix >= nb ? ix - nb : ix); ix = ix < 0 ? 0 : (ix > nb - 1 ? nb - 1 : ix);
@@ -171,18 +101,11 @@ static __device__ __noinline__ bool d_nw_near(const DevSys &S, const ISweepParam
 template <bool COM>
 static __device__ __noinline__ bool d_hit_virtual(const DevSys &S, const ISweepParams &P, const IsCtx &X, int c, double x, double y, int sl, int exc, int d)
 {
-    Stencil9 T; d_stencil9(S, x, y, T);
-    int h0[9], h1[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) { h0[q] = T.cell[q] >= 0 ? S.cell_head[HIDX(S, c, sl, T.cell[q])] : -1; h1[q] = T.cell[q] >= 0 ? P.nw_head[HIDX(S, c, sl, T.cell[q])] : -1; }
-    bool all_empty = true;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) all_empty = all_empty && h0[q] < 0 && h1[q] < 0;
-    if (all_empty) return false;
+    const int b = d_bin(S, x, y), nst = S.dim == 2 ? 9 : 3;
     int best = -1; double bd = 0.0, bx = 0.0, by = 0.0;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) {
-        for (int o = h0[q]; o >= 0; o = S.cell_next[NIDX(S, c, sl, o)]) {
+    for (int q = 0; q < nst; ++q) {
+        const int cell = d_stencil(S, b, q);
+        for (int o = S.cell_head[HIDX(S, c, sl, cell)]; o >= 0; o = S.cell_next[NIDX(S, c, sl, o)]) {
             if (o == exc) continue;
             int t; const int k = d_is_writer<COM>(X, o, sl, t);
             if (k >= 0 && k < d && t >= 1 && (X.stat[k] & ISW_ACC)) continue;          // moved away by an accepted lower proposal
@@ -190,7 +113,7 @@ static __device__ __noinline__ bool d_hit_virtual(const DevSys &S, const ISweepP
             const double pe = d_peuclid(S, ox, oy, x, y);
             if (best < 0 || pe < bd) { best = o; bd = pe; bx = ox; by = oy; }
         }
-        for (int o = h1[q]; o >= 0; o = P.nw_next[NIDX(S, c, sl, o)]) {
+        for (int o = P.nw_head[HIDX(S, c, sl, cell)]; o >= 0; o = P.nw_next[NIDX(S, c, sl, o)]) {
             if (o == exc) continue;
             int t; const int k = d_is_writer<COM>(X, o, sl, t);
             if (!(k >= 0 && k < d && (X.stat[k] & ISW_ACC))) continue;                  // only final rows of accepted lower proposals exist
@@ -278,7 +201,7 @@ __device__ __forceinline__ bool d_isw_rs_eval(const DevSys &S, const ISweepParam
     bool hit = false;
     for (int j = 1 + lane; j <= mb; j += 32) {
         const int a = first + j, sl = a >= M ? a - M : a;
-        if (d_hc_hit_s0(S, c, px[j], py[j], sl, n)) hit = true;
+        if (d_hardcore_hit(S, c, px[j], py[j], sl, n)) hit = true;
     }
     return __any_sync(0xffffffffu, hit);
 }
@@ -670,7 +593,7 @@ __global__ void __launch_bounds__(ISW_THREADS, 4) k_isweep_com(const __grid_cons
 #pragma unroll
         for (int k = 0; k < KM; ++k) {
             const int j = lane + 32 * k;
-            if (j < M && d_hc_hit_s0(S, c, x[k], y[k], j, n)) hit = true;
+            if (j < M && d_hardcore_hit(S, c, x[k], y[k], j, n)) hit = true;
         }
         if (lane == 0) my_beads += (unsigned long long)M;
         if (__any_sync(0xffffffffu, hit)) { if (lane == 0) stat[n] = ISW_PROP | ISW_DIRTY; __syncwarp(); continue; }

@@ -59,6 +59,15 @@ cudaError_t pimc_launch_sweep(int grid, size_t smem, cudaStream_t st, const DevS
 cudaError_t pimc_launch_swap_iter(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);
 cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const MeasParams &P, const unsigned char *mdone);
 size_t pimc_paircorr_smem(const DevSys &S, const PcDev &G, int *TS, int *smem_hist);
+// chain-major persistent kernel (pimc_chain.cuh)
+struct ChainParams {
+    Sweep2Params sw;            // update descriptors, weights, round keys (sw.sp.iter = first iteration of the call)
+    MeasParams mp;              // estimator objects; mp.ord = index of the first measurement event of this call
+    long long n;                // iterations per chain
+    long long Nctr0; int Ncycle; int measure;   // cadence counter at the start of the call (measurement.jl:1-17)
+    int *queue;                 // next chain to take
+};
+cudaError_t pimc_launch_chain(size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const ChainParams &Q, int *grid_out);
 cudaError_t pimc_launch_paircorr(int grid, cudaStream_t st, const DevSys &S, const PcDev &G);
 cudaError_t pimc_launch_winding(int grid, cudaStream_t st, const DevSys &S, const WiDev &W, long long k);
 cudaError_t pimc_launch_isweep(int grid, cudaStream_t st, const DevSys &S, const ISweepParams &P, bool has_rs, bool has_com);

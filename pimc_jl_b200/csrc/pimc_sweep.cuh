@@ -42,7 +42,7 @@ __device__ __forceinline__ double d_wi_halfwarp(const double *w1, const double *
 
 template <int POT>
 __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdDev &U, const SweepParams &P, const pimc_stream &st,
-                                                     const pimc_u4 &di, const int pick, const int BCAP)
+                                                     const pimc_u4 &di, const int pick, const int BCAP, const int c)
 {
     extern __shared__ double sm[];
     double *xs = sm, *ys = sm + BCAP;          // BCAP staged rows per batch (a multiple of 16, sized by the host from the shared-memory budget)
@@ -58,7 +58,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
     __shared__ int s_first;
     __shared__ unsigned long long s_bead;
 
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = S.M, N = S.N, dim = S.dim;
     const double varf = U.var[c];             // the only global load the segment lengths wait for: issued first
     // counters of the apply! bookkeeping and the tables arrive by cp.async (no registers, nobody waits): the scalars now, the ring
@@ -179,29 +179,30 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
                 // software pipelined by hand: next step's alpha and xi*sigma are fetched before this step's store, so that only
                 // DMUL -> DADD -> DADD sits on the serial path (the compiler cannot hoist the loads over the aliasing store)
                 double a = al[-1], g = ar[1];
-                // the teleport of every row (helper.jl:136-138) rides in the latency shadow of the recurrence: the wrapped value is what gets
-                // stored, the recurrence itself continues on the unwrapped one in the register (no separate teleport pass, one barrier less)
-                ar[0] = d_teleport_fast(prev, L, twoL, inv2L);
+                // (folding the teleport of every row into this loop was measured: -10 % -- the recurrence runs on TB * dim lanes only, and the
+                //  extra dozen fp64 instructions per step lengthen the serial phase by more than the parallel pass below costs)
                 for (int row = 1; row < mq; ++row) {
                     const double a_n = al[-(row + 1)], g_n = ar[row + 1];   // row + 1 <= mq: the end row / alpha_1 slots exist
                     const double t = (1 - a) * e;
                     prev = a * prev + t + g;
-                    ar[row] = d_teleport_fast(prev, L, twoL, inv2L);
+                    ar[row] = prev;
                     a = a_n; g = g_n;
                 }
-                ar[mq] = d_teleport_fast(e, L, twoL, inv2L);
             }
 #endif
             __syncthreads();
             TICK(2);
-            // ---- phase C: potential at the new (already wrapped) positions; nothing to do for V = 0 ----
+            // ---- phase C: teleport every row (helper.jl:136-138), potential at the new positions ----
 #ifndef EXP_SKIP_C
-            if (POT != PIMC_POT_ZERO) {
 #pragma unroll kSweepUnrollC
-                for (int s = tid; s < B; s += SWEEP_THREADS) pv[s] = d_pot_t<POT>(S.pot, xs[s], dim > 1 ? ys[s] : 0.0, dim);
-                __syncthreads();
+            for (int s = tid; s < B; s += SWEEP_THREADS) {
+                double x = d_teleport_fast(xs[s], L, twoL, inv2L), y = 0.0;
+                xs[s] = x;
+                if (dim > 1) { y = d_teleport_fast(ys[s], L, twoL, inv2L); ys[s] = y; }
+                if (POT != PIMC_POT_ZERO) pv[s] = d_pot_t<POT>(S.pot, x, y, dim);
             }
 #endif
+            __syncthreads();
             TICK(3);
             // ---- phase D: Delta-U from shared memory, Metropolis, coalesced commit -- one warp per task ----
             {   // half a warp per task: twice as many tasks in flight per phase, 4-step shuffle reductions
@@ -275,6 +276,7 @@ __device__ __forceinline__ void d_reshape_sweep_body(const DevSys &S, const UpdD
 
 // ---- 1-D bulk async copies (TMA, cp.async.bulk + mbarrier complete_tx): HBM -> shared memory without register staging ----
 __device__ __forceinline__ void d_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void d_mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void d_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void d_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -398,10 +400,10 @@ __device__ __forceinline__ void d_pcom_cycles(const DevSys &S, const SweepParams
 // exchange cycles (whose members this sweep does not stream) leave mdone[c] = 0 and are measured by k_measure.
 template <int POT, int KM, bool FUSE, int TH = SWEEP_THREADS>
 __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &U, const SweepParams &P, const pimc_stream &st,
-                                                 const int pick, const Sweep2Params &P2, const DevTables *__restrict__ T)
+                                                 const int pick, const Sweep2Params &P2, const DevTables *__restrict__ T, const int c)
 {
     extern __shared__ double sm[];
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TH / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TH / 32;
     const int M = S.M, N = S.N, dim = S.dim;
     unsigned char *flag = (unsigned char *)sm;
     __shared__ unsigned long long s_bead;
@@ -579,6 +581,7 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
     }
     if (my_beads) atomicAdd(&s_bead, my_beads);
     __syncthreads();
+    if (use_tma && lane == 0) { d_mbar_inval(bar_u); d_mbar_inval(bar_u + 8); }   // the shared memory is reused by whatever runs next in this CTA
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 }
 
@@ -593,8 +596,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
     pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
     const int pick = d_pick_update(P, di);
     const int kind = P.kind[pick];
-    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, FUSE>(S, P2.upd[pick], P, st, pick, P2, T);
+    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap, c);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, FUSE>(S, P2.upd[pick], P, st, pick, P2, T, c);
 }
 
 // The swap move stays one proposal per chain and iteration (reshape.jl:123-283): one warp per chain.  Everything that touches
@@ -602,15 +605,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_
 // tail exchange); the two staging recurrences run on four lanes (bridge x dim); every SUM keeps the sequential order of the
 // one-thread reference implementation d_reshape_swap / d_swap_weights on lane 0, so results are bit-identical to it and to the oracle.
 // Shared memory (dynamic): w[N] | 2 bridges x { x[M+1], y[M+1], v[M+1], link[M+1], vold[M+1] }.
-__global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
+__device__ __forceinline__ void d_swap_iter_body(const DevSys &S, const Sweep2Params &P2, const pimc_stream &st, const int pick, const int c, double *sm)
 {
-    extern __shared__ double sm[];
     const SweepParams &P = P2.sp;
-    const int c = blockIdx.x, N = S.N, M = S.M, dim = S.dim, lane = threadIdx.x;
-    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const int pick = d_pick_update(P, di);
-    if (P.kind[pick] != PIMC_UPD_RESHAPE_SWAP) return;
+    const int N = S.N, M = S.M, dim = S.dim, lane = threadIdx.x & 31;
     const UpdDev &U = P2.upd[pick];
     double *w = sm, *br = sm + N;                              // br: bridge b at br + b * 5 * (M + 1)
     const int R1 = M + 1;
@@ -751,6 +749,17 @@ __global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys
     U.bead_moves[c] += (long long)beads;
     if ((R.tries % U.adj) == 0) d_adjust(U, c, R);
     if (P.stats) { atomicAdd(P.stats + 0, 1ull); atomicAdd(P.stats + 2, beads); }
+}
+static __global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ Sweep2Params P2)
+{
+    extern __shared__ double sm[];
+    const SweepParams &P = P2.sp;
+    const int c = blockIdx.x;
+    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    if (P.kind[pick] != PIMC_UPD_RESHAPE_SWAP) return;
+    d_swap_iter_body(S, P2, st, pick, c, sm);
 }
 
 // Energy functor (measurement.jl:92-122) with one warp per worldline (lanes stride the slices: coalesced, no index division)
@@ -900,6 +909,8 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
         }
         nx = nx_next;
     }
+    __syncwarp();
+    if (lane == 0) { d_mbar_inval(bar_u); d_mbar_inval(bar_u + 8); }   // the shared memory is reused by whatever runs next in this CTA
     link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
     __syncthreads();
     if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }
@@ -911,19 +922,16 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
         *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
     }
 }
+// one measurement event of chain c (measurement.jl:1-17 cadence handled by the caller): Energy objects, then Density objects
 template <int POT, int KM>
-__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
-                                                    const unsigned char *__restrict__ mdone)
+__device__ __forceinline__ void d_measure_body(const DevSys &S, const DevTables *__restrict__ T, const MeasParams &P, const int c, const bool en_done,
+                                               double *red, char *dyn)
 {
-    __shared__ double red[96];
-    extern __shared__ __align__(16) char dyn_meas[];   // TMA ring of the Energy pass (P.tma), else unused
-    const int c = blockIdx.x;
-    const bool en_done = mdone && mdone[c];     // Energy of this chain was evaluated inside the sweep launch (fused)
     for (int e = 0; e < P.nen && !en_done; ++e) {
         const EnDev &En = T->en[P.en_id[e]];
         const long long k = P.en_k0[e] + P.ord; // the object's own count (measurement.jl:119-120)
         double E, Ev;
-        if (KM > 0 && P.tma && e == 0) d_energy_block_tma<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev, dyn_meas);
+        if (KM > 0 && P.tma && e == 0) d_energy_block_tma<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev, dyn);
         else if (KM > 0) d_energy_block_reg<POT, (KM > 0 ? KM : 1)>(S, c, red, &E, &Ev);
         else d_energy_block_fast<POT>(S, c, red, &E, &Ev);
         if (threadIdx.x == 0) {
@@ -934,4 +942,13 @@ __global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevS
         __syncthreads();
     }
     for (int d = 0; d < P.nde; ++d) d_density_block(S, c, T->de[P.de_id[d]]);
+}
+template <int POT, int KM>
+__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
+                                                    const unsigned char *__restrict__ mdone)
+{
+    __shared__ double red[96];
+    extern __shared__ __align__(16) char dyn_meas[];   // TMA ring of the Energy pass (P.tma), else unused
+    const int c = blockIdx.x;
+    d_measure_body<POT, KM>(S, T, P, c, mdone && mdone[c], red, dyn_meas);   // mdone: Energy of this chain was evaluated inside the sweep launch (fused)
 }

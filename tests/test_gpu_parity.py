@@ -336,14 +336,17 @@ def test_interacting_faithful_cell_list(oracle, compat, fimpl):
             e.run(10, ge, sched=L.SCHED_SWEEP)
 
 
+@pytest.mark.parametrize("isw", [0, 2], ids=["sequential-kernel", "optimistic-kernels"])
 @pytest.mark.parametrize("compat", [L.COMPAT_ALL, 0], ids=["as-shipped", "intended"])
-def test_interacting_sweep_sequential(oracle, compat):
+def test_interacting_sweep_sequential(oracle, compat, isw):
     """Sweep schedule of INTERACTING worldlines (hard core, lnU table, cell list): every worldline proposes once per iteration, strictly
-    in order, inside the persistent kernel; held to the oracle's ORA_SCHED_SWEEP_SEQ bit for bit."""
+    in order; held to the oracle's ORA_SCHED_SWEEP_SEQ bit for bit in both executions -- inside the persistent kernel (default) and by the
+    optimistic-parallel kernels of pimc_isweep.cuh (PIMC_OPT_ISWEEP = 2; they apply to the as-shipped compat mode, the intended mode stays sequential)."""
     ob = oracle
     tab, lo, hi = synthetic_table()
     cfg = dict(pot="harmonic", dim=2, M=12, N=9, L=3.0, T=0.5, lam=0.5, Ncycle=3)
     e, os_ = make_pair(ob, cfg, chains=3, seed=31, interactions=True, g=3.0, r_a=1.0, tab=tab, tab_lo=lo, tab_hi=hi, compat=compat)
+    e.set_option(L.OPT_ISWEEP, isw)
     assert e.a > 0
     spec = [(2, L.UPD_SINGLE_COM, 0.4), (1, L.UPD_RESHAPE_LINEAR, 6), (2, L.UPD_RESHAPE_SWAP, 6), (3, L.UPD_POLYMER_COM, 0.3)]
     ge, oo = _mk_updates(ob, e, os_, spec)
@@ -417,7 +420,7 @@ def test_interacting_faithful_warp_stress(oracle, cfg, g, n_it, compat):
     assert np.array_equal(r1, r2) and np.array_equal(V1, V2) and np.array_equal(b1, b2) and np.array_equal(n1, n2)
 
 
-@pytest.mark.parametrize("impl", [1, 2], ids=["sweep-persistent", "sweep-batched"])
+@pytest.mark.parametrize("impl", [1, 2, 3], ids=["sweep-persistent", "sweep-batched", "sweep-chain-major"])
 @pytest.mark.parametrize("cfg,rng_,n_it", [
     (dict(pot="zero", dim=2, M=33, N=300, L=5.0, T=1.0, lam=1.0, Ncycle=3), 10000, 14),      # two super-batches, ragged M (KM = 2)
     (dict(pot="harmonic", dim=2, M=200, N=5, L=6.0, T=0.25, lam=0.5, Ncycle=2), 10000, 30),   # KM = 8 register tiles
@@ -510,21 +513,27 @@ def _check_against_oracle(ob, e, ge, spec, cfg, chains, measure, n_it, seed, sch
     return dsum
 
 
+@pytest.mark.parametrize("impl", [3, 2], ids=["chain-major", "per-iteration"])
 @pytest.mark.parametrize("name", sorted(BASELINE_SHAPES))
-def test_baseline_shapes_batched_kernels_vs_oracle(oracle, name):
-    """k_sweep<POT,KM> / k_swap_iter / k_measure<POT,KM> -- the per-iteration kernels bench.py times -- at every BASELINE shape against the
-    oracle: bit-exact positions / link cache / permutation / counters, E within 1e-12 dN/2tau, histogram integer-equal."""
+def test_baseline_shapes_batched_kernels_vs_oracle(oracle, name, impl):
+    """the throughput kernels bench.py times -- k_chain<POT,KM> (chain-major persistent kernel, the default dispatch) and the per-iteration
+    k_sweep<POT,KM> / k_swap_iter / k_measure<POT,KM> it shares its device bodies with -- at every BASELINE shape against the oracle:
+    bit-exact positions / link cache / permutation / counters, E within 1e-12 dN/2tau, histogram integer-equal."""
     ob = oracle
     cfg, spec, measure, n_it = BASELINE_SHAPES[name]
     chains = 2 if cfg["N"] >= 256 else 3
     pg = pots(ob)[cfg["pot"]][1]
     e = pj.Engine(pg, chains=chains, L_=cfg["L"], dim=cfg["dim"], M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=2025)
-    e.set_option(L.OPT_SWEEP_IMPL, 2)          # the per-iteration sweep kernels regardless of the batch size
+    e.set_option(L.OPT_SWEEP_IMPL, impl)       # regardless of the batch size
     ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
     e._test_en = e.energy_create(64)
     de = e.density_create(500)
-    st = e.run(n_it, ge, energies=[e._test_en] if measure == "energy" else [], densities=[de] if measure == "density" else [], sched=L.SCHED_SWEEP)
-    assert st["launches"] >= n_it              # one k_sweep (+ k_swap_iter, + k_measure) launch per iteration, not the persistent kernel
+    kw = dict(energies=[e._test_en] if measure == "energy" else [], densities=[de] if measure == "density" else [], sched=L.SCHED_SWEEP)
+    n1 = n_it // 2 + 1                         # two calls: the iteration / cadence counters carry over
+    st = e.run(n1, ge, **kw)
+    st2 = e.run(n_it - n1, ge, **kw)
+    # one k_sweep (+ k_swap_iter, + k_measure) launch per iteration, or ONE k_chain launch per call
+    assert (st["launches"] >= n1 and st2["launches"] >= n_it - n1) if impl == 2 else (st["launches"] == 1 and st2["launches"] == 1)
     dsum = _check_against_oracle(ob, e, ge, spec, cfg, range(chains), measure, n_it, 2025)
     if measure == "density":
         dg, nd, _ = e.density_read(de, 500)
@@ -537,17 +546,19 @@ def test_c2_default_dispatch_at_bench_scale_vs_oracle(oracle):
     ob = oracle
     cfg, spec, measure, n_it = BASELINE_SHAPES["C2"]
     out = []
-    for fuse in (1, 0):
+    for impl, fuse in ((0, 0), (2, 1), (2, 0)):   # default dispatch = chain-major kernel; per-iteration kernels with and without the fused Energy
         e = pj.Engine(pots(ob)["zero"][1], chains=128, L_=cfg["L"], dim=2, M=128, N=64, T=1.0, lam=1.0, Ncycle=2, seed=7)
+        e.set_option(L.OPT_SWEEP_IMPL, impl)
         e.set_option(L.OPT_FUSE_ENERGY, fuse)
         ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
         e._test_en = e.energy_create(64)
         st = e.run(n_it, ge, energies=[e._test_en], sched=L.SCHED_SWEEP)
-        assert st["launches"] >= n_it
+        assert st["launches"] == 1 if impl == 0 else st["launches"] >= n_it
         _check_against_oracle(ob, e, ge, spec, cfg, [0, 37, 127], "energy", n_it, 7)
         out.append((e.paths(want=("r",))[0], e.energy_read(e._test_en, -1)[0]))
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.all(np.abs(out[0][1] - out[1][1]) <= 1e-12 * 2 * 64 / (2 * e.tau))
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0])
+        assert np.all(np.abs(out[0][1] - o[1]) <= 1e-12 * 2 * 64 / (2 * e.tau))
 
 
 def _real_table(Lbox, g, T, M):
@@ -558,7 +569,7 @@ def _real_table(Lbox, g, T, M):
     return p, tau
 
 
-@pytest.mark.parametrize("sched", ["faithful", "sweep"])
+@pytest.mark.parametrize("sched", ["faithful", "sweep", "sweep-optimistic"])
 @pytest.mark.parametrize("name", ["C3i", "C4i"])
 def test_interacting_baseline_scale_real_table(oracle, name, sched):
     """The interacting BASELINE configurations at full per-chain size with the REAL pair-propagator table (propint.build_prop_int) on both
@@ -583,6 +594,8 @@ def test_interacting_baseline_scale_real_table(oracle, name, sched):
     chains = 2
     e = pj.Engine(pots(ob)[cfg["pot"]][1], chains=chains, L_=cfg["L"], dim=2, M=cfg["M"], N=cfg["N"], T=cfg["T"], lam=cfg["lam"], Ncycle=cfg["Ncycle"], seed=31, **ia)
     assert e.a > 0 and (name != "C3i" or e.nbins == 32)
+    if sched == "sweep-optimistic":
+        e.set_option(L.OPT_ISWEEP, 2)
     ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
     de = e.density_create(500)
     n_it = 150 if sched == "faithful" else 6
