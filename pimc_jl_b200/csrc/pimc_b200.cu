@@ -1197,7 +1197,10 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
         const bool fuse_ok = nen > 0 && has_com && h->opt_fuse_energy != 0;
         if (fuse_ok && !h->mdone) { int rc = dalloc(h, &h->mdone, (size_t)S.C); if (rc) return rc; }
         // chain-major persistent kernel (pimc_chain.cuh): one launch for the whole call, every CTA takes a chain through all n iterations
-        const bool chain_major = h->opt_sweep_impl == 3 || (h->opt_sweep_impl == 0 && getenv("PIMC_NO_CHAIN_MAJOR") == nullptr);
+        // (measured on C2, profiles/r02_summary.md: 5.2e10 against 6.0e10 bead-moves/s of the per-iteration kernels -- the resident chains' 116 MB do
+        //  not stay in the two 63 MB L2 partitions, and the in-kernel estimator pass loses the all-SMs streaming pattern of k_measure -- so the
+        //  automatic choice stays per-iteration; the kernel is kept selectable)
+        const bool chain_major = h->opt_sweep_impl == 3 || (h->opt_sweep_impl == 0 && getenv("PIMC_CHAIN_MAJOR") != nullptr);
         if (chain_major) {
             if (!h->queue) { int rc = dalloc(h, &h->queue, 4); if (rc) return rc; }
             CK(h, cudaMemsetAsync(h->queue, 0, sizeof(int), h->stream));

@@ -7,7 +7,10 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pimc_jl_b200", "libpimc_b200.so")
 os.makedirs("/tmp/cub", exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd="/tmp/cub", capture_output=True)
-dis = subprocess.run(["nvdisasm", "--print-line-info", "/tmp/cub/pimc_b200.sm_100a.cubin"], capture_output=True, text=True).stdout.splitlines()
+import glob
+dis = []
+for cub in sorted(glob.glob("/tmp/cub/*.cubin")):    # one cubin per translation unit of the library
+    dis += subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
 line_of, cur, infn = {}, None, False
 for l in dis:
     if l.startswith("\t.section\t.text."):
