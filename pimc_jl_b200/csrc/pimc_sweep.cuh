@@ -847,9 +847,34 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
         *Ev = 1.0 / (2 * S.M) * vkin + 1.0 / (2 * S.M) * pot;
     }
 }
-// TMA-fed variant (even M): every warp keeps the NEXT worldline's rows in flight (cp.async.bulk into its own two-stage shared-memory ring,
-// completion on an mbarrier) while it reduces the current one -- bytes in flight without registers; the permutation entry of the next
-// worldline is fetched one step ahead.  Same sums as d_energy_block_reg.
+// One staged worldline (rows sx | sy in shared memory) into the lane-partial Energy sums.  DV: 0 zero, 1 identity, 2 general gradient --
+// hoisted out of the bead loop (a per-bead runtime branch was a tenth of the kernel's instructions); the successor bead is read from the
+// staged row itself (no register tile, no shuffles), only the link that leaves the last slice needs the first bead of the cycle's next member.
+template <int POT, int KM, int DV>
+__device__ __forceinline__ void d_energy_row(const DevSys &S, const double *sx, const double x0n, const double y0n, const double twoL,
+                                             double &link, double &pot, double &vkin)
+{
+    const int M = S.M, dim = S.dim, lane = threadIdx.x & 31;
+    const double *sy = sx + M;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+        const int j = lane + 32 * k;
+        if (j < M) {
+            const double ax = sx[j], ay = dim > 1 ? sy[j] : 0.0;
+            const double bx = j + 1 < M ? sx[j + 1] : x0n, by = dim > 1 ? (j + 1 < M ? sy[j + 1] : y0n) : 0.0;
+            double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
+            double d2 = dx * dx;
+            if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
+            link += d2;
+            if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
+            if (DV == 1) { double q = ax * ax; if (dim > 1) q = q + ay * ay; vkin += q; }   // r . dV(r), measurement.jl:105
+            else if (DV == 2) vkin += d_rdv(S.pot, ax, ay, dim);
+        }
+    }
+}
+// TMA-fed Energy pass (even M): every warp keeps the NEXT worldline's rows in flight (cp.async.bulk into its own two-stage shared-memory ring,
+// completion on an mbarrier) while it reduces the current one straight from shared memory; the permutation entry of the next worldline is
+// fetched one step ahead.  Same per-lane summation order as d_energy_block_reg.
 template <int POT, int KM>
 __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, double *red, double *E, double *Ev, char *dyn)
 {
@@ -880,33 +905,14 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
         __syncwarp();                                   // every lane is done with the other stage
         if (n + nw < N) issue(n + nw, stg ^ 1);
         const int nx_next = n + nw < N ? nextc[n + nw] : 0;
-        // first bead of the next particle of the cycle (the worldline's own bead 0 when it is closed on itself)
-        double x0n = 0.0, y0n = 0.0;
+        double x0n = 0.0, y0n = 0.0;                    // first bead of the next particle of the cycle
         if (nx != n) { const double *qx = rc + (size_t)(nx * dim) * M; x0n = qx[0]; y0n = dim > 1 ? qx[M] : 0.0; }
         d_mbar_wait(bar_u + 8u * stg, par);
         const double *sx = stage0 + (size_t)stg * dim * M;
-        double x[KM], y[KM];
-#pragma unroll
-        for (int k = 0; k < KM; ++k) { const int j = lane + 32 * k; x[k] = j < M ? sx[j] : 0.0; y[k] = (dim > 1 && j < M) ? sx[M + j] : 0.0; }
-        if (nx == n) { x0n = __shfl_sync(0xffffffffu, x[0], 0); y0n = __shfl_sync(0xffffffffu, y[0], 0); }
-#pragma unroll
-        for (int k = 0; k < KM; ++k) {
-            const int j = lane + 32 * k;
-            double bx = __shfl_down_sync(0xffffffffu, x[k], 1), by = __shfl_down_sync(0xffffffffu, y[k], 1);
-            const double nbx = __shfl_sync(0xffffffffu, x[(k + 1 < KM) ? k + 1 : k], 0), nby = __shfl_sync(0xffffffffu, y[(k + 1 < KM) ? k + 1 : k], 0);
-            if (lane == 31) { bx = nbx; by = nby; }
-            if (j == M - 1) { bx = x0n; by = y0n; }
-            if (j < M) {
-                const double ax = x[k], ay = y[k];
-                double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
-                double d2 = dx * dx;
-                if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
-                link += d2;
-                if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
-                if (dvk == PIMC_DV_IDENTITY) { double q = ax * ax; if (dim > 1) q = q + ay * ay; vkin += q; }   // r . dV(r), measurement.jl:105
-                else if (dvk != PIMC_DV_ZERO) vkin += d_rdv(S.pot, ax, ay, dim);
-            }
-        }
+        if (nx == n) { x0n = sx[0]; y0n = dim > 1 ? sx[M] : 0.0; }   // closed on itself: its own bead 0
+        if (dvk == PIMC_DV_IDENTITY) d_energy_row<POT, KM, 1>(S, sx, x0n, y0n, twoL, link, pot, vkin);
+        else if (dvk == PIMC_DV_ZERO) d_energy_row<POT, KM, 0>(S, sx, x0n, y0n, twoL, link, pot, vkin);
+        else d_energy_row<POT, KM, 2>(S, sx, x0n, y0n, twoL, link, pot, vkin);
         nx = nx_next;
     }
     __syncwarp();

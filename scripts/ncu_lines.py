@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Join an ncu SASS source page with nvdisasm line info: instructions executed / stall samples per source line.
-usage: ncu_lines.py report.ncu-rep mangled_kernel_substring [top]"""
+usage: ncu_lines.py report.ncu-rep mangled_kernel_substring [top]
+The substring must select ONE instantiation (e.g. k_measureILi0ELi4E): sections of several instantiations share their address offsets."""
 import csv, subprocess, sys, re, os, collections
 rep, ksub = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
@@ -28,6 +29,7 @@ rows = list(csv.reader(raw.splitlines()))
 hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
 hdr = rows[hi]
 ai, ci, si, ti = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+srci = hdr.index("Source") if "Source" in hdr else None      # the report's own SASS text (reliable for opcodes)
 base = int(rows[hi + 1][ai], 16)
 agg = collections.defaultdict(lambda: [0, 0, 0])
 ops = collections.defaultdict(int)
@@ -41,7 +43,10 @@ for r in rows[hi + 1:]:
     for k in range(3):
         agg[key][k] += v[k]
         tot[k] += v[k]
-    ops[sass.split()[0].split(".")[0] if sass != "?" else "?"] += v[0]
+    if srci is not None and len(r) > srci and r[srci].strip():
+        sass = r[srci].strip()
+    toks = [t for t in sass.split() if not t.startswith("@")]
+    ops[toks[0].split(".")[0] if toks and sass != "?" else "?"] += v[0]
 print(f"total warp-inst {tot[0]}  thread-inst {tot[2]}  samples {tot[1]}")
 src_cache = {}
 def src(key):
