@@ -207,6 +207,14 @@ def main():
     import numpy as np
     import torch
     import pimc_jl_b200 as pj
+    trace_on = os.environ.get("PIMC_BENCH_TRACE") is not None
+
+    def trace(msg):
+        if trace_on:
+            print(f"[bench rank {rank} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+    if trace_on:
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("PIMC_BENCH_TRACE") or 90), exit=False, file=sys.stderr)
     from pimc_jl_b200 import _lib as L, engine as eng
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -228,6 +236,7 @@ def main():
         engine_.comm_init(world, rank, ids[0])
     if dist is not None:
         attach_comm(e)
+    trace('engine + communicator ready')
     if args.faithful_impl:
         e.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
     use_density = wl["measure"] == "density"
@@ -239,6 +248,7 @@ def main():
     stream = torch.cuda.current_stream()
     e.set_stream(stream.cuda_stream)
     e.run(args.therm, ups, sched=SCHED)  # thermalisation: adaptive slice count / step settle
+    trace('thermalised')
 
     def block_read(n_before, engine_=None, obj=None):
         """the step's estimator block.  With N > 1 GPUs the library has all-reduced it itself (ncclAllReduce on its side stream, queued at the
@@ -261,6 +271,7 @@ def main():
     for _ in range(args.warmup):
         e.run(args.iters, ups, sched=SCHED, **mkw)
         _, n_seen = block_allreduce(n_seen)
+    trace('warm-up done')
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -289,6 +300,7 @@ def main():
     ms, kern_ms, total_bm = float(t[0]), float(t[1]), float(tot[0])
     value = total_bm / (ms * 1e-3)
 
+    trace('device-resident arm done')
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----
     # The public API as a user with pinned host buffers drives it, double-buffered: TWO Systems of the full batch (two handles, two streams, two
     # host threads -- the library is synchronous per handle) take the steps alternately, so the H2D / D2H copies of one batch overlap the moves
@@ -311,6 +323,7 @@ def main():
         hk = torch.empty((Cc, wl["N"], wl["dim"], wl["M"]), dtype=torch.float64).pin_memory().numpy()
         ek.get_r_into(hk)
         halves.append(dict(e=ek, ups=uk, obj=ok, host=hk, stream=sk, mkw=dict(densities=[ok]) if use_density else dict(energies=[ok]), seen=0, bm=0, blk=None))
+    trace('e2e buffers ready')
     turn = [0]
     cv = threading.Condition()
     errors = []
@@ -342,6 +355,7 @@ def main():
     [w.join() for w in workers]
     barrier()
     t_e2e = time.perf_counter() - t0
+    trace('e2e arm done')
     if errors:
         raise errors[0]
     e2e_bm = sum(hf["bm"] for hf in halves)
@@ -357,10 +371,6 @@ def main():
     d2h = per * Cc * 8 + (8 * wl["nbins"] ** wl["dim"] if use_density else 2 * 8 * (args.iters // wl["Ncycle"]))
     comm_info = e.comm_info()
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
     hbm, how = peaks()
     # dominant kernel: k_sweep (one launch per iteration: staging-bridge + centre-of-mass sweeps of every chain).  Its own launch time
     # is measured live on a moves-only leg (no estimator launches in between): achieved = algorithmic bytes per launch / avg launch time.
@@ -393,6 +403,19 @@ def main():
             by_family["measure"] = {"launch_ms_marginal": ms_meas, "alg_bytes_per_launch": bytes_meas, "achieved": bytes_meas / (ms_meas * 1e-3) / 1e9,
                                     "frac": bytes_meas / (ms_meas * 1e-3) / 1e9 / hbm,
                                     "note": "marginal cost of one measurement event inside the step (fused Energy sums ride on the centre-of-mass sweep)"}
+    trace('family legs done')
+    # (every rank runs the legs above: a measured run queues the library's all-reduce of its Energy block, which all ranks must join)
+    # tear the communicators down in the same order on every rank (ncclCommDestroy waits for its peers), before rank 0 goes on alone
+    barrier()
+    for hf in halves:
+        hf["e"].close()
+    e.close()
+    if dist is not None:
+        dist.destroy_process_group()
+        dist = None
+    trace('communicators closed')
+    if rank != 0:
+        return
     fp64 = C.c_double(0.0)
     lib.pimc_measure_fp64_peak(C.byref(fp64))
     traffic = None

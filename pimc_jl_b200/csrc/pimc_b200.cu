@@ -1195,6 +1195,7 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
         for (int i = 0; i < nupd; ++i) SP2.upd[i] = h->T.upd[update_ids[i]];
         // Energy fused into the sweep launch of a measurement iteration (chains whose centre-of-mass sweep streams every worldline anyway)
         const bool fuse_ok = nen > 0 && has_com && h->opt_fuse_energy != 0;
+        const bool separate_swap = getenv("PIMC_SEPARATE_SWAP") != nullptr;
         if (fuse_ok && !h->mdone) { int rc = dalloc(h, &h->mdone, (size_t)S.C); if (rc) return rc; }
         // chain-major persistent kernel (pimc_chain.cuh): one launch for the whole call, every CTA takes a chain through all n iterations
         // (measured on C2, profiles/r02_summary.md: 5.2e10 against 6.0e10 bead-moves/s of the per-iteration kernels -- the resident chains' 116 MB do
@@ -1223,8 +1224,13 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
             MP.ord = ctrv / h->cfg.Ncycle - 1;
             SP2.sp = SP; SP2.fuse = meas_now && fuse_ok; SP2.mp = MP; SP2.mdone = h->mdone;
             if (SP2.fuse) CK(h, cudaMemsetAsync(h->mdone, 0, (size_t)S.C, h->stream));
-            if (has_com || has_rs) { CK(h, pimc_launch_sweep(S.C, (smem_rs > smem_cs ? smem_rs : smem_cs) + smem_pad, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
-            if (has_swap) { CK(h, pimc_launch_swap_iter(S.C, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
+            // chains that picked the swap move run their one proposal on warp 0 of their k_sweep CTA; the stand-alone swap kernel is
+            // launched only when no sweep family is listed (or for the A/B: PIMC_SEPARATE_SWAP=1)
+            size_t smem_sw = smem_rs > smem_cs ? smem_rs : smem_cs;
+            if (has_swap && swap_smem_bytes(S.N, S.M) > smem_sw) smem_sw = swap_smem_bytes(S.N, S.M);
+            SP2.swap_in_sweep = (has_swap && (has_com || has_rs) && smem_sw <= 200 * 1024 && !separate_swap) ? 1 : 0;
+            if (has_com || has_rs) { CK(h, pimc_launch_sweep(S.C, smem_sw + smem_pad, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
+            if (has_swap && !SP2.swap_in_sweep) { CK(h, pimc_launch_swap_iter(S.C, h->stream, S, h->dT, SP2)); LAUNCHED(); launches++; }
             if (meas_now) { CK(h, pimc_launch_measure(S.C, h->stream, S, h->dT, MP, SP2.fuse ? h->mdone : nullptr)); LAUNCHED(); launches++; }
         }
     }

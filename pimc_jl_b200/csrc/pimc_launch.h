@@ -25,7 +25,7 @@ struct MeasParams { int tma; int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC
 // on the prologue or the bookkeeping tail of a CTA (measured: +24 % on the centre-of-mass half, 2x at N = 1024).
 // fuse: the sweep launch of a measurement iteration also evaluates the Energy functor for the chains whose picked update streamed
 // every worldline anyway (centre-of-mass sweep of a chain without exchange cycles); mdone[c] = 1 tells k_measure to skip that chain.
-struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; double *fscr; };
+struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; double *fscr; int swap_in_sweep; };
 
 __host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
 __host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }

@@ -585,21 +585,6 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
     if (warp == 0) d_bookkeep_sweep_warp(U, c, flag, N, s_bead, P.stats, s_pre);
 }
 
-// One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
-template <int POT, int KM, bool FUSE>
-__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(const __grid_constant__ DevSys S, const DevTables *__restrict__ T,
-                                                                                                   const __grid_constant__ Sweep2Params P2)
-{
-    const int c = blockIdx.x;
-    const SweepParams &P = P2.sp;
-    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
-    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
-    const int pick = d_pick_update(P, di);
-    const int kind = P.kind[pick];
-    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap, c);
-    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, FUSE>(S, P2.upd[pick], P, st, pick, P2, T, c);
-}
-
 // The swap move stays one proposal per chain and iteration (reshape.jl:123-283): one warp per chain.  Everything that touches
 // memory or a transcendental runs across the lanes (weight table of sampleparticles, Gaussians of the two bridges, potentials, commit,
 // tail exchange); the two staging recurrences run on four lanes (bridge x dim); every SUM keeps the sequential order of the
@@ -760,6 +745,25 @@ static __global__ void __launch_bounds__(32) k_swap_iter(const __grid_constant__
     const int pick = d_pick_update(P, di);
     if (P.kind[pick] != PIMC_UPD_RESHAPE_SWAP) return;
     d_swap_iter_body(S, P2, st, pick, c, sm);
+}
+
+// One launch per iteration: every CTA (= chain) picks its update (simulation.jl:33-37) and runs that family's sweep.
+template <int POT, int KM, bool FUSE>
+__global__ void __launch_bounds__(SWEEP_THREADS, (KM <= 4 ? 1024 : 768) / SWEEP_THREADS) k_sweep(const __grid_constant__ DevSys S, const DevTables *__restrict__ T,
+                                                                                                   const __grid_constant__ Sweep2Params P2)
+{
+    const int c = blockIdx.x;
+    const SweepParams &P = P2.sp;
+    pimc_stream st = pimc_stream_make(S.seed, S.chain_offset + c, P.iter);
+    pimc_u4 di = pimc_draw_rk(st, &P.rk, PIMC_SLOT_CHAIN, PIMC_K_ITER, 0, 0);
+    const int pick = d_pick_update(P, di);
+    const int kind = P.kind[pick];
+    if (kind == PIMC_UPD_RESHAPE_LINEAR) d_reshape_sweep_body<POT>(S, P2.upd[pick], P, st, di, pick, P2.cap, c);
+    else if (kind == PIMC_UPD_SINGLE_COM || kind == PIMC_UPD_POLYMER_COM) d_com_sweep_body<POT, KM, FUSE>(S, P2.upd[pick], P, st, pick, P2, T, c);
+    else if (kind == PIMC_UPD_RESHAPE_SWAP && P2.swap_in_sweep && (threadIdx.x >> 5) == 0) {   // the one swap proposal of this chain, on warp 0: no second launch per iteration
+        extern __shared__ double sm_swap[];
+        d_swap_iter_body(S, P2, st, pick, c, sm_swap);
+    }
 }
 
 // Energy functor (measurement.jl:92-122) with one warp per worldline (lanes stride the slices: coalesced, no index division)
