@@ -426,7 +426,9 @@ def main():
         if tj.get("workload") == args.workload and tj.get("chains") == Cc:
             traffic = tj.get("k_sweep_dram_bytes_per_launch")
     whole = total_bm / world / (kern_ms * 1e-3)            # moves + estimator kernels, per GPU
-    roofline = {"bound": "hbm", "kernel": "k_run" if st_mv["launches"] == 1 else "k_sweep", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+    big = Cc * wl["N"] * wl["M"] >= 2 ** 20
+    kname = "k_sweep" if st_mv["launches"] > 1 else ("k_run_cells" if wl.get("interactions") else ("k_chain" if (big and not faithful) else "k_run"))
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json ({how})", "alg_bytes_per_bead_move": B_ALG,
                 "alg_bytes_per_launch": sweep_bytes, "launch_ms": sweep_ms, "by_family": by_family,
                 "traffic_source": "committed ncu --set full capture (profiles/traffic.json), not measured in this run" if traffic is not None else None,

@@ -95,8 +95,8 @@ int  pimc_version(void);
 int  pimc_set_stream(pimc_handle *h, void *cuda_stream);                /* run kernels on this cudaStream_t   */
 /* engine options (no reference counterpart). PIMC_OPT_SWEEP_IMPL (sweep schedule, independent worldlines): 0 auto, 1 persistent kernel of the
  * reference-schedule bodies (k_run), 2 per-iteration sweep kernels (k_sweep + k_swap_iter + k_measure), 3 chain-major persistent sweep kernel
- * (k_chain: every CTA takes a chain through all iterations of the call; measured slower than 2 on B200, kept selectable); the auto choice
- * is 2 for batches of >= 2^20 beads and 1 below.  Identical trajectories. */
+ * (k_chain: every CTA takes a chain through all iterations of the call).  Auto: below 2^20 beads 1; above, 3 when the chains fill at most two
+ * rounds of CTA slots (measured faster there) and 2 for larger batches (measured faster there).  Identical trajectories. */
 #define PIMC_OPT_SWEEP_IMPL 1
 /* PIMC_OPT_FAITHFUL_IMPL: proposals of the reference schedule: 0 warp-cooperative (default), 1 one thread per proposal (A/B, same bits) */
 #define PIMC_OPT_FAITHFUL_IMPL 2

@@ -1198,10 +1198,13 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
         const bool separate_swap = getenv("PIMC_SEPARATE_SWAP") != nullptr;
         if (fuse_ok && !h->mdone) { int rc = dalloc(h, &h->mdone, (size_t)S.C); if (rc) return rc; }
         // chain-major persistent kernel (pimc_chain.cuh): one launch for the whole call, every CTA takes a chain through all n iterations
-        // (measured on C2, profiles/r02_summary.md: 5.2e10 against 6.0e10 bead-moves/s of the per-iteration kernels -- the resident chains' 116 MB do
-        //  not stay in the two 63 MB L2 partitions, and the in-kernel estimator pass loses the all-SMs streaming pattern of k_measure -- so the
-        //  automatic choice stays per-iteration; the kernel is kept selectable)
-        const bool chain_major = h->opt_sweep_impl == 3 || (h->opt_sweep_impl == 0 && getenv("PIMC_CHAIN_MAJOR") != nullptr);
+        // Automatic choice, from the measurements of profiles/r02_summary.md: the persistent kernel wins when the chains fill at most two
+        // rounds of CTA slots (C3 1024 chains: 3.1e10 vs 2.7e10; C5 512 chains: 4.3e10 vs 3.7e10 -- no partly filled waves, no launch gaps),
+        // the per-iteration kernels win for large batches (C2 4096 chains: 6.0e10 vs 5.2e10 -- the resident chains' 116 MB do not stay in the
+        // two 63 MB L2 partitions, and the in-kernel estimator pass loses the all-SMs streaming pattern of k_measure; C4 2.3 rounds: 1.37e10 vs 1.28e10)
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const int slots = sms * ((S.M + 31) / 32 <= 4 ? 4 : 3);
+        const bool chain_major = h->opt_sweep_impl == 3 || (h->opt_sweep_impl == 0 && (getenv("PIMC_CHAIN_MAJOR") != nullptr || (S.C <= 2 * slots && getenv("PIMC_NO_CHAIN_MAJOR") == nullptr)));
         if (chain_major) {
             if (!h->queue) { int rc = dalloc(h, &h->queue, 4); if (rc) return rc; }
             CK(h, cudaMemsetAsync(h->queue, 0, sizeof(int), h->stream));

@@ -546,14 +546,14 @@ def test_c2_default_dispatch_at_bench_scale_vs_oracle(oracle):
     ob = oracle
     cfg, spec, measure, n_it = BASELINE_SHAPES["C2"]
     out = []
-    for impl, fuse in ((0, 0), (0, 1), (3, 0)):   # default dispatch = per-iteration kernels, without and with the fused Energy; chain-major kernel
+    for impl, fuse in ((0, 0), (2, 1), (2, 0)):   # default dispatch (chain-major at this batch size); per-iteration kernels with and without the fused Energy
         e = pj.Engine(pots(ob)["zero"][1], chains=128, L_=cfg["L"], dim=2, M=128, N=64, T=1.0, lam=1.0, Ncycle=2, seed=7)
         e.set_option(L.OPT_SWEEP_IMPL, impl)
         e.set_option(L.OPT_FUSE_ENERGY, fuse)
         ge = [(every, e.update_create(kind, v0)) for every, kind, v0 in spec]
         e._test_en = e.energy_create(64)
         st = e.run(n_it, ge, energies=[e._test_en], sched=L.SCHED_SWEEP)
-        assert st["launches"] == 1 if impl == 3 else st["launches"] >= n_it
+        assert st["launches"] == 1 if impl == 0 else st["launches"] >= n_it   # 128 chains fill less than two rounds of CTA slots: auto = chain-major
         _check_against_oracle(ob, e, ge, spec, cfg, [0, 37, 127], "energy", n_it, 7)
         out.append((e.paths(want=("r",))[0], e.energy_read(e._test_en, -1)[0]))
     for o in out[1:]:
