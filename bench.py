@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--sched", default="", choices=["", "faithful", "sweep"], help="override the workload's schedule (side measurements)")
     ap.add_argument("--faithful-impl", type=int, default=0, help="reference-schedule proposals: 0 warp-cooperative (default), 1 one thread (A/B)")
     ap.add_argument("--cpu-iters", type=int, default=0)
+    ap.add_argument("--isweep", type=int, default=-1, help="interacting sweep schedule: 0 sequential kernel (library default), 1 adaptive, 2 optimistic kernels (side measurements)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.sched:
@@ -239,6 +240,8 @@ def main():
     trace('engine + communicator ready')
     if args.faithful_impl:
         e.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
+    if args.isweep >= 0:
+        e.set_option(L.OPT_ISWEEP, args.isweep)
     use_density = wl["measure"] == "density"
     kind = {"com": L.UPD_SINGLE_COM, "reshape": L.UPD_RESHAPE_LINEAR, "swap": L.UPD_RESHAPE_SWAP, "pcom": L.UPD_POLYMER_COM}
     ups = [(every, e.update_create(kind[k], v0)) for k, every, v0 in wl["updates"]]
@@ -313,6 +316,8 @@ def main():
                        T=wl["T"], lam=wl["lam"], Ncycle=wl["Ncycle"], seed=1 + 1000 * (k + 1), device=local_rank, **interaction_args(wl))
         if args.faithful_impl:
             ek.set_option(L.OPT_FAITHFUL_IMPL, args.faithful_impl)
+        if args.isweep >= 0:
+            ek.set_option(L.OPT_ISWEEP, args.isweep)
         sk = torch.cuda.Stream()
         ek.set_stream(sk.cuda_stream)
         if dist is not None:
@@ -383,7 +388,7 @@ def main():
     # per-family legs (after every timed region; they perturb nothing that is reported above): one update family alone, moves only, and the
     # estimator launch as the difference between a measured and an unmeasured run of the same moves
     by_family = {}
-    if not faithful:
+    if not faithful and not wl.get("interactions"):   # (one move family alone on a hard-core system spins in the reference's retry loops: not a throughput figure)
         fam_iters = max(8, args.iters // 4)
         for (kk, every, v0), (_, uid) in zip(wl["updates"], ups):
             lf = lib.pimc_launch_count()
