@@ -7,7 +7,7 @@
 # example tools read (s.N, s.M, s.L, s.β, s.τ, s.μ, s.a, s.Ncycle, s.N_MC, s.world[n].{r,V,bins,next}, s.nn, s.nbs, s.lnV/lnK/lnU,
 # u.var.size/m, u.counter_var.queue, d.dens ...).
 #
-# Environment: PIMC_B200_LIB (path of the .so), PIMC_CHAINS (independent replicas, default 1), PIMC_SEED,
+# Environment: PIMC_B200_LIB (path of the .so), PIMC_CHAINS (independent replicas, default 1), PIMC_CHAIN_OFFSET (first global chain of this worker), PIMC_SEED,
 #              PIMC_SCHED = "faithful" (default: exactly run!) | "sweep" (batched schedule, DESIGN.md section 3).
 module Pimc
 
@@ -135,7 +135,7 @@ mutable struct System
             # Note the shipped script never forwards g (examples/density_SRL_lattice.jl:18-19): g = 0.0 => a = exp(-2π/0.0) = 0.0 (system.jl:151),
             # no hard core, the interaction enters through lnU only -- reproduced as is.
         end
-        cfg = Ref(CConfig(dim, M, N, chains, 0, μ, λ, L, T, interactions, g, rₐ, length_measurement_cycle, 15, 1, seed, pot,
+        cfg = Ref(CConfig(dim, M, N, chains, parse(UInt32, get(ENV, "PIMC_CHAIN_OFFSET", "0")), μ, λ, L, T, interactions, g, rₐ, length_measurement_cycle, 15, 1, seed, pot,
                           isempty(tab) ? C_NULL : pointer(tab), size(tab, 1), lo, hi, -1))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve tab check(C_NULL, ccall((:pimc_create, LIB), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
@@ -203,6 +203,26 @@ function nn_lists(s::System; chain::Integer = 0)
     end
     nn
 end
+# ---- multi-GPU: one worker per GPU (the scripts' `addprocs` + `pmap`, examples/density_SRL_lattice.jl:1-2,46) -------------------------------
+# Build every worker's System with `chains` = its share and ENV["PIMC_CHAIN_OFFSET"] = first global chain, create the id on one worker, ship it
+# (e.g. `remotecall_fetch`) and attach: afterwards `mea.energy[N]`, `d.dens`, `d.ndata` are reduced over all workers inside the library
+# (ncclAllReduce on a side stream, per measurement block).  Every worker must issue the same read-outs in the same order.
+function comm_unique_id()::Vector{UInt8}
+    id = zeros(UInt8, 128)
+    check(C_NULL, ccall((:pimc_comm_get_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id
+end
+comm_init!(s::System, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(s.h, ccall((:pimc_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), s.h, nranks, rank, id))
+# complete chain state (resumes bit for bit): checkpoint(s) -> Vector{UInt8}; restore!(s2, blob) on a System built with the same arguments and objects
+function checkpoint(s::System)::Vector{UInt8}
+    n = Ref{Int64}(0)
+    check(s.h, ccall((:pimc_state_size, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), s.h, n))
+    buf = Vector{UInt8}(undef, n[])
+    check(s.h, ccall((:pimc_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), s.h, buf, n[]))
+    buf
+end
+restore!(s::System, buf::Vector{UInt8}) = check(s.h, ccall((:pimc_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), s.h, buf, length(buf)))
 update_nnbins!(s::System) = check(s.h, ccall((:pimc_update_nnbins, LIB), Cint, (Ptr{Cvoid},), s.h))
 
 # ---- updates (src/updates/helper.jl:6-52, com.jl, reshape.jl) -------------------------------------------------------------

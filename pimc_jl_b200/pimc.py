@@ -215,7 +215,7 @@ class Energy:                       # src/measurement.jl:78-122
         E, Ev, cnt = self.s.engine.energy_read(self.id, -1)
         if cnt > self.n:
             raise IndexError("Energy: the pre-sized vector is full (reference: findfirst(ismissing, ...) is nothing)")
-        if _dist() is not None:
+        if _dist() is not None and not self.s.library_comm:     # (with the library's communicator the values are global already)
             E = chain_mean_over_ranks(E, self.s.engine.C)
             Ev = chain_mean_over_ranks(Ev, self.s.engine.C)
         return E, Ev
@@ -246,7 +246,7 @@ class Density:                      # src/measurement.jl:31-55
 
     def _read(self):
         d, nd, b = self.s.engine.density_read(self.id, self.nbins)
-        if _dist() is not None:
+        if _dist() is not None and not self.s.library_comm:
             d = allreduce_sum(d)
             nd = int(allreduce_sum(np.array([float(nd)]))[0])
         return d, nd
@@ -353,6 +353,14 @@ class System:                       # src/system.jl:93-168
                              interactions=interactions, g=g, r_a=r_a, Ncycle=length_measurement_cycle, compat=compat, seed=seed,
                              tab=tab, tab_lo=tab_lo or 0.0, tab_hi=tab_hi or 1.0, device=device)
         e = self.engine
+        # multi-GPU: with an NCCL process group the library's own communicator is attached (one rank per process), so that the estimator
+        # read-outs below are reduced inside the library (side stream, no host bounce); other backends (gloo on CPU hosts) keep the host reduction
+        self.library_comm = False
+        if dist is not None and world > 1 and dist.get_backend() == "nccl":
+            ids = [_eng.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            e.comm_init(world, rank, ids[0])
+            self.library_comm = True
         self.dim, self.M, self.N, self.Ninit, self.mu, self.lam, self.L = dim, M, N, N, mu, lam, L
         self.beta, self.tau, self.vol, self.a, self.nbins = e.beta, e.tau, (2 * L) ** dim, e.a, e.nbins
         self.Ncycle, self.measure_scheme, self.chains = length_measurement_cycle, measure_scheme, chains

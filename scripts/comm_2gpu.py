@@ -45,4 +45,30 @@ for a, b in ((got[0], ref[0]), (got[1], ref[1]), (got[2], ref[2])):
 assert np.array_equal(got[4], ref[4]) and got[5] == ref[5]
 print(f"rank {rank}/{world}: library communicator ok (nccl {info['nccl_version']}), global Energy blocks and density equal the single-GPU run", flush=True)
 dist.barrier()
+
+# ---- the same through the host-side mirror of the reference API (pimc.System under torchrun attaches the library communicator itself) ----
+import pimc_jl_b200.pimc as P
+kwm = dict(dV="identity", dim=2, M=32, N=8, L=4.0, T=1.0, lam=0.5, length_measurement_cycle=2, seed=11, schedule="sweep", device=lr)
+
+
+def run_mirror(s):
+    ups = [(1, P.SingleCenterOfMass(s, 1.0)), (1, P.ReshapeLinear(s, 6))]
+    en, de = P.Energy(s, 128), P.Density(s, nbins=24)
+    P.run_b(s, 40, ups, Zmeasurements=[en, de])
+    return en.energy[s.N], de.dens, de.ndata
+
+
+s = P.System(P.harmonic(), chains=Ctot, **kwm)               # sharded over the ranks
+assert s.library_comm and s.engine.C == cnt
+Em, dm, ndm = run_mirror(s)
+dist.barrier()
+ref_s = pj.Engine(pj.make_potential("harmonic", "identity"), chains=Ctot, chain_offset=0, device=lr, dim=2, M=32, N=8, T=1.0, lam=0.5, Ncycle=2, seed=11, L_=4.0)
+ur = [(1, ref_s.update_create(L.UPD_SINGLE_COM, 1.0)), (1, ref_s.update_create(L.UPD_RESHAPE_LINEAR, 6))]
+er, dr = ref_s.energy_create(128), ref_s.density_create(24)
+ref_s.run(40, ur, energies=[er], densities=[dr], sched=L.SCHED_SWEEP)
+assert np.allclose(Em, ref_s.energy_read(er, -1)[0], rtol=1e-13, atol=0) and np.array_equal(dm, ref_s.density_read(dr, 24)[0]) and ndm == ref_s.density_read(dr, 24)[1]
+print(f"rank {rank}/{world}: pimc.System mirror with the library communicator ok", flush=True)
+dist.barrier()
+s.engine.close()
+e.close()
 dist.destroy_process_group()
