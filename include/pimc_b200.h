@@ -187,8 +187,7 @@ int pimc_density_measure(pimc_handle *h, int32_t id);                   /* Densi
 int pimc_density_read(pimc_handle *h, int32_t id, double *dens, int64_t *ndata, double *bin);
 
 /* ---- estimators the reference lists as TODO (src/measurement.jl:125-127 `#TODO radial distribution`, `#TODO Superfluid Fraction`), written in the
- *      style of its functors (the CPU checker under tests/ restates the same definitions).  (`#TODO Compressibilty` needs particle-number fluctuations, i.e. the
- *      grand-canonical worm sector the reference never shipped: not provided.)
+ *      style of its functors (the CPU checker under tests/ restates the same definitions).
  *  g(r): per measurement, for every slice and every pair i < j, ib = floor(|distance.(r_i, r_j, L)| / (rmax / nbins)); hist[ib] += 1 if
  *        ib < nbins; ndata += M.   g(r_b) = hist[b] * vol / (ndata * N (N - 1) / 2 * shell_b) at read-out.
  *  winding: W_k = (1 / 2L) * sum over links of teleport(r_next[k] - r[k], L), an integer for closed paths; superfluid fraction
@@ -200,12 +199,23 @@ int pimc_winding_create(pimc_handle *h, int64_t cap, int32_t *id);
 int pimc_winding_now(pimc_handle *h, double *W /* [chains][dim] */);
 /* chain >= 0: out[n][dim] that chain's series; chain = -1: out[n] = mean over this handle's chains of W^2 per measurement */
 int pimc_winding_read(pimc_handle *h, int32_t id, int32_t chain, double *out, int64_t cap, int64_t *n);
+/* `#TODO Compressibilty` (src/measurement.jl:127), canonical ensemble: static structure factor on the wave vectors of the periodic box,
+ *  k = (pi / L)(a, b), a = 0..kmax, |b| <= kmax (half plane a > 0, or a = 0 and b > 0; 1-D: b = 0, a >= 1), kmax <= 6.  Per measurement and slice m:
+ *  rho_k(m) = sum_n exp(i k . r_n[m, :]); sums[a * (2 kmax + 1) + b + kmax] += |rho_k(m)|^2; ndata += M.  S(k) = sums / (ndata * N).
+ *  Compressibility from the long-wavelength limit S(k -> 0) = rho k_B T kappa_T on the smallest shell |k| = pi / L:
+ *  kappa_T = beta * S(k_min) / rho, rho = N / (2L)^dim (a finite-size estimate; a number-fluctuation estimator would need the grand-canonical
+ *  worm sector the reference never shipped). */
+int pimc_structure_create(pimc_handle *h, int32_t kmax, int32_t *id);
+int pimc_structure_measure(pimc_handle *h, int32_t id);                                        /* functor call now, every chain */
+int pimc_structure_read(pimc_handle *h, int32_t id, double *sums, int64_t *ndata, int32_t *kmax); /* summed over chains (and ranks) */
+int pimc_compressibility(pimc_handle *h, int32_t id, double *kappa, double *s_kmin);
 /* run! with the full Zmeasurements list (src/simulation.jl:29-42): pimc_run plus the estimators above, same cadence */
 typedef struct {
     const int32_t *energy_ids; int32_t nenergy;
     const int32_t *density_ids; int32_t ndensity;
     const int32_t *paircorr_ids; int32_t npaircorr;
     const int32_t *winding_ids; int32_t nwinding;
+    const int32_t *structure_ids; int32_t nstructure;
 } pimc_measurements;
 int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
                 const pimc_measurements *meas, int32_t sched, pimc_run_stats *stats);

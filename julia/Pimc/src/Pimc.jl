@@ -19,6 +19,7 @@ export subcycle, pcycle, Update, Updates
 export Counter, Step, NumbOfSlices
 export SingleCenterOfMass, PolymerCenterOfMass, ReshapeLinear, ReshapeSwapLinear
 export Density, Measurement, ZMeasurement, Energy
+export PairCorrelation, Winding, superfluid_fraction, StructureFactor, compressibility   # the TODOs of src/measurement.jl:125-127
 
 const LIB = get(ENV, "PIMC_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "pimc_jl_b200", "libpimc_b200.so"))
 
@@ -318,14 +319,94 @@ function Base.getproperty(d::Density, f::Symbol)
 end
 (d::Density)(s::System) = check(s.h, ccall((:pimc_density_measure, LIB), Cint, (Ptr{Cvoid}, Int32), s.h, d.id))
 
+# ---- the estimators src/measurement.jl:125-127 lists as TODO, in the style of the functors above ---------------------------
+struct PairCorrelation <: ZMeasurement                                  # `#TODO radial distribution`
+    s::System; id::Int32; nbins::Int64; rmax::Float64; bin::Float64
+    function PairCorrelation(s::System; nbins = 200, rmax = s.L)
+        id = Ref{Int32}(0)
+        check(s.h, ccall((:pimc_paircorr_create, LIB), Cint, (Ptr{Cvoid}, Int64, Float64, Ref{Int32}), s.h, nbins, rmax, id))
+        new(s, id[], nbins, rmax, rmax / nbins)
+    end
+end
+function Base.getproperty(g::PairCorrelation, f::Symbol)
+    if f === :hist || f === :ndata || f === :g
+        s = getfield(g, :s); nb = getfield(g, :nbins); bin = getfield(g, :bin)
+        hist = zeros(Float64, nb); nd = Ref{Int64}(0); b = Ref(0.0)
+        check(s.h, ccall((:pimc_paircorr_read, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{Int64}, Ref{Float64}), s.h, getfield(g, :id), hist, nd, b))
+        f === :hist && return hist
+        f === :ndata && return nd[]
+        edges = (0:nb) .* bin
+        shell = s.dim == 2 ? π .* (edges[2:end] .^ 2 .- edges[1:end-1] .^ 2) : fill(2 * bin, nb)
+        return hist ./ max.(nd[] * s.N * (s.N - 1) / 2 .* shell ./ s.vol, 1e-300)
+    end
+    return getfield(g, f)
+end
+(g::PairCorrelation)(s::System) = check(s.h, ccall((:pimc_paircorr_measure, LIB), Cint, (Ptr{Cvoid}, Int32), s.h, g.id))
+
+struct Winding <: ZMeasurement                                          # `#TODO Superfluid Fraction`
+    s::System; id::Int32; n::Int64
+    function Winding(s::System, n = 20_000)
+        id = Ref{Int32}(0)
+        check(s.h, ccall((:pimc_winding_create, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Int32}), s.h, n, id))
+        new(s, id[], n)
+    end
+end
+function winding_W2(w::Winding)::Vector{Float64}                        # chain-mean of W^2 per measurement
+    s = w.s; cnt = Ref{Int64}(0); out = Vector{Float64}(undef, w.n)
+    check(s.h, ccall((:pimc_winding_read, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Ref{Int64}), s.h, w.id, -1, out, w.n, cnt))
+    return out[1:min(cnt[], w.n)]
+end
+# rho_s / rho = <W^2> (2L)^2 / (2 dim lambda beta N)  (Pollock & Ceperley, PRB 36, 8343)
+superfluid_fraction(w::Winding) = (W2 = winding_W2(w); isempty(W2) ? NaN : sum(W2) / length(W2) * (2 * w.s.L)^2 / (2 * w.s.dim * w.s.λ * w.s.β * w.s.N))
+
+struct StructureFactor <: ZMeasurement                                  # `#TODO Compressibilty`
+    s::System; id::Int32; kmax::Int32
+    function StructureFactor(s::System; kmax = 4)
+        id = Ref{Int32}(0)
+        check(s.h, ccall((:pimc_structure_create, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}), s.h, kmax, id))
+        new(s, id[], kmax)
+    end
+end
+function Base.getproperty(k::StructureFactor, f::Symbol)
+    if f === :S || f === :ndata
+        s = getfield(k, :s); km = Int(getfield(k, :kmax))
+        sums = zeros(Float64, 2km + 1, km + 1); nd = Ref{Int64}(0); kk = Ref{Int32}(0)      # column-major: sums[b + km + 1, a + 1]
+        check(s.h, ccall((:pimc_structure_read, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{Int64}, Ref{Int32}), s.h, getfield(k, :id), sums, nd, kk))
+        return f === :ndata ? nd[] : sums ./ max(1, nd[] * s.N)      # S(k) at k = (π / L)(a, b)
+    end
+    return getfield(k, f)
+end
+(k::StructureFactor)(s::System) = check(s.h, ccall((:pimc_structure_measure, LIB), Cint, (Ptr{Cvoid}, Int32), s.h, k.id))
+function compressibility(k::StructureFactor)::Float64                   # κ_T = β S(k_min) / ρ on the smallest shell of the box
+    κ = Ref(0.0); s0 = Ref(0.0)
+    check(k.s.h, ccall((:pimc_compressibility, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}, Ref{Float64}), k.s.h, k.id, κ, s0))
+    return κ[]
+end
+
+struct CMeasurements                                                    # pimc_measurements (include/pimc_b200.h)
+    energy_ids::Ptr{Int32}; nenergy::Int32; density_ids::Ptr{Int32}; ndensity::Int32
+    paircorr_ids::Ptr{Int32}; npaircorr::Int32; winding_ids::Ptr{Int32}; nwinding::Int32
+    structure_ids::Ptr{Int32}; nstructure::Int32
+end
+
 # ---- run! (src/simulation.jl:29-42) ----------------------------------------------------------------------------------------
 function run!(s::System, n::Int64, updates; Zmeasurements = ZMeasurement[], sched::Int32 = s.sched)::Nothing
     ids = Int32[u.id for (_, u) in updates]; every = Int64[e for (e, _) in updates]
     en = Int32[m.id for m in Zmeasurements if m isa Energy]; de = Int32[m.id for m in Zmeasurements if m isa Density]
+    pc = Int32[m.id for m in Zmeasurements if m isa PairCorrelation]; wi = Int32[m.id for m in Zmeasurements if m isa Winding]
+    sk = Int32[m.id for m in Zmeasurements if m isa StructureFactor]
     st = RunStats()
-    GC.@preserve ids every en de check(s.h, ccall((:pimc_run, LIB), Cint,
-        (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Ref{RunStats}),
-        s.h, n, ids, every, length(ids), en, length(en), de, length(de), sched, st))
+    if isempty(pc) && isempty(wi) && isempty(sk)
+        GC.@preserve ids every en de check(s.h, ccall((:pimc_run, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Ref{RunStats}),
+            s.h, n, ids, every, length(ids), en, length(en), de, length(de), sched, st))
+    else
+        GC.@preserve ids every en de pc wi sk begin
+            z = CMeasurements(pointer(en), length(en), pointer(de), length(de), pointer(pc), length(pc), pointer(wi), length(wi), pointer(sk), length(sk))
+            check(s.h, ccall((:pimc_run_ex, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int64}, Int32, Ref{CMeasurements}, Int32, Ref{RunStats}),
+                             s.h, n, ids, every, length(ids), z, sched, st))
+        end
+    end
     nothing
 end
 

@@ -966,6 +966,31 @@ void ora_winding_now(const ora_system *s, double *W)
         W[k - 1] = acc / (2 * s->L);
     }
 }
+/* Static structure factor (`#TODO Compressibilty`, measurement.jl:127): for the wave vectors of the periodic box k = (pi / L) (a, b),
+ * a = 0..kmax, b = -kmax..kmax (the half plane a > 0, or a = 0 and b > 0; 1-D: b = 0, a = 1..kmax), and every time slice m:
+ * rho_k(m) = sum_n exp(i k . r_n[m, :]);  out[a * (2 kmax + 1) + (b + kmax)] = sum_m |rho_k(m)|^2 (entries outside the half plane stay 0).
+ * S(k) = <|rho_k|^2> / N at read-out (ndata += M per call, the convention of Density, measurement.jl:54); the isothermal compressibility follows
+ * from the long-wavelength limit S(k -> 0) = rho k_B T kappa_T, estimated on the smallest shell |k| = pi / L. */
+void ora_structure_now(const ora_system *s, int kmax, double *out)
+{
+    const int nb = 2 * kmax + 1;
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < (kmax + 1) * nb; ++i) out[i] = 0.0;
+    for (int a = 0; a <= kmax; ++a)
+        for (int b = -kmax; b <= kmax; ++b) {
+            if (s->dim == 1 ? (b != 0 || a == 0) : !(a > 0 || b > 0)) continue;
+            double acc = 0.0;
+            for (int64_t m = 1; m <= s->M; ++m) {
+                double re = 0.0, im = 0.0;
+                for (int64_t n = 1; n <= s->N; ++n) {
+                    const double ph = PI * ((a * R_(s, n, m, 1) + (s->dim > 1 ? b * R_(s, n, m, 2) : 0.0)) / s->L);
+                    re += cos(ph); im += sin(ph);
+                }
+                acc += re * re + im * im;
+            }
+            out[a * nb + (b + kmax)] = acc;
+        }
+}
 struct ora_density { int64_t nbins; int dim; double bin; double *dens; int64_t ndata; };
 /* measurement.jl:31-38 */
 ora_density *ora_density_create(const ora_system *s, int64_t nbins)

@@ -143,6 +143,8 @@ void ora_paircorr_destroy(ora_paircorr *g);
 void ora_paircorr_measure(ora_paircorr *g, const ora_system *s);
 int64_t ora_paircorr_read(const ora_paircorr *g, double *hist, double *bin);
 void ora_winding_now(const ora_system *s, double *W /* dim */);
+/* static structure factor sums of the current configuration (definition in pimc_oracle.c): out[(kmax + 1) * (2 kmax + 1)] */
+void ora_structure_now(const ora_system *s, int kmax, double *out);
 
 /* ---- driver ---- */
 int ora_run(ora_system *s, int64_t n, ora_update **upd, const int64_t *every, int nupd,

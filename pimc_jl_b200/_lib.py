@@ -55,7 +55,8 @@ class RunStats(C.Structure):
 
 class Measurements(C.Structure):
     _fields_ = [("energy_ids", i32p), ("nenergy", C.c_int32), ("density_ids", i32p), ("ndensity", C.c_int32),
-                ("paircorr_ids", i32p), ("npaircorr", C.c_int32), ("winding_ids", i32p), ("nwinding", C.c_int32)]
+                ("paircorr_ids", i32p), ("npaircorr", C.c_int32), ("winding_ids", i32p), ("nwinding", C.c_int32),
+                ("structure_ids", i32p), ("nstructure", C.c_int32)]
 
 
 _vp, _d, _i32, _i64, _u32, _u64 = C.c_void_p, C.c_double, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
@@ -110,6 +111,10 @@ SIGNATURES = {
     "pimc_winding_create": (C.c_int, [_vp, _i64, i32p]),
     "pimc_winding_now": (C.c_int, [_vp, f64p]),
     "pimc_winding_read": (C.c_int, [_vp, _i32, _i32, f64p, _i64, i64p]),
+    "pimc_structure_create": (C.c_int, [_vp, _i32, i32p]),
+    "pimc_structure_measure": (C.c_int, [_vp, _i32]),
+    "pimc_structure_read": (C.c_int, [_vp, _i32, f64p, i64p, i32p]),
+    "pimc_compressibility": (C.c_int, [_vp, _i32, f64p, f64p]),
     "pimc_run_ex": (C.c_int, [_vp, _i64, i32p, i64p, _i32, C.POINTER(Measurements), _i32, C.POINTER(RunStats)]),
     "pimc_comm_get_unique_id": (C.c_int, [_vp]),
     "pimc_comm_init": (C.c_int, [_vp, _i32, _i32, _vp]),

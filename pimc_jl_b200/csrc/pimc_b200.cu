@@ -287,6 +287,8 @@ struct pimc_handle {
     int device;
     PcDev pc[PIMC_MAXP]; long long pc_ndata[PIMC_MAXP]; int npc;      // g(r) objects
     WiDev wi[PIMC_MAXW]; long long wi_count[PIMC_MAXW]; int nwi;       // winding-number objects
+    SkDev sk[PIMC_MAXS]; long long sk_ndata[PIMC_MAXS]; int nsk;       // structure-factor objects
+    double *g_f64; size_t g_f64_n;     // structure-factor read-out staging (sums + ndata, all-reduced over the ranks)
     // multi-GPU: one rank per handle; estimator blocks are all-reduced on a side stream while the next block's moves run
     void *comm;                        // ncclComm_t, null = single GPU
     int nranks, rank; long long chains_total;
@@ -554,6 +556,7 @@ extern "C" int pimc_create(const pimc_config *cfg, pimc_handle **out)
     memset(h->en_count, 0, sizeof h->en_count);
     memset(&h->T, 0, sizeof h->T);
     h->npc = h->nwi = 0; memset(h->pc_ndata, 0, sizeof h->pc_ndata); memset(h->wi_count, 0, sizeof h->wi_count);
+    h->nsk = 0; memset(h->sk_ndata, 0, sizeof h->sk_ndata); h->g_f64 = nullptr; h->g_f64_n = 0;
     h->comm = nullptr; h->nranks = 1; h->rank = 0; h->chains_total = cfg->chains; h->cstream = nullptr; h->cev = nullptr; h->g_u64 = nullptr; h->g_u64_n = 0;
     memset(h->g_en, 0, sizeof h->g_en); memset(h->g_en_upto, 0, sizeof h->g_en_upto);
     int rc = PIMC_OK;
@@ -1112,7 +1115,8 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
     // staging half: xs, ys, (pv) and the row map take BCAP rows; BCAP fills what four CTAs per SM leave of the shared memory
     const size_t rs_fixed = (size_t)SWEEP_THREADS * sizeof(double) + 2 * SWEEP_THREADS * sizeof(int) + (((size_t)S.N + 15) & ~(size_t)15) + (size_t)(S.M + 1 + 2 * PIMC_LOGTAB_N) * sizeof(double) + 32;
     const size_t rs_row = (size_t)(pk == PIMC_POT_ZERO ? 2 : 3) * sizeof(double) + 1;
-    const size_t rs_budget = ((S.M + 31) / 32 <= 4 ? 56000 : 74000);   // launch bounds: four (KM <= 4) or three CTAs per SM
+    const size_t rs_budget256 = ((S.M + 31) / 32 <= 4 ? 56000 : 74000);   // launch bounds: four (KM <= 4) or three CTAs of 256 threads per SM
+    const size_t rs_budget = SWEEP_THREADS == 256 ? rs_budget256 : rs_budget256 * SWEEP_THREADS / 256 - 1200;   // (smaller CTAs: 1 KiB reserved + static shared memory per CTA weigh more)
     const int bcap = rs_fixed + 512 * rs_row < rs_budget ? (int)(((rs_budget - rs_fixed) / rs_row) & ~(size_t)15) : 512;
     const size_t smem_rs = rs_fixed + (size_t)bcap * rs_row;
     // COM half: flags, then (TMA path, even M) two mbarriers per warp and two stages of (dim + 1) rows per warp
@@ -1374,6 +1378,72 @@ extern "C" int pimc_winding_read(pimc_handle *h, int32_t id, int32_t chain, doub
     return PIMC_OK;
 }
 
+// ---- static structure factor and compressibility (`#TODO Compressibilty`, measurement.jl:127) ----
+extern "C" int pimc_structure_create(pimc_handle *h, int32_t kmax, int32_t *id)
+{
+    if (!h || !id) return PIMC_ERR_INVALID;
+    if (kmax < 1 || kmax > PIMC_SK_KMAX) { SETERR(h, "structure factor: kmax must lie in 1..%d", PIMC_SK_KMAX); return PIMC_ERR_INVALID; }
+    if (h->nsk >= PIMC_MAXS) { SETERR(h, "at most %d structure-factor objects per handle", PIMC_MAXS); return PIMC_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    int TS; if (pimc_structure_smem(h->S, &TS) > 200 * 1024) { SETERR(h, "structure factor: N = %d does not fit the shared-memory tile", h->S.N); return PIMC_ERR_UNSUPPORTED; }
+    SkDev &K = h->sk[h->nsk]; K.kmax = kmax;
+    int rc = dalloc(h, &K.S, (size_t)h->S.C * (kmax + 1) * (2 * kmax + 1)); if (rc) return rc;
+    h->sk_ndata[h->nsk] = 0;
+    *id = h->nsk++;
+    return PIMC_OK;
+}
+extern "C" int pimc_structure_measure(pimc_handle *h, int32_t id)
+{
+    if (!h || id < 0 || id >= h->nsk) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, pimc_launch_structure(h->S.C, h->stream, h->S, h->sk[id])); LAUNCHED();
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->sk_ndata[id] += (long long)h->S.M * h->S.C;
+    return PIMC_OK;
+}
+// sums[(kmax + 1) * (2 kmax + 1)]: sum of |rho_k|^2 over slices, measurements and this handle's chains in chain order (over all ranks with a
+// communicator attached), entry (a, b + kmax) for k = (pi / L)(a, b); ndata likewise.  S(k) = sums / (ndata * N).
+extern "C" int pimc_structure_read(pimc_handle *h, int32_t id, double *sums, int64_t *ndata, int32_t *kmax)
+{
+    if (!h || id < 0 || id >= h->nsk) return PIMC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const SkDev &K = h->sk[id]; const size_t nv = (size_t)(K.kmax + 1) * (2 * K.kmax + 1), C = (size_t)h->S.C;
+    std::vector<double> all(C * nv), tot(nv + 1, 0.0);
+    CK(h, cudaMemcpy(all.data(), K.S, all.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < C; ++c) for (size_t v = 0; v < nv; ++v) tot[v] += all[c * nv + v];
+    tot[nv] = (double)h->sk_ndata[id];
+    if (h->comm) {
+        if (h->g_f64_n < nv + 1) { int rc = dalloc(h, &h->g_f64, nv + 1); if (rc) return rc; h->g_f64_n = nv + 1; }
+        CK(h, cudaMemcpyAsync(h->g_f64, tot.data(), (nv + 1) * sizeof(double), cudaMemcpyHostToDevice, h->cstream));
+        NK(h, nccl_api()->AllReduce(h->g_f64, h->g_f64, nv + 1, ncclDouble, ncclSum, (ncclComm_t)h->comm, h->cstream));
+        CK(h, cudaMemcpyAsync(tot.data(), h->g_f64, (nv + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->cstream));
+        CK(h, cudaStreamSynchronize(h->cstream));
+    }
+    if (sums) for (size_t v = 0; v < nv; ++v) sums[v] = tot[v];
+    if (ndata) *ndata = (int64_t)tot[nv];
+    if (kmax) *kmax = K.kmax;
+    return PIMC_OK;
+}
+// isothermal compressibility from the long-wavelength limit S(k -> 0) = rho k_B T kappa_T, estimated on the smallest shell of the box
+// (|k| = pi / L: the mean of S over (1, 0) and (0, 1); 1-D: (1)):  kappa_T = beta S(k_min) / rho, rho = N / (2L)^dim, beta = M tau.
+extern "C" int pimc_compressibility(pimc_handle *h, int32_t id, double *kappa, double *s_kmin)
+{
+    if (!h || id < 0 || id >= h->nsk || !kappa) return PIMC_ERR_INVALID;
+    const int kmax = h->sk[id].kmax, nb = 2 * kmax + 1;
+    std::vector<double> sums((size_t)(kmax + 1) * nb); int64_t nd = 0;
+    int rc = pimc_structure_read(h, id, sums.data(), &nd, nullptr); if (rc) return rc;
+    if (nd <= 0) { SETERR(h, "compressibility: the structure-factor object holds no measurement"); return PIMC_ERR_STATE; }
+    const DevSys &S = h->S;
+    double s0 = sums[(size_t)1 * nb + kmax];                         // (1, 0)
+    if (S.dim > 1) s0 = 0.5 * (s0 + sums[(size_t)0 * nb + kmax + 1]);   // (0, 1)
+    s0 /= (double)nd * S.N;
+    double vol = 1.0; for (int k = 0; k < S.dim; ++k) vol *= 2 * S.L;
+    *kappa = (S.M * S.tau) * s0 / ((double)S.N / vol);
+    if (s_kmin) *s_kmin = s0;
+    return PIMC_OK;
+}
+
 // run! with the full estimator list.  Energy / Density are evaluated inside the run kernels; the estimators above are launched between
 // segments of the run that end on a measurement event (same cadence: measurement_Z_sector, measurement.jl:1-17).
 extern "C" int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids, const int64_t *every, int32_t nupd,
@@ -1382,10 +1452,11 @@ extern "C" int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids,
     if (!h) return PIMC_ERR_INVALID;
     pimc_measurements none; memset(&none, 0, sizeof none);
     const pimc_measurements &Z = meas ? *meas : none;
-    if (Z.npaircorr < 0 || Z.npaircorr > PIMC_MAXP || Z.nwinding < 0 || Z.nwinding > PIMC_MAXW) { SETERR(h, "pimc_run_ex: bad estimator counts"); return PIMC_ERR_INVALID; }
+    if (Z.npaircorr < 0 || Z.npaircorr > PIMC_MAXP || Z.nwinding < 0 || Z.nwinding > PIMC_MAXW || Z.nstructure < 0 || Z.nstructure > PIMC_MAXS) { SETERR(h, "pimc_run_ex: bad estimator counts"); return PIMC_ERR_INVALID; }
+    for (int i = 0; i < Z.nstructure; ++i) if (Z.structure_ids[i] < 0 || Z.structure_ids[i] >= h->nsk) { SETERR(h, "bad structure-factor id"); return PIMC_ERR_INVALID; }
     for (int i = 0; i < Z.npaircorr; ++i) if (Z.paircorr_ids[i] < 0 || Z.paircorr_ids[i] >= h->npc) { SETERR(h, "bad pair-correlation id"); return PIMC_ERR_INVALID; }
     for (int i = 0; i < Z.nwinding; ++i) if (Z.winding_ids[i] < 0 || Z.winding_ids[i] >= h->nwi) { SETERR(h, "bad winding id"); return PIMC_ERR_INVALID; }
-    const int nextra = Z.npaircorr + Z.nwinding;
+    const int nextra = Z.npaircorr + Z.nwinding + Z.nstructure;
     if (nextra == 0) return run_core(h, n, update_ids, every, nupd, Z.energy_ids, Z.nenergy, Z.density_ids, Z.ndensity, sched, false, stats);
     {   // winding series overflow: like Energy, the pre-sized vector must hold every sample of this run
         const long long nmeas = (h->Nctr + n) / h->cfg.Ncycle;
@@ -1405,6 +1476,7 @@ extern "C" int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids,
             CK(h, cudaEventRecord(e0, h->stream));
             for (int i = 0; i < Z.npaircorr; ++i) { CK(h, pimc_launch_paircorr(h->S.C, h->stream, h->S, h->pc[Z.paircorr_ids[i]])); LAUNCHED(); tot.launches++; h->pc_ndata[Z.paircorr_ids[i]] += (long long)h->S.M * h->S.C; }
             for (int i = 0; i < Z.nwinding; ++i) { const int id = Z.winding_ids[i]; CK(h, pimc_launch_winding(h->S.C, h->stream, h->S, h->wi[id], h->wi_count[id])); LAUNCHED(); tot.launches++; h->wi_count[id] += 1; }
+            for (int i = 0; i < Z.nstructure; ++i) { const int id = Z.structure_ids[i]; CK(h, pimc_launch_structure(h->S.C, h->stream, h->S, h->sk[id])); LAUNCHED(); tot.launches++; h->sk_ndata[id] += (long long)h->S.M * h->S.C; }
             CK(h, cudaEventRecord(e1, h->stream));
             CK(h, cudaStreamSynchronize(h->stream));
             float ms = 0; CK(h, cudaEventElapsedTime(&ms, e0, e1)); tot.kernel_ms += ms;
@@ -1425,6 +1497,7 @@ struct StateHeader {
     unsigned long long iter; long long N_MC, Nctr;
     long long en_count[PIMC_MAXE], en_cap[PIMC_MAXE], de_ndata[PIMC_MAXD], de_nbins[PIMC_MAXD];
     long long pc_ndata[PIMC_MAXP], pc_nbins[PIMC_MAXP], wi_count[PIMC_MAXW], wi_cap[PIMC_MAXW];
+    int nsk, sk_kmax[PIMC_MAXS]; long long sk_ndata[PIMC_MAXS];
     int upd_kind[PIMC_MAXU], upd_ring_words[PIMC_MAXU]; long long upd_adj[PIMC_MAXU], upd_range[PIMC_MAXU];
     double upd_vmin[PIMC_MAXU], upd_vmax[PIMC_MAXU], upd_minacc[PIMC_MAXU], upd_maxacc[PIMC_MAXU];
 };
@@ -1452,13 +1525,15 @@ static std::vector<Seg> state_segments(pimc_handle *h)
     for (int i = 0; i < h->nde; ++i) { DeDev &D = h->T.de[i]; v.push_back({ D.dens, (S.dim == 2 ? (size_t)D.nbins * D.nbins : (size_t)D.nbins) * 8 }); }
     for (int i = 0; i < h->npc; ++i) v.push_back({ h->pc[i].hist, (size_t)h->pc[i].nbins * 8 });
     for (int i = 0; i < h->nwi; ++i) { const size_t rows = (size_t)(h->wi_count[i] < h->wi[i].cap ? h->wi_count[i] : h->wi[i].cap); v.push_back({ h->wi[i].W, rows * S.dim * C * 8 }); }
+    for (int i = 0; i < h->nsk; ++i) v.push_back({ h->sk[i].S, C * (size_t)(h->sk[i].kmax + 1) * (2 * h->sk[i].kmax + 1) * 8 });
     return v;
 }
 static void state_header(pimc_handle *h, StateHeader *H)
 {
     memset(H, 0, sizeof *H);
     DevSys &S = h->S;
-    H->magic = PIMC_STATE_MAGIC; H->version = 2; H->npc = h->npc; H->nwi = h->nwi;
+    H->magic = PIMC_STATE_MAGIC; H->version = 3; H->npc = h->npc; H->nwi = h->nwi; H->nsk = h->nsk;
+    for (int i = 0; i < h->nsk; ++i) { H->sk_ndata[i] = h->sk_ndata[i]; H->sk_kmax[i] = h->sk[i].kmax; }
     for (int i = 0; i < h->npc; ++i) { H->pc_ndata[i] = h->pc_ndata[i]; H->pc_nbins[i] = h->pc[i].nbins; }
     for (int i = 0; i < h->nwi; ++i) { H->wi_count[i] = h->wi_count[i]; H->wi_cap[i] = h->wi[i].cap; } H->dim = S.dim; H->M = S.M; H->N = S.N; H->C = S.C; H->need_cells = S.need_cells; H->ncell = S.ncell;
     H->nupd = h->nupd; H->nen = h->nen; H->nde = h->nde; H->chain_offset = S.chain_offset; H->seed = S.seed;
@@ -1498,12 +1573,14 @@ extern "C" int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes)
     if (!h || !buf || bytes < (int64_t)sizeof(StateHeader)) return PIMC_ERR_INVALID;
     StateHeader H; memcpy(&H, buf, sizeof H);
     DevSys &S = h->S;
-    if (H.magic != PIMC_STATE_MAGIC || H.version != 2) { SETERR(h, "not a pimc_b200 state blob (magic / version)"); return PIMC_ERR_INVALID; }
+    if (H.magic != PIMC_STATE_MAGIC || H.version != 3) { SETERR(h, "not a pimc_b200 state blob (magic / version)"); return PIMC_ERR_INVALID; }
     if (H.dim != S.dim || H.M != S.M || H.N != S.N || H.C != S.C || H.need_cells != S.need_cells || H.ncell != S.ncell || H.seed != S.seed || H.chain_offset != S.chain_offset) {
         SETERR(h, "state blob belongs to another System (dim/M/N/chains/cells/seed/chain_offset differ)"); return PIMC_ERR_STATE; }
     if (H.npc != h->npc || H.nwi != h->nwi) { SETERR(h, "state blob holds %d/%d pair-correlation/winding objects, the handle %d/%d", H.npc, H.nwi, h->npc, h->nwi); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->npc; ++i) if (H.pc_nbins[i] != h->pc[i].nbins) { SETERR(h, "pair-correlation object %d differs in nbins", i); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->nwi; ++i) if (H.wi_cap[i] != h->wi[i].cap) { SETERR(h, "winding object %d differs in capacity", i); return PIMC_ERR_STATE; }
+    if (H.nsk != h->nsk) { SETERR(h, "state blob holds %d structure-factor objects, the handle %d", H.nsk, h->nsk); return PIMC_ERR_STATE; }
+    for (int i = 0; i < h->nsk; ++i) if (H.sk_kmax[i] != h->sk[i].kmax) { SETERR(h, "structure-factor object %d differs in kmax", i); return PIMC_ERR_STATE; }
     if (H.nupd != h->nupd || H.nen != h->nen || H.nde != h->nde) { SETERR(h, "state blob holds %d/%d/%d update/Energy/Density objects, the handle %d/%d/%d: create the same objects in the same order first", H.nupd, H.nen, H.nde, h->nupd, h->nen, h->nde); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->nupd; ++i) if (H.upd_kind[i] != h->T.upd[i].kind || H.upd_range[i] != h->T.upd[i].range) { SETERR(h, "update object %d differs in kind or window range", i); return PIMC_ERR_STATE; }
     for (int i = 0; i < h->nen; ++i) if (H.en_cap[i] != h->T.en[i].cap) { SETERR(h, "Energy object %d differs in capacity", i); return PIMC_ERR_STATE; }
@@ -1515,6 +1592,7 @@ extern "C" int pimc_set_state(pimc_handle *h, const void *buf, int64_t bytes)
     for (int i = 0; i < h->nde; ++i) h->de_ndata[i] = H.de_ndata[i];
     for (int i = 0; i < h->npc; ++i) h->pc_ndata[i] = H.pc_ndata[i];
     for (int i = 0; i < h->nwi; ++i) h->wi_count[i] = H.wi_count[i];
+    for (int i = 0; i < h->nsk; ++i) h->sk_ndata[i] = H.sk_ndata[i];
     for (int i = 0; i < h->nupd; ++i) { UpdDev &U = h->T.upd[i]; U.adj = H.upd_adj[i]; U.vmin = H.upd_vmin[i]; U.vmax = H.upd_vmax[i]; U.minacc = H.upd_minacc[i]; U.maxacc = H.upd_maxacc[i]; }
     int64_t need; pimc_state_size(h, &need);   // after en_count is restored: the Energy segments hold the rows taken so far
     if (bytes < need) { SETERR(h, "state blob truncated (%lld of %lld bytes)", (long long)bytes, (long long)need); return PIMC_ERR_INVALID; }

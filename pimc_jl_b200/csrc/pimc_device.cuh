@@ -69,6 +69,9 @@ struct DevTables { UpdDev upd[PIMC_MAXU]; EnDev en[PIMC_MAXE]; DeDev de[PIMC_MAX
 #define PIMC_MAXW 4
 struct PcDev { unsigned long long *hist; long long nbins; double rmax, bin; };   // g(r): counts per radial bin, all chains of the handle
 struct WiDev { double *W; long long cap; };                                      // winding series W[cap][dim][C]
+#define PIMC_MAXS 4
+#define PIMC_SK_KMAX 6   // wave vectors (pi / L)(a, b) with a <= kmax, |b| <= kmax; one warp of k_structure per value of a
+struct SkDev { double *S; int kmax; };                                           // structure-factor sums S[C][kmax + 1][2 kmax + 1] of |rho_k|^2 (per chain: deterministic)
 
 struct RunParams {
     long long n;

@@ -96,6 +96,79 @@ __global__ void __launch_bounds__(256) k_winding(const __grid_constant__ DevSys 
     }
 }
 
+// ---- static structure factor S(k) = <|rho_k|^2> / N, rho_k(m) = sum_n exp(i k . r_n[m]) on the wave vectors of the periodic box
+// k = (pi / L)(a, b), a = 0..kmax, |b| <= kmax (half plane: a > 0, or a = 0 and b > 0; the other half is the complex conjugate; 1-D: b = 0).
+// One CTA per chain; tiles of TS slices staged in shared memory like k_paircorr (positions read once: 16 B per bead); warp w owns a = w, its
+// lanes stride the particles of one slice after the other.  Per bead: exp(i a th_x) by one sincospi, the table exp(i b th_y), b = 0..kmax, by
+// one sincospi and a complex-product recurrence; rho(a, b) and rho(a, -b) share the four real sums A = cx cy, B = sx sy, C = cx sy, D = sx cy:
+// rho(a, b) = (A - B, C + D), rho(a, -b) = (A + B, D - C).  The sums over the slices are added to the chain's own accumulators by one lane
+// (no atomics: bit-reproducible).  Bound: fp64 pipe (~200 flops per bead and value of a).
+__global__ void __launch_bounds__(256) k_structure(const __grid_constant__ DevSys S, const __grid_constant__ SkDev K, int TS)
+{
+    extern __shared__ double sm[];
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, a = tid >> 5, N = S.N, M = S.M, dim = S.dim, kmax = K.kmax;
+    const int TP = TS + 1;
+    double *xs = sm, *ys = sm + (size_t)N * TP;
+    const double *rc = S.r + (size_t)c * N * dim * M;
+    const double invL = 1.0 / S.L;
+    double accp[PIMC_SK_KMAX + 1], accm[PIMC_SK_KMAX + 1];   // sums over the slices of |rho(a, b)|^2 and |rho(a, -b)|^2
+#pragma unroll
+    for (int b = 0; b <= PIMC_SK_KMAX; ++b) { accp[b] = 0.0; accm[b] = 0.0; }
+    for (int m0 = 0; m0 < M; m0 += TS) {
+        const int ts = M - m0 < TS ? M - m0 : TS;
+        __syncthreads();
+        for (int idx = tid; idx < N * TS; idx += blockDim.x) {
+            const int n = idx / TS, s = idx - n * TS;
+            if (s < ts) {
+                xs[n * TP + s] = rc[(size_t)(n * dim) * M + m0 + s];
+                if (dim > 1) ys[n * TP + s] = rc[(size_t)(n * dim + 1) * M + m0 + s];
+            }
+        }
+        __syncthreads();
+        if (a > kmax) continue;
+        for (int s = 0; s < ts; ++s) {
+            double A[PIMC_SK_KMAX + 1], B[PIMC_SK_KMAX + 1], Cc[PIMC_SK_KMAX + 1], D[PIMC_SK_KMAX + 1];
+#pragma unroll
+            for (int b = 0; b <= PIMC_SK_KMAX; ++b) { A[b] = 0.0; B[b] = 0.0; Cc[b] = 0.0; D[b] = 0.0; }
+            for (int n = lane; n < N; n += 32) {
+                double sx, cx, s1, c1;
+                sincospi((double)a * (xs[n * TP + s] * invL), &sx, &cx);
+                if (dim > 1) sincospi(ys[n * TP + s] * invL, &s1, &c1); else { s1 = 0.0; c1 = 1.0; }
+                double cy = 1.0, sy = 0.0;
+#pragma unroll
+                for (int b = 0; b <= PIMC_SK_KMAX; ++b) {
+                    if (b <= kmax) {
+                        A[b] += cx * cy; B[b] += sx * sy; Cc[b] += cx * sy; D[b] += sx * cy;
+                        const double cn = cy * c1 - sy * s1, sn = sy * c1 + cy * s1;
+                        cy = cn; sy = sn;
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b <= PIMC_SK_KMAX; ++b) {
+                if (b <= kmax) {
+                    const double Ar = e_warp_sum(A[b]), Br = e_warp_sum(B[b]), Cr = e_warp_sum(Cc[b]), Dr = e_warp_sum(D[b]);
+                    const double pr = Ar - Br, pi_ = Cr + Dr, mr = Ar + Br, mi = Dr - Cr;
+                    accp[b] += pr * pr + pi_ * pi_;
+                    accm[b] += mr * mr + mi * mi;
+                }
+            }
+        }
+    }
+    if (a <= kmax && lane == 0) {
+        const int nb = 2 * kmax + 1;
+        double *out = K.S + ((size_t)c * (kmax + 1) + a) * nb;
+#pragma unroll
+        for (int b = 0; b <= PIMC_SK_KMAX; ++b) {
+            if (b > kmax) continue;
+            const bool plus = dim == 1 ? (b == 0 && a > 0) : (a > 0 || b > 0);     // the half plane of independent wave vectors
+            const bool minus = dim > 1 && a > 0 && b > 0;
+            if (plus) out[kmax + b] += accp[b];
+            if (minus) out[kmax - b] += accm[b];
+        }
+    }
+}
+
 size_t pimc_paircorr_smem(const DevSys &S, const PcDev &G, int *TS, int *smem_hist)
 {
     *smem_hist = G.nbins <= 8192 ? 1 : 0;
@@ -117,5 +190,21 @@ cudaError_t pimc_launch_paircorr(int grid, cudaStream_t st, const DevSys &S, con
 cudaError_t pimc_launch_winding(int grid, cudaStream_t st, const DevSys &S, const WiDev &W, long long k)
 {
     k_winding<<<grid, 256, 0, st>>>(S, W, k);
+    return cudaGetLastError();
+}
+size_t pimc_structure_smem(const DevSys &S, int *TS)
+{
+    int ts = 8;
+    while (ts > 1 && (size_t)S.dim * S.N * (ts + 1) * sizeof(double) > 160 * 1024) ts >>= 1;
+    *TS = ts;
+    return (size_t)S.dim * S.N * (ts + 1) * sizeof(double) + 16;
+}
+cudaError_t pimc_launch_structure(int grid, cudaStream_t st, const DevSys &S, const SkDev &K)
+{
+    int TS; const size_t smem = pimc_structure_smem(S, &TS);
+    if (smem > 200 * 1024 || K.kmax < 1 || K.kmax > PIMC_SK_KMAX) return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) { cudaError_t e = cudaFuncSetAttribute(k_structure, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; configured = true; }
+    k_structure<<<grid, 256, smem, st>>>(S, K, TS);
     return cudaGetLastError();
 }

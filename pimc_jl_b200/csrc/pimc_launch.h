@@ -4,7 +4,9 @@
 #pragma once
 #include "pimc_device.cuh"
 
-#define SWEEP_THREADS 256
+#ifndef SWEEP_THREADS
+#define SWEEP_THREADS 256   // threads per CTA of k_sweep / k_chain (A/B knob: 128 = twice the CTAs per SM, scripts/build_variant_all.sh)
+#endif
 
 struct SweepParams {
     unsigned long long iter;
@@ -70,5 +72,7 @@ struct ChainParams {
 cudaError_t pimc_launch_chain(size_t smem, cudaStream_t st, const DevSys &S, const DevTables *dT, const ChainParams &Q, int *grid_out);
 cudaError_t pimc_launch_paircorr(int grid, cudaStream_t st, const DevSys &S, const PcDev &G);
 cudaError_t pimc_launch_winding(int grid, cudaStream_t st, const DevSys &S, const WiDev &W, long long k);
+size_t pimc_structure_smem(const DevSys &S, int *TS);
+cudaError_t pimc_launch_structure(int grid, cudaStream_t st, const DevSys &S, const SkDev &K);
 cudaError_t pimc_launch_isweep(int grid, cudaStream_t st, const DevSys &S, const ISweepParams &P, bool has_rs, bool has_com);
 cudaError_t pimc_launch_iswap(int grid, cudaStream_t st, const DevSys &S, const DevTables *dT, const Sweep2Params &P);

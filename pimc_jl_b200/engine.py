@@ -234,7 +234,7 @@ class Engine:
         self._ck(self.lib.pimc_density_read(self.h, did, _p(dens), C.byref(nd), C.byref(b)))
         return dens.reshape(shape, order="F"), nd.value, b.value
 
-    def run(self, n, updates, energies=(), densities=(), sched=L.SCHED_FAITHFUL, paircorrs=(), windings=()):
+    def run(self, n, updates, energies=(), densities=(), sched=L.SCHED_FAITHFUL, paircorrs=(), windings=(), structures=()):
         """updates: [(every, update_id)] ; returns RunStats as dict"""
         nu = len(updates)
         ids = (C.c_int32 * nu)(*[u for _, u in updates])
@@ -242,13 +242,14 @@ class Engine:
         en = (C.c_int32 * max(1, len(energies)))(*energies)
         de = (C.c_int32 * max(1, len(densities)))(*densities)
         st = L.RunStats()
-        if not paircorrs and not windings:
+        if not paircorrs and not windings and not structures:
             self._ck(self.lib.pimc_run(self.h, n, ids, ev, nu, en, len(energies), de, len(densities), sched, C.byref(st)))
         else:
             pc = (C.c_int32 * max(1, len(paircorrs)))(*paircorrs)
             wi = (C.c_int32 * max(1, len(windings)))(*windings)
+            sk = (C.c_int32 * max(1, len(structures)))(*structures)
             z = L.Measurements(C.cast(en, L.i32p), len(energies), C.cast(de, L.i32p), len(densities), C.cast(pc, L.i32p), len(paircorrs),
-                               C.cast(wi, L.i32p), len(windings))
+                               C.cast(wi, L.i32p), len(windings), C.cast(sk, L.i32p), len(structures))
             self._ck(self.lib.pimc_run_ex(self.h, n, ids, ev, nu, C.byref(z), sched, C.byref(st)))
         return {k: getattr(st, k) for k, _ in L.RunStats._fields_}
 
@@ -282,6 +283,27 @@ class Engine:
         out = np.zeros((max(1, n.value), self.dim)) if chain >= 0 else np.zeros(max(1, n.value))
         self._ck(self.lib.pimc_winding_read(self.h, wid, chain, _p(out), n.value, C.byref(n)))
         return out[:n.value], n.value
+
+    def structure_create(self, kmax):
+        i = C.c_int32()
+        self._ck(self.lib.pimc_structure_create(self.h, int(kmax), C.byref(i)))
+        return i.value
+
+    def structure_measure(self, sid):
+        self._ck(self.lib.pimc_structure_measure(self.h, sid))
+
+    def structure_read(self, sid, kmax):
+        """sums of |rho_k|^2 [kmax + 1][2 kmax + 1] (entry (a, b + kmax) for k = (pi / L)(a, b)) and ndata; S(k) = sums / (ndata * N)"""
+        sums, nd, km = np.zeros((kmax + 1, 2 * kmax + 1)), C.c_int64(), C.c_int32()
+        self._ck(self.lib.pimc_structure_read(self.h, sid, _p(sums), C.byref(nd), C.byref(km)))
+        assert km.value == kmax
+        return sums, nd.value
+
+    def compressibility(self, sid):
+        """(kappa_T, S(k_min)) from the smallest shell of the box"""
+        k, s0 = C.c_double(), C.c_double()
+        self._ck(self.lib.pimc_compressibility(self.h, sid, C.byref(k), C.byref(s0)))
+        return k.value, s0.value
 
 
 # ---- stateless device hooks ----

@@ -322,6 +322,41 @@ class Winding:                      # `#TODO Superfluid Fraction` (src/measureme
         return s.engine.winding_now()
 
 
+class StructureFactor:              # `#TODO Compressibilty` (src/measurement.jl:127), in the style of Density
+    """static structure factor on the box's wave vectors k = (pi / L)(a, b), a = 0..kmax, |b| <= kmax:
+    StructureFactor(s; kmax=4); .S ([kmax + 1][2 kmax + 1], NaN outside the half plane of independent vectors), .k (|k| of every entry),
+    .ndata, .compressibility() (kappa_T = beta S(k_min) / rho, the long-wavelength limit on the smallest shell)"""
+
+    def __init__(self, s, kmax=4):
+        self.s, self.kmax = s, int(kmax)
+        self.id = s.engine.structure_create(self.kmax)
+
+    def _read(self):
+        return self.s.engine.structure_read(self.id, self.kmax)   # global over the ranks when the library communicator is attached
+
+    @property
+    def ndata(self):
+        return self._read()[1]
+
+    @property
+    def S(self):
+        sums, nd = self._read()
+        a, b = np.meshgrid(np.arange(self.kmax + 1), np.arange(-self.kmax, self.kmax + 1), indexing="ij")
+        half = ((a > 0) | (b > 0)) if self.s.dim > 1 else ((b == 0) & (a > 0))
+        return np.where(half, sums / max(1, nd * self.s.N), np.nan)
+
+    @property
+    def k(self):
+        a, b = np.meshgrid(np.arange(self.kmax + 1), np.arange(-self.kmax, self.kmax + 1), indexing="ij")
+        return np.pi / self.s.L * np.hypot(a, b if self.s.dim > 1 else 0 * b)
+
+    def compressibility(self):
+        return self.s.engine.compressibility(self.id)[0]
+
+    def __call__(self, s):
+        s.engine.structure_measure(self.id)
+
+
 class System:                       # src/system.jl:93-168
     def __init__(self, potential, dV="zero", dim=2, M=100, N=2, mu=0.0, L=4.0, T=1.0, lam=1.0, interactions=False, propint=None,
                  g=0.0, r_a=0.0, length_measurement_cycle=10, measure_scheme="c", chains=None, seed=None, compat=_L.COMPAT_ALL,
@@ -399,8 +434,9 @@ def run_b(s, n, updates, Zmeasurements=()):
     de = [m.id for m in Zmeasurements if isinstance(m, Density)]
     pc = [m.id for m in Zmeasurements if isinstance(m, PairCorrelation)]
     wi = [m.id for m in Zmeasurements if isinstance(m, Winding)]
+    sk = [m.id for m in Zmeasurements if isinstance(m, StructureFactor)]
     sched = _L.SCHED_SWEEP if s.schedule == "sweep" else _L.SCHED_FAITHFUL
-    return s.engine.run(n, [(every, u.id) for every, u in updates], energies=en, densities=de, sched=sched, paircorrs=pc, windings=wi)
+    return s.engine.run(n, [(every, u.id) for every, u in updates], energies=en, densities=de, sched=sched, paircorrs=pc, windings=wi, structures=sk)
 
 
 def apply_b(s, f):

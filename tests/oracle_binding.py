@@ -92,6 +92,7 @@ def lib():
             "ora_paircorr_create": (vp, [vp, i64, d]), "ora_paircorr_destroy": (None, [vp]),
             "ora_paircorr_measure": (None, [vp, vp]), "ora_paircorr_read": (i64, [vp, f64p, f64p]),
             "ora_winding_now": (None, [vp, f64p]),
+            "ora_structure_now": (None, [vp, C.c_int, f64p]),
             "ora_run": (C.c_int, [vp, i64, C.POINTER(vp), i64p, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.c_int]),
         }
         for name, (res, args) in sig.items():
@@ -205,6 +206,13 @@ def winding_now(system):
     W = np.zeros(system.dim)
     lib().ora_winding_now(system.h, _p(W))
     return W
+
+
+def structure_now(system, kmax):
+    """sum over the slices of |rho_k|^2 of the current configuration, [kmax + 1][2 kmax + 1] (a, b + kmax)"""
+    S = np.zeros((kmax + 1, 2 * kmax + 1))
+    lib().ora_structure_now(system.h, int(kmax), _p(S))
+    return S
 
 
 class System:

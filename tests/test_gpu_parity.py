@@ -772,3 +772,77 @@ def test_paircorr_and_winding_vs_oracle(oracle, cfg, nb, rmax):
     assert np.allclose(W[1], ob.winding_now(os_[1]), atol=1e-9) and np.rint(W[1, 0]) == 1 + np.rint(Wo[1][-1][0])
     with pytest.raises(pj.PimcError):
         e.run(64 * nC, ge, windings=[wi], sched=L.SCHED_SWEEP)   # more samples than the pre-sized series holds: refused like Energy
+
+
+@pytest.mark.parametrize("cfg,kmax", [
+    (dict(pot="harmonic", dim=2, M=20, N=13, L=3.0, T=0.6, lam=0.5, Ncycle=3), 4),
+    (dict(pot="zero", dim=2, M=33, N=70, L=4.0, T=1.0, lam=1.0, Ncycle=2), 6),     # largest kmax, odd M: ragged last tile, N > 64: three passes per warp
+    (dict(pot="sin2", dim=1, M=16, N=9, L=2.0, T=1.0, lam=0.5, Ncycle=4), 3),
+], ids=["trap2d", "free2d-kmax6", "1d"])
+def test_structure_factor_and_compressibility_vs_oracle(oracle, cfg, kmax):
+    """`#TODO Compressibilty` (measurement.jl:127): static structure factor sums |rho_k|^2 on the box's wave vectors against the oracle's
+    definition (1e-9 relative: the sums run in a different order, sincospi vs libm), (i) as a functor on the current configuration,
+    (ii) inside run! with swaps (pimc_run_ex, the cadence of Energy, which is measured alongside and must not change), (iii) the
+    compressibility read-out, (iv) a checkpoint taken mid-run carries the accumulators."""
+    ob = oracle
+    chains = 3
+    e, os_ = make_pair(ob, cfg, chains=chains, seed=91)
+    spec = [(1, L.UPD_SINGLE_COM, 0.5), (1, L.UPD_RESHAPE_LINEAR, 6), (1, L.UPD_RESHAPE_SWAP, 6)]
+    ge, oo = _mk_updates(ob, e, os_, spec)
+    sk, en = e.structure_create(kmax), e.energy_create(64)
+    oen = [ob.Energy(64) for _ in os_]
+    N, M, dim = cfg["N"], cfg["M"], cfg["dim"]
+    a, b = np.meshgrid(np.arange(kmax + 1), np.arange(-kmax, kmax + 1), indexing="ij")
+    half = ((a > 0) | (b > 0)) if dim > 1 else ((b == 0) & (a > 0))
+
+    def same(got, want):
+        return np.all(np.abs(got - want) <= 1e-9 * np.maximum(1.0, np.abs(want))) and np.all(got[~half] == 0) and np.all(got[half] > 0)
+    # (i) functor call
+    e.structure_measure(sk)
+    ref = sum(ob.structure_now(s, kmax) for s in os_)
+    got, nd = e.structure_read(sk, kmax)
+    assert nd == chains * M and same(got, ref)
+    # independent numpy evaluation of one entry: k = (pi / L)(1, -1) (2-D) or (1) (1-D), chain 0
+    r0 = e.paths(0, 1, want=("r",))[0][0]                       # [N][dim][M]
+    ph = np.pi / cfg["L"] * (r0[:, 0, :] - (r0[:, 1, :] if dim > 1 else 0.0))
+    one = (np.abs(np.exp(1j * ph).sum(axis=0)) ** 2).sum()
+    assert abs(ob.structure_now(os_[0], kmax)[1, kmax - (1 if dim > 1 else 0)] - one) <= 1e-9 * one
+    # (ii) inside run!
+    nC = cfg["Ncycle"]
+    blob = None
+    for n_it in (23, 18):
+        e.run(n_it, ge, energies=[en], structures=[sk], sched=L.SCHED_SWEEP)
+        if blob is None:
+            blob = e.get_state()
+            mid = e.structure_read(sk, kmax)
+    for s, ups, eo in zip(os_, oo, oen):
+        done = 0
+        while done < 41:
+            seg = min(nC - s.scalars()["Nctr"], 41 - done)
+            s.run(seg, ups, energies=[eo], sched=ob.SCHED_SWEEP)
+            done += seg
+            if s.scalars()["Nctr"] == 0:
+                ref = ref + ob.structure_now(s, kmax)
+    _sync_paths(e, os_, exact_v=cfg["pot"] in ("zero", "harmonic"))
+    got, nd = e.structure_read(sk, kmax)
+    nm = 41 // nC
+    assert nd == chains * M * (1 + nm) and same(got, ref)
+    scale = dim * N / (2 * os_[0].tau)
+    for c in range(chains):
+        E, _, ne = e.energy_read(en, c)
+        assert ne == nm and np.all(np.abs(E - oen[c].read()[0]) <= 1e-12 * scale)
+    # (iii) kappa_T = beta S(k_min) / rho on the smallest shell
+    kappa, s0 = e.compressibility(sk)
+    Sk = got / (nd * N)
+    s0_ref = 0.5 * (Sk[1, kmax] + Sk[0, kmax + 1]) if dim > 1 else Sk[1, kmax]
+    beta, rho = 1.0 / cfg["T"], N / (2 * cfg["L"]) ** dim
+    assert abs(s0 - s0_ref) <= 1e-12 * s0_ref and abs(kappa - beta * s0_ref / rho) <= 1e-12 * kappa
+    # (iv) the state blob carries the accumulators: restore the mid-run checkpoint, finish the run, same sums bit for bit
+    e.set_state(blob)
+    g2, n2 = e.structure_read(sk, kmax)
+    assert n2 == mid[1] and np.array_equal(g2, mid[0])
+    e.run(18, ge, energies=[en], structures=[sk], sched=L.SCHED_SWEEP)
+    g3, n3 = e.structure_read(sk, kmax)
+    assert n3 == nd and np.array_equal(g3, got)
+    with pytest.raises(pj.PimcError):
+        e.structure_create(7)                                    # kmax beyond the kernel's table

@@ -481,3 +481,32 @@ def test_paircorr_and_winding_estimators_against_numpy(oracle):
     s.set_paths(r2, s.paths()[3])
     W = ob.winding_now(s)
     assert abs(W[0] - 1.0) < 1e-12 and abs(W[1]) < 1e-12
+
+
+@pytest.mark.parametrize("dim", [1, 2])
+def test_structure_factor_against_numpy(oracle, dim):
+    """`#TODO Compressibilty` (measurement.jl:127) as the oracle defines it -- sums over the slices of |rho_k|^2 on the wave vectors of the
+    periodic box -- against a direct numpy evaluation, plus two closed forms: a perfect lattice of N = n^2 sites at spacing 2L / n scatters
+    only at the reciprocal-lattice vectors (|rho_k|^2 = N^2 at (a, b) = (n, 0), zero at the other k), and one particle gives |rho_k|^2 = 1."""
+    ob = oracle
+    kmax, M, N, L_ = 4, 6, 9, 1.5
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=dim, M=M, N=N, L=L_, T=0.7, lam=0.5, seed=11)
+    S = ob.structure_now(s, kmax)
+    r = s.paths()[0]                                        # [N][dim][M]
+    for a in range(kmax + 1):
+        for b in range(-kmax, kmax + 1):
+            indep = (a > 0 or b > 0) if dim == 2 else (b == 0 and a > 0)
+            ph = np.pi / L_ * (a * r[:, 0, :] + (b * r[:, 1, :] if dim == 2 else 0.0))
+            want = (np.abs(np.exp(1j * ph).sum(axis=0)) ** 2).sum() if indep else 0.0
+            assert abs(S[a, b + kmax] - want) <= 1e-12 * max(1.0, want)
+    if dim == 2:   # 3 x 3 square lattice, every slice the same
+        g = -L_ + (np.arange(3) + 0.25) * (2 * L_ / 3)
+        r2 = np.stack([np.stack([np.full(M, x), np.full(M, y)]) for x in g for y in g])
+        s.set_paths(r2, s.paths()[3])
+        S = ob.structure_now(s, kmax)
+        assert abs(S[3, kmax] - M * N * N) < 1e-9 and abs(S[0, kmax + 3] - M * N * N) < 1e-9 and abs(S[3, kmax + 3] - M * N * N) < 1e-9
+        assert abs(S[1, kmax]) < 1e-9 and abs(S[2, kmax + 1]) < 1e-9 and abs(S[4, kmax - 2]) < 1e-9
+    s1 = ob.System(ob.make_potential("zero", "identity"), dim=dim, M=M, N=1, L=L_, T=0.7, lam=0.5, seed=5)
+    S1 = ob.structure_now(s1, 2)
+    nv = 2 * 2 + 2 * 2 * 2 if dim == 2 else 2              # independent vectors: kmax + kmax (2 kmax + 1) in 2-D, kmax in 1-D
+    assert np.count_nonzero(S1) == nv and np.allclose(S1[S1 != 0], M, atol=1e-12)
