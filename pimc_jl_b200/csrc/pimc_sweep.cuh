@@ -854,21 +854,26 @@ __device__ __forceinline__ void d_energy_block_reg(const DevSys &S, int c, doubl
 // One staged worldline (rows sx | sy in shared memory) into the lane-partial Energy sums.  DV: 0 zero, 1 identity, 2 general gradient --
 // hoisted out of the bead loop (a per-bead runtime branch was a tenth of the kernel's instructions); the successor bead is read from the
 // staged row itself (no register tile, no shuffles), only the link that leaves the last slice needs the first bead of the cycle's next member.
-template <int POT, int KM, int DV>
+template <int POT, int KM, int DV, bool FAST>
 __device__ __forceinline__ void d_energy_row(const DevSys &S, const double *sx, const double x0n, const double y0n, const double twoL,
                                              double &link, double &pot, double &vkin)
 {
-    const int M = S.M, dim = S.dim, lane = threadIdx.x & 31;
+    // FAST: dim == 2 and M == 32 * KM, both checked by the caller -- no bead predicates, the y row at a constant offset, the successor of every
+    // bead but the last one an unconditional read.  Same arithmetic per bead in the same order: the sums are bit-identical to the general form.
+    const int M = FAST ? 32 * KM : S.M, dim = FAST ? 2 : S.dim, lane = threadIdx.x & 31;
     const double *sy = sx + M;
 #pragma unroll
     for (int k = 0; k < KM; ++k) {
         const int j = lane + 32 * k;
-        if (j < M) {
+        if (FAST || j < M) {
             const double ax = sx[j], ay = dim > 1 ? sy[j] : 0.0;
-            const double bx = j + 1 < M ? sx[j + 1] : x0n, by = dim > 1 ? (j + 1 < M ? sy[j + 1] : y0n) : 0.0;
-            double dx = fabs(ax - bx); { const double alt = twoL - dx; dx = alt < dx ? alt : dx; }
-            double d2 = dx * dx;
-            if (dim > 1) { double dy = fabs(ay - by); const double alt = twoL - dy; dy = alt < dy ? alt : dy; d2 = d2 + dy * dy; }
+            double bx, by;
+            if (FAST && k + 1 < KM) { bx = sx[j + 1]; by = sy[j + 1]; }
+            else { bx = j + 1 < M ? sx[j + 1] : x0n; by = dim > 1 ? (j + 1 < M ? sy[j + 1] : y0n) : 0.0; }
+            // distance() of propagator.jl:6-9, squared: min(2L - |d|, |d|)^2; the sign of d does not survive the square, so |d| is never materialised
+            const double ddx = ax - bx, altx = twoL - fabs(ddx), tx = altx < fabs(ddx) ? altx : ddx;
+            double d2 = tx * tx;
+            if (dim > 1) { const double ddy = ay - by, alty = twoL - fabs(ddy), ty = alty < fabs(ddy) ? alty : ddy; d2 = d2 + ty * ty; }
             link += d2;
             if (POT != PIMC_POT_ZERO) pot += d_pot_t<POT>(S.pot, ax, ay, dim) + d_pot_t<POT>(S.pot, bx, by, dim);
             if (DV == 1) { double q = ax * ax; if (dim > 1) q = q + ay * ay; vkin += q; }   // r . dV(r), measurement.jl:105
@@ -885,42 +890,52 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
     const int M = S.M, N = S.N, dim = S.dim, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double twoL = 2 * S.L;
     const double *rc = S.r + (size_t)c * N * dim * M;
-    const int *nextc = S.next + (size_t)c * N;
+    asm volatile("" : "+l"(rc));                        // keep the chain's base in a register pair: left alone, ptxas rematerialises the 64-bit product per worldline
     const int dvk = S.pot.dv_kind;
-    const uint32_t row_bytes = (uint32_t)M * 8u;
-    unsigned long long *mbar = (unsigned long long *)dyn + warp * 2;
-    double *stage0 = (double *)(dyn + nw * 16) + (size_t)warp * 2 * dim * M;
-    const uint32_t bar_u = d_smem_u32(mbar), stage_u = d_smem_u32(stage0);
-    auto issue = [&](int n_, int stg) {
-        if (lane == 0) {
-            const uint32_t b = bar_u + 8u * stg;
-            d_mbar_expect_tx(b, (uint32_t)dim * row_bytes);
-            d_bulk_g2s(stage_u + (uint32_t)stg * dim * row_bytes, rc + (size_t)(n_ * dim) * M, (uint32_t)dim * row_bytes, b);
-        }
-    };
-    if (lane == 0) { d_mbar_init(bar_u, 1); d_mbar_init(bar_u + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    const bool fast = dim == 2 && M == 32 * KM;
+    // Everything the loop needs per worldline is carried as a running value (32-bit offsets inside the chain, the two stage / barrier addresses
+    // swapped each step): the first form recomputed the 64-bit addresses of rows, stages and barriers per worldline -- more than half of the
+    // kernel's instructions, and the kernel is issue-bound (ncu: issue slots 77 % busy, DRAM 65 %).
+    const unsigned wl = (unsigned)(dim * M), wl_bytes = wl * 8u;               // one worldline: dim rows of M doubles
+    const unsigned step = (unsigned)nw * wl;
+    double *stage0 = (double *)(dyn + nw * 16) + (size_t)warp * 2 * wl;
+    const double *sx_cur = stage0, *sx_nxt = stage0 + wl;
+    uint32_t bar_cur = d_smem_u32((unsigned long long *)dyn + warp * 2), bar_nxt = bar_cur + 8u;
+    uint32_t st_cur = d_smem_u32(stage0), st_nxt = st_cur + wl_bytes;
+    if (lane == 0) { d_mbar_init(bar_cur, 1); d_mbar_init(bar_nxt, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     double link = 0.0, pot = 0.0, vkin = 0.0;
-    int it = 0;
-    if (warp < N) issue(warp, 0);
-    int nx = warp < N ? nextc[warp] : 0;
+    unsigned off_nxt = (unsigned)warp * wl;                                    // offset (doubles) of the next worldline to fetch
+    const int *pnx = S.next + (size_t)c * N + warp;                            // its permutation entry
+    if (warp < N && lane == 0) { d_mbar_expect_tx(bar_cur, wl_bytes); d_bulk_g2s(st_cur, rc + off_nxt, wl_bytes, bar_cur); }
+    int nx = warp < N ? *pnx : 0;
+    uint32_t par = 0u, flip = 0u;                                              // phase parity of the current stage: 0 0 1 1 0 0 ...
     for (int n = warp; n < N; n += nw) {
-        const int stg = it & 1; const uint32_t par = (uint32_t)(it >> 1) & 1u; ++it;
         __syncwarp();                                   // every lane is done with the other stage
-        if (n + nw < N) issue(n + nw, stg ^ 1);
-        const int nx_next = n + nw < N ? nextc[n + nw] : 0;
+        off_nxt += step; pnx += nw;
+        const bool more = n + nw < N;
+        if (more && lane == 0) { d_mbar_expect_tx(bar_nxt, wl_bytes); d_bulk_g2s(st_nxt, rc + off_nxt, wl_bytes, bar_nxt); }
+        const int nx_next = more ? *pnx : 0;
         double x0n = 0.0, y0n = 0.0;                    // first bead of the next particle of the cycle
-        if (nx != n) { const double *qx = rc + (size_t)(nx * dim) * M; x0n = qx[0]; y0n = dim > 1 ? qx[M] : 0.0; }
-        d_mbar_wait(bar_u + 8u * stg, par);
-        const double *sx = stage0 + (size_t)stg * dim * M;
-        if (nx == n) { x0n = sx[0]; y0n = dim > 1 ? sx[M] : 0.0; }   // closed on itself: its own bead 0
-        if (dvk == PIMC_DV_IDENTITY) d_energy_row<POT, KM, 1>(S, sx, x0n, y0n, twoL, link, pot, vkin);
-        else if (dvk == PIMC_DV_ZERO) d_energy_row<POT, KM, 0>(S, sx, x0n, y0n, twoL, link, pot, vkin);
-        else d_energy_row<POT, KM, 2>(S, sx, x0n, y0n, twoL, link, pot, vkin);
+        if (nx != n) { const double *qx = rc + (unsigned)nx * wl; x0n = qx[0]; y0n = dim > 1 ? qx[M] : 0.0; }
+        d_mbar_wait(bar_cur, par);
+        if (nx == n) { x0n = sx_cur[0]; y0n = dim > 1 ? sx_cur[M] : 0.0; }   // closed on itself: its own bead 0
+        if (POT != PIMC_POT_LATTICE && fast) {          // (the lattice bodies are large: one copy)
+            if (dvk == PIMC_DV_IDENTITY) d_energy_row<POT, KM, 1, POT != PIMC_POT_LATTICE>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
+            else if (dvk == PIMC_DV_ZERO) d_energy_row<POT, KM, 0, POT != PIMC_POT_LATTICE>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
+            else d_energy_row<POT, KM, 2, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
+        }
+        else if (dvk == PIMC_DV_IDENTITY) d_energy_row<POT, KM, 1, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
+        else if (dvk == PIMC_DV_ZERO) d_energy_row<POT, KM, 0, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
+        else d_energy_row<POT, KM, 2, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
         nx = nx_next;
+        { const double *t = sx_cur; sx_cur = sx_nxt; sx_nxt = t; }
+        { const uint32_t t = bar_cur; bar_cur = bar_nxt; bar_nxt = t; }
+        { const uint32_t t = st_cur; st_cur = st_nxt; st_nxt = t; }
+        par ^= flip; flip ^= 1u;
     }
     __syncwarp();
-    if (lane == 0) { d_mbar_inval(bar_u); d_mbar_inval(bar_u + 8); }   // the shared memory is reused by whatever runs next in this CTA
+    if (lane == 0) { d_mbar_inval(bar_cur); d_mbar_inval(bar_nxt); }   // the shared memory is reused by whatever runs next in this CTA
     link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
     __syncthreads();
     if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }

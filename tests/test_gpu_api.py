@@ -320,15 +320,16 @@ def test_library_communicator_single_rank():
             info = e.comm_info()
             assert info["nranks"] == 1 and info["rank"] == 0 and info["chains_total"] == 6 and info["nccl_version"] > 20000
         ups = [(1, e.update_create(L.UPD_SINGLE_COM, 1.0)), (1, e.update_create(L.UPD_RESHAPE_LINEAR, 6))]
-        en, de = e.energy_create(64), e.density_create(16)
+        en, de, sk = e.energy_create(64), e.density_create(16), e.structure_create(2)
         for _ in range(3):   # three blocks: each is reduced at the end of its pimc_run
-            e.run(10, ups, energies=[en], densities=[de], sched=L.SCHED_SWEEP)
+            e.run(10, ups, energies=[en], densities=[de], structures=[sk], sched=L.SCHED_SWEEP)
         E, Ev, n = e.energy_read(en, -1)
         per_chain = np.stack([e.energy_read(en, c)[0] for c in range(6)])
         d, nd, _ = e.density_read(de, 16)
         blk = e.energy_read_range(en, 5, 5)
-        out.append((E, Ev, n, per_chain, d, nd, blk[0]))
-    (E0, Ev0, n0, pc0, d0, nd0, b0), (E1, Ev1, n1, pc1, d1, nd1, b1) = out
+        out.append((E, Ev, n, per_chain, d, nd, blk[0], e.structure_read(sk, 2), e.compressibility(sk)))
+    (E0, Ev0, n0, pc0, d0, nd0, b0, s0, k0), (E1, Ev1, n1, pc1, d1, nd1, b1, s1, k1) = out
     assert n0 == n1 == 15 and np.array_equal(pc0, pc1) and np.array_equal(d0, d1) and nd0 == nd1
+    assert s0[1] == s1[1] == 15 * 16 * 6 and np.array_equal(s0[0], s1[0]) and k0 == k1 and k0[0] > 0   # structure-factor sums through ncclAllReduce (double)
     assert np.allclose(E0, E1, rtol=1e-14, atol=0) and np.allclose(Ev0, Ev1, rtol=1e-14, atol=0) and np.allclose(b0, b1, rtol=1e-14, atol=0)
     assert np.allclose(E1, pc1.mean(axis=0), rtol=1e-13)
