@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.environ.get("PIMC_B200_SO", os.path.join(_HERE, "libpimc_b200.so"))  # override only for kernel-variant experiments
+SO_PATH = os.environ.get("PIMC_B200_SO") or os.path.join(_HERE, "libpimc_b200.so")  # override only for kernel-variant experiments
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "pimc_b200.h")
 
 MAX_ANGLES = 32

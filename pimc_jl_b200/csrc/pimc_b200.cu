@@ -1219,7 +1219,7 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
             Q.mp.tma = (nen > 0 && (S.M + 31) / 32 <= 8 && (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr) ? 1 : 0;
             Q.n = n; Q.Nctr0 = h->Nctr; Q.Ncycle = h->cfg.Ncycle; Q.measure = nen + nde > 0 ? 1 : 0; Q.queue = h->queue;
             size_t smem_ch = smem_rs > smem_cs ? smem_rs : smem_cs;
-            const size_t smem_sw = has_swap ? swap_smem_bytes(S.N, S.M) : 0, smem_me = Q.mp.tma ? (size_t)8 * 16 + (size_t)8 * 2 * S.dim * S.M * sizeof(double) : 0;
+            const size_t smem_sw = has_swap ? swap_smem_bytes(S.N, S.M) : 0, smem_me = Q.mp.tma ? meas_smem_bytes(SWEEP_THREADS / 32, S.dim, S.M) : 0;
             if (smem_sw > smem_ch) smem_ch = smem_sw;
             if (smem_me > smem_ch) smem_ch = smem_me;
             CK(h, pimc_launch_chain(smem_ch + smem_pad, h->stream, S, h->dT, Q, nullptr)); LAUNCHED(); launches++;

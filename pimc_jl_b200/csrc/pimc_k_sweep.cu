@@ -42,7 +42,7 @@ cudaError_t pimc_launch_measure(int grid, cudaStream_t st, const DevSys &S, cons
     // Energy pass fed by TMA (even M, register-resident variants): 2 mbarriers + 2 stages of dim rows per warp
     MeasParams Q = P;
     Q.tma = (P.nen > 0 && KM <= 8 && (S.M % 2) == 0 && getenv("PIMC_NO_TMA") == nullptr) ? 1 : 0;
-    const size_t smem = Q.tma ? (size_t)8 * 16 + (size_t)8 * 2 * S.dim * S.M * sizeof(double) : 0;
+    const size_t smem = Q.tma ? meas_smem_bytes(256 / 32, S.dim, S.M) : 0;
     if (smem > 48 * 1024) {
         static meas_fn configured[16]; static int nconf = 0;
         bool seen = false; for (int i = 0; i < nconf; ++i) seen |= configured[i] == k;

@@ -29,6 +29,17 @@ struct MeasParams { int tma; int nen; int en_id[PIMC_MAXE]; long long en_k0[PIMC
 // every worldline anyway (centre-of-mass sweep of a chain without exchange cycles); mdone[c] = 1 tells k_measure to skip that chain.
 struct Sweep2Params { SweepParams sp; UpdDev upd[PIMC_MAXU]; int cap; int fuse; MeasParams mp; unsigned char *mdone; double *fscr; int swap_in_sweep; };
 
+// TMA ring of the Energy pass (d_energy_block_tma): per warp MEAS_STAGES mbarriers and MEAS_STAGES stages of one worldline (dim rows of M doubles)
+#ifndef MEAS_STAGES
+#define MEAS_STAGES 2       // (3 measured: no change, 100.8 vs 101 us per event on C2 -- the pass is not short of bytes in flight)
+#endif
+#ifndef MEAS_MINBLOCKS
+#define MEAS_MINBLOCKS 4     // resident CTAs per SM k_measure is compiled for (64 registers; 3 = 80 registers, no spills: A/B knob, measured no change)
+#endif
+#ifndef COM_PREFETCH_NEXT
+#define COM_PREFETCH_NEXT 0   // centre-of-mass sweep: permutation entry of the next proposal fetched one step ahead (A/B knob; measured 4 % SLOWER on C2: the entry is an L1 hit, the extra live register is not free at the 64-register cap)
+#endif
+__host__ __device__ inline size_t meas_smem_bytes(int nwarps, int dim, int M) { return (size_t)nwarps * MEAS_STAGES * 8 + (size_t)nwarps * MEAS_STAGES * dim * M * sizeof(double); }
 __host__ __device__ inline size_t pcom_smem_bytes(int N) { return (size_t)53 * N + 64; }
 __host__ __device__ inline size_t swap_smem_bytes(int N, int M) { return ((size_t)N + 10 * (size_t)(M + 1)) * sizeof(double) + 16; }
 #define FA_ARR 6

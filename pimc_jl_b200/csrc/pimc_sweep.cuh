@@ -435,6 +435,9 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
     __syncthreads();
     int it = 0;
     if (use_tma && warp < N) issue(warp, 0);
+#if COM_PREFETCH_NEXT
+    int nx_pf = warp < N ? nextc[warp] : 0;
+#endif
     unsigned long long my_beads = 0;
     double e_link = 0.0, e_pot = 0.0, e_vkin = 0.0; int e_cyc = 0;   // FUSE: lane partials of the Energy sums of this warp's worldlines
     const int dvk = S.pot.dv_kind;
@@ -458,7 +461,12 @@ __device__ __forceinline__ void d_com_sweep_body(const DevSys &S, const UpdDev &
                 if (n + NW < N) issue(n + NW, stg ^ 1);
                 d_mbar_wait(bar_u + 8u * stg, par);        // this proposal's rows have landed
             }
+#if COM_PREFETCH_NEXT
+            const int nx = nx_pf;
+            nx_pf = n + NW < N ? nextc[n + NW] : 0;        // the next proposal's permutation entry: in flight behind this proposal's arithmetic
+#else
             const int nx = nextc[n];
+#endif
             const bool single = nx == n;
             if (!single) { if (FUSE) e_cyc = 1; continue; }   // members of exchange cycles: PolymerCOM moves them below, SingleCOM never (com.jl:139-141)
             double *rx = S.r + RIDX(S, c, n, 0, 0), *ry = rx + M, *vl = S.Vl + VIDX(S, c, n, 0);
@@ -893,32 +901,41 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
     asm volatile("" : "+l"(rc));                        // keep the chain's base in a register pair: left alone, ptxas rematerialises the 64-bit product per worldline
     const int dvk = S.pot.dv_kind;
     const bool fast = dim == 2 && M == 32 * KM;
-    // Everything the loop needs per worldline is carried as a running value (32-bit offsets inside the chain, the two stage / barrier addresses
-    // swapped each step): the first form recomputed the 64-bit addresses of rows, stages and barriers per worldline -- more than half of the
-    // kernel's instructions, and the kernel is issue-bound (ncu: issue slots 77 % busy, DRAM 65 %).
+    // Everything the loop needs per worldline is carried as a running value (32-bit offsets inside the chain, stage indices): the first form
+    // recomputed the 64-bit addresses of rows, stages and barriers per worldline -- more than half of the kernel's instructions, and the
+    // kernel was issue-bound (ncu: issue slots 77 % busy, DRAM 65 %).
     const unsigned wl = (unsigned)(dim * M), wl_bytes = wl * 8u;               // one worldline: dim rows of M doubles
     const unsigned step = (unsigned)nw * wl;
-    double *stage0 = (double *)(dyn + nw * 16) + (size_t)warp * 2 * wl;
-    const double *sx_cur = stage0, *sx_nxt = stage0 + wl;
-    uint32_t bar_cur = d_smem_u32((unsigned long long *)dyn + warp * 2), bar_nxt = bar_cur + 8u;
-    uint32_t st_cur = d_smem_u32(stage0), st_nxt = st_cur + wl_bytes;
-    if (lane == 0) { d_mbar_init(bar_cur, 1); d_mbar_init(bar_nxt, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    constexpr int NST = MEAS_STAGES;                                           // ring depth: NST - 1 worldlines in flight while one is reduced
+    double *stage0 = (double *)(dyn + nw * NST * 8) + (size_t)warp * NST * wl;
+    const uint32_t bar0 = d_smem_u32((unsigned long long *)dyn + warp * NST), st0 = d_smem_u32(stage0);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) d_mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     double link = 0.0, pot = 0.0, vkin = 0.0;
-    unsigned off_nxt = (unsigned)warp * wl;                                    // offset (doubles) of the next worldline to fetch
-    const int *pnx = S.next + (size_t)c * N + warp;                            // its permutation entry
-    if (warp < N && lane == 0) { d_mbar_expect_tx(bar_cur, wl_bytes); d_bulk_g2s(st_cur, rc + off_nxt, wl_bytes, bar_cur); }
+    unsigned off_iss = (unsigned)warp * wl;                                    // offset (doubles) of the next worldline to fetch
+    int n_iss = warp, s_iss = 0;                                               // its index and the stage it goes to
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) {                                        // prologue: fill all stages but one
+        if (n_iss < N && lane == 0) { d_mbar_expect_tx(bar0 + 8u * s_iss, wl_bytes); d_bulk_g2s(st0 + (uint32_t)s_iss * wl_bytes, rc + off_iss, wl_bytes, bar0 + 8u * s_iss); }
+        n_iss += nw; off_iss += step; s_iss += 1;
+    }
+    const int *pnx = S.next + (size_t)c * N + warp;                            // permutation entry, fetched one worldline ahead
     int nx = warp < N ? *pnx : 0;
-    uint32_t par = 0u, flip = 0u;                                              // phase parity of the current stage: 0 0 1 1 0 0 ...
+    int s_cur = 0; uint32_t par = 0u;                                          // current stage and the phase parity of its barrier
     for (int n = warp; n < N; n += nw) {
-        __syncwarp();                                   // every lane is done with the other stage
-        off_nxt += step; pnx += nw;
-        const bool more = n + nw < N;
-        if (more && lane == 0) { d_mbar_expect_tx(bar_nxt, wl_bytes); d_bulk_g2s(st_nxt, rc + off_nxt, wl_bytes, bar_nxt); }
-        const int nx_next = more ? *pnx : 0;
+        __syncwarp();                                   // every lane is done with the stage read in the previous step: it is refilled now
+        if (n_iss < N && lane == 0) { d_mbar_expect_tx(bar0 + 8u * s_iss, wl_bytes); d_bulk_g2s(st0 + (uint32_t)s_iss * wl_bytes, rc + off_iss, wl_bytes, bar0 + 8u * s_iss); }
+        n_iss += nw; off_iss += step; s_iss = s_iss + 1 == NST ? 0 : s_iss + 1;
+        pnx += nw;
+        const int nx_next = n + nw < N ? *pnx : 0;
         double x0n = 0.0, y0n = 0.0;                    // first bead of the next particle of the cycle
         if (nx != n) { const double *qx = rc + (unsigned)nx * wl; x0n = qx[0]; y0n = dim > 1 ? qx[M] : 0.0; }
-        d_mbar_wait(bar_cur, par);
+        d_mbar_wait(bar0 + 8u * s_cur, par);
+        const double *sx_cur = stage0 + (unsigned)s_cur * wl;
         if (nx == n) { x0n = sx_cur[0]; y0n = dim > 1 ? sx_cur[M] : 0.0; }   // closed on itself: its own bead 0
         if (POT != PIMC_POT_LATTICE && fast) {          // (the lattice bodies are large: one copy)
             if (dvk == PIMC_DV_IDENTITY) d_energy_row<POT, KM, 1, POT != PIMC_POT_LATTICE>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
@@ -929,13 +946,13 @@ __device__ __forceinline__ void d_energy_block_tma(const DevSys &S, int c, doubl
         else if (dvk == PIMC_DV_ZERO) d_energy_row<POT, KM, 0, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
         else d_energy_row<POT, KM, 2, false>(S, sx_cur, x0n, y0n, twoL, link, pot, vkin);
         nx = nx_next;
-        { const double *t = sx_cur; sx_cur = sx_nxt; sx_nxt = t; }
-        { const uint32_t t = bar_cur; bar_cur = bar_nxt; bar_nxt = t; }
-        { const uint32_t t = st_cur; st_cur = st_nxt; st_nxt = t; }
-        par ^= flip; flip ^= 1u;
+        s_cur += 1; if (s_cur == NST) { s_cur = 0; par ^= 1u; }
     }
     __syncwarp();
-    if (lane == 0) { d_mbar_inval(bar_cur); d_mbar_inval(bar_nxt); }   // the shared memory is reused by whatever runs next in this CTA
+    if (lane == 0) {   // the shared memory is reused by whatever runs next in this CTA
+#pragma unroll
+        for (int i = 0; i < NST; ++i) d_mbar_inval(bar0 + 8u * i);
+    }
     link = warp_sum(link); pot = warp_sum(pot); vkin = warp_sum(vkin);
     __syncthreads();
     if (lane == 0) { red[warp] = link; red[32 + warp] = pot; red[64 + warp] = vkin; }
@@ -969,7 +986,7 @@ __device__ __forceinline__ void d_measure_body(const DevSys &S, const DevTables 
     for (int d = 0; d < P.nde; ++d) d_density_block(S, c, T->de[P.de_id[d]]);
 }
 template <int POT, int KM>
-__global__ void __launch_bounds__(256, 4) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
+__global__ void __launch_bounds__(256, MEAS_MINBLOCKS) k_measure(const __grid_constant__ DevSys S, const DevTables *__restrict__ T, const __grid_constant__ MeasParams P,
                                                     const unsigned char *__restrict__ mdone)
 {
     __shared__ double red[96];

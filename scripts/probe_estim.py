@@ -14,3 +14,14 @@ h, nd, _ = e.paircorr_read(pc, 400)
 print(f"C={C}: moves only {a['kernel_ms']:.2f} ms, with g(r)+winding every 5 iterations {b['kernel_ms']:.2f} ms -> {(b['kernel_ms'] - a['kernel_ms']) / 10:.3f} ms per measurement event "
       f"({C * 100 * 256 * 255 // 2 / ((b['kernel_ms'] - a['kernel_ms']) / 10 * 1e-3):.3e} pair distances/s); pairs counted {int(h.sum())}, ndata {nd}, "
       f"<W^2> {e.winding_read(wi, -1)[0].mean():.4f}")
+# static structure factor (k_structure), kmax = 4: timed per functor call
+import torch
+sk = e.structure_create(4)
+e.structure_measure(sk)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    e.structure_measure(sk)
+t1 = time.perf_counter()
+S, nds = e.structure_read(sk, 4)
+print(f"S(k), kmax 4: {(t1 - t0) / 5 * 1e3:.3f} ms per event ({C * 100 * 256 / ((t1 - t0) / 5):.3e} beads/s); S(pi/L (1,0)) = {S[1, 4] / (nds * 256):.4f}, kappa_T = {e.compressibility(sk)[0]:.4f}")
