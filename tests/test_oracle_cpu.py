@@ -510,3 +510,19 @@ def test_structure_factor_against_numpy(oracle, dim):
     S1 = ob.structure_now(s1, 2)
     nv = 2 * 2 + 2 * 2 * 2 if dim == 2 else 2              # independent vectors: kmax + kmax (2 kmax + 1) in 2-D, kmax in 1-D
     assert np.count_nonzero(S1) == nv and np.allclose(S1[S1 != 0], M, atol=1e-12)
+
+
+def test_structure_factor_ideal_gas_limit(oracle):
+    """physical pin of the estimator: init_world (system.jl:36-78) places every worldline uniformly and independently in the periodic box, so
+    for V = 0 the density modes are uncorrelated and <|rho_k|^2> = N at every k != 0, i.e. S(k) = 1 and kappa_T = beta / rho (ideal gas).
+    Mean over 300 independent systems of S on the smallest shell; its standard error is ~ 1 / sqrt(300) (|rho_k|^2 / N is exponential-like)."""
+    ob = oracle
+    N, M, L_, kmax, nsys = 6, 4, 2.0, 2, 300
+    acc = np.zeros((kmax + 1, 2 * kmax + 1))
+    for seed in range(nsys):
+        s = ob.System(ob.make_potential("zero", "identity"), dim=2, M=M, N=N, L=L_, T=1.0, lam=1.0, seed=1000 + seed)
+        acc += ob.structure_now(s, kmax)
+    S = acc / (nsys * M * N)
+    shell = np.array([S[1, kmax], S[0, kmax + 1], S[1, kmax + 1], S[1, kmax - 1]])
+    assert np.all(np.abs(shell - 1.0) < 0.25), shell
+    assert abs(S[(np.arange(kmax + 1)[:, None] > 0) | (np.arange(-kmax, kmax + 1)[None, :] > 0)].mean() - 1.0) < 0.08
