@@ -420,6 +420,12 @@ void ora_gauss_pair(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot,
     pimc_gauss_pair(pimc_draw(pimc_stream_make(seed, chain, iter), slot, kind, retry, bead), g0, g1);
 }
 
+/* the two uniforms in [0, 1) of one addressed draw (words 0-1 and 2-3): lets a test restate the retry loops that consume them */
+void ora_uniform_pair(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind, uint32_t retry, uint32_t bead, double *u0, double *u1)
+{
+    pimc_u4 w = pimc_draw(pimc_stream_make(seed, chain, iter), slot, kind, retry, bead);
+    *u0 = pimc_u01_co(w.w[0], w.w[1]); *u1 = pimc_u01_co(w.w[2], w.w[3]);
+}
 /* helper.jl:141-181 ; rp is rows x dim column-major; exc = fpcycle(mod1(j0+j, M)) = first particle of the closure's cycle */
 static int hardspherelevy(double *rp, int rows, const ora_system *s, int64_t j0, int64_t exc, const gsrc *g)
 {

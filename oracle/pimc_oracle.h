@@ -88,6 +88,9 @@ double ora_prop_rel0(const double *r1, const double *r2, int dim, double tau);
 void   ora_gauss_pair(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind,
                       uint32_t retry, uint32_t bead, double *g0, double *g1);
 
+void   ora_uniform_pair(uint64_t seed, uint32_t chain, uint64_t iter, uint32_t slot, uint32_t kind,
+                        uint32_t retry, uint32_t bead, double *u0, double *u1);
+
 /* ---- system ---- */
 ora_system *ora_create(const ora_config *cfg);
 void ora_destroy(ora_system *s);

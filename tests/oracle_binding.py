@@ -66,6 +66,7 @@ def lib():
             "ora_adjust_slices": (i64, [i64, i64, i64, d, d, d]),
             "ora_prop_rel0": (d, [f64p, f64p, C.c_int, d]),
             "ora_gauss_pair": (None, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f64p, f64p]),
+            "ora_uniform_pair": (None, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f64p, f64p]),
             "ora_create": (vp, [C.POINTER(Config)]), "ora_destroy": (None, [vp]), "ora_last_error": (C.c_char_p, []),
             "ora_get_paths": (None, [vp, f64p, f64p, i64p, i64p]), "ora_set_paths": (None, [vp, f64p, i64p]),
             "ora_get_scalars": (None, [vp, f64p, i64p]), "ora_set_iter": (None, [vp, C.c_uint64]), "ora_set_ctr": (None, [vp, i64]),

@@ -526,3 +526,316 @@ def test_structure_factor_ideal_gas_limit(oracle):
     shell = np.array([S[1, kmax], S[0, kmax + 1], S[1, kmax + 1], S[1, kmax - 1]])
     assert np.all(np.abs(shell - 1.0) < 0.25), shell
     assert abs(S[(np.arange(kmax + 1)[:, None] > 0) | (np.arange(-kmax, kmax + 1)[None, :] > 0)].mean() - 1.0) < 0.08
+
+
+def test_reshape_swap_delta_u_and_commit_against_numpy(oracle):
+    """ReshapeSwapLinear for independent worldlines (src/updates/reshape.jl:123-283), restated from the Julia source: crossed end points
+    (r1 ends on fpcycle2(j_m), r2 on fpcycle1(j_m), :148-151), w_initial = cached links of both strands (:165), w_updated = sum(V1) + sum(V2)
+    (:244), and on acceptance the commit in the reference's order -- exchange `next`, RE-COMPUTE both cycles, write rows 2..m+1 and links 1..m
+    through the new cycles (:252-268), exchange the tails j_m+1..M of r and V when j_m < M (:269-275; the cached link AT j_m stays where it was:
+    B14).  Permutations with 1-, 2- and 3-cycles, windows that wrap onto the next member of the cycle."""
+    ob = oracle
+    rng = np.random.default_rng(17)
+    M, N, L, lam = 7, 4, 3.0, 0.5
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=L, T=0.7, lam=lam, seed=23)
+    r_start = rng.uniform(-L, L, (N, 2, M))
+    s.set_paths(r_start, np.array([2, 1, 4, 3], dtype=np.int64))
+    mod1 = lambda j: (j - 1) % M + 1
+
+    def cycle(nxt, n):                                   # subcycle (helper.jl:64-85): the cycle of n, starting at n
+        pol, p = [n], nxt[n - 1]
+        while p != n:
+            pol.append(p); p = nxt[p - 1]
+        return pol
+    naccept = nwrap = ntail = 0
+    for trial in range(120):
+        r, V, _, nxt = s.paths()
+        nxt = [int(x) for x in nxt]
+        n1 = int(rng.integers(1, N + 1)); n2 = int(rng.integers(1, N)); n2 += n2 >= n1
+        j0, m = int(rng.integers(1, M + 1)), int(rng.integers(2, M - 1))
+        jm = j0 + m
+        xi1, xi2 = 0.3 * rng.standard_normal((m - 1, 2)), 0.3 * rng.standard_normal((m - 1, 2))
+        u = float(rng.uniform())
+        pol1, pol2 = cycle(nxt, n1), cycle(nxt, n2)
+        fp = lambda pol, j: pol[(1 + (j - 1) // M - 1) % len(pol)]          # pcycle (helper.jl:269-271)
+        r1, r2 = np.zeros((m + 1, 2)), np.zeros((m + 1, 2))
+        r1[0], r2[0] = r[n1 - 1, :, j0 - 1], r[n2 - 1, :, j0 - 1]
+        r1[m], r2[m] = r[fp(pol2, jm) - 1, :, mod1(jm) - 1], r[fp(pol1, jm) - 1, :, mod1(jm) - 1]
+        b1, b2 = levy_py(r1, s.tau, L, lam, xi1), levy_py(r2, s.tau, L, lam, xi2)
+        w_i = 0.0
+        for j in range(j0, jm):
+            w_i += V[fp(pol1, j) - 1, mod1(j) - 1] + V[fp(pol2, j) - 1, mod1(j) - 1]
+        V1 = [_lnV_py(b1[k], b1[k + 1], s.tau, _harm) for k in range(m)]
+        V2 = [_lnV_py(b2[k], b2[k + 1], s.tau, _harm) for k in range(m)]
+        w_u = sum(V1) + sum(V2)
+        delta = math.exp(w_u - w_i)
+        acc_py = delta >= 1.0 or delta > u
+        wi, wu = C.c_double(), C.c_double()
+        acc = ob.lib().ora_reshape_swap_explicit(s.h, n1, n2, j0, m, ob._p(xi1), ob._p(xi2), u, 1, C.byref(wi), C.byref(wu))
+        assert abs(wi.value - w_i) <= 1e-12 * max(1, abs(w_i)) and abs(wu.value - w_u) <= 1e-12 * max(1, abs(w_u)), (trial, wi.value, w_i, wu.value, w_u)
+        assert bool(acc) == acc_py, trial
+        exp_r, exp_V, exp_n = r.copy(), V.copy(), list(nxt)
+        if acc_py:
+            naccept += 1; nwrap += jm - 1 > M; ntail += jm < M
+            exp_n[n1 - 1], exp_n[n2 - 1] = nxt[n2 - 1], nxt[n1 - 1]
+            q1, q2 = cycle(exp_n, n1), cycle(exp_n, n2)                    # the closures see the re-computed cycles (:254-257)
+            for j in range(2, m + 2):
+                exp_r[fp(q1, j0 + j - 1) - 1, :, mod1(j0 + j - 1) - 1] = b1[j - 1]
+                exp_r[fp(q2, j0 + j - 1) - 1, :, mod1(j0 + j - 1) - 1] = b2[j - 1]
+            for j in range(1, m + 1):
+                exp_V[fp(q1, j0 + j - 1) - 1, mod1(j0 + j - 1) - 1] = V1[j - 1]
+                exp_V[fp(q2, j0 + j - 1) - 1, mod1(j0 + j - 1) - 1] = V2[j - 1]
+            if jm < M:
+                for j in range(jm + 1, M + 1):
+                    exp_r[n1 - 1, :, j - 1], exp_r[n2 - 1, :, j - 1] = exp_r[n2 - 1, :, j - 1].copy(), exp_r[n1 - 1, :, j - 1].copy()
+                    exp_V[n1 - 1, j - 1], exp_V[n2 - 1, j - 1] = exp_V[n2 - 1, j - 1], exp_V[n1 - 1, j - 1]
+        r2_, V2_, _, n2_ = s.paths()
+        assert [int(x) for x in n2_] == exp_n, trial
+        assert np.array_equal(r2_, exp_r), trial
+        assert np.allclose(V2_, exp_V, rtol=1e-14, atol=0), trial
+    assert naccept > 20 and nwrap > 3 and ntail > 3, (naccept, nwrap, ntail)
+
+
+def test_interacting_swap_pair_action_against_numpy(oracle):
+    """The one place where the pair action enters the moves as shipped: ReshapeSwapLinear on an interacting System (reshape.jl:163-243),
+    restated from the Julia source in numpy -- find_nns (stencil of the bead's cell, periodic Euclidean distance <= one cell width,
+    nearest_neighbours.jl:72-154), next() (helper.jl:286-300), lnU = p < 0 ? -mu : log(p), p = 1 + terms(|r|, |r'|) / prop_rel0(r, r', tau)
+    (system.jl:25-28, propagator.jl:73-86) with the scaled linear B-spline of the term table, the component-wise |distance| vectors of
+    propagator.jl:6-9 -- and with BOTH the old-pair and the new-pair sums added to w_initial (B4, reshape.jl:182-239).  Proposals are not
+    committed, so the permutation (a 3-cycle and a fixed point) and the cell lists stay as set."""
+    ob = oracle
+    rng = np.random.default_rng(29)
+    M, N, L, lam, T, mu = 6, 4, 3.0, 0.5, 0.8, 0.3
+    n_tab, lo, hi = 24, 1e-3, 9.0
+    x = np.linspace(lo, hi, n_tab)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    tab = -0.6 * np.exp(-0.5 * (X + Y)) * (1 + 0.3 * np.cos(X - 2 * Y))         # not symmetric: pins the (|r|, |r'|) argument order
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=L, T=T, lam=lam, mu=mu, interactions=True, g=0.3, r_a=1.0,
+                  tab=tab, tab_lo=lo, tab_hi=hi, seed=31)
+    r0 = rng.uniform(-1.2, 1.2, (N, 2, M))                                      # a dense cloud: every bead has neighbours within a cell width
+    nxt = [2, 3, 1, 4]
+    s.set_paths(r0, np.array(nxt, dtype=np.int64))
+    r, V, bins, _ = s.paths()
+    tau, nb = s.tau, 6
+    w_cell = 2 * L / nb
+    mod1 = lambda j: (j - 1) % M + 1
+    dist = lambda a, b: np.array([distance_py(a[k], b[k], L) for k in range(2)])
+
+    def bin_py(p):
+        ix, iy = (int(math.floor((p[k] + L) / w_cell)) for k in range(2))
+        return ix, iy
+    assert all(bins[n, j] == bin_py(r[n, :, j])[0] + nb * bin_py(r[n, :, j])[1] + 1 for n in range(N) for j in range(M))
+
+    def find_nns_py(pos, sl, exc):                       # particles (1-based) within one cell width of pos at slice sl
+        ix, iy = bin_py(pos)
+        cells = {((ix + dx) % nb, (iy + dy) % nb) for dx in (-1, 0, 1) for dy in (-1, 0, 1)}
+        out = []
+        for n in range(1, N + 1):
+            if n in exc or bin_py(r[n - 1, :, sl - 1]) not in cells:
+                continue
+            if math.sqrt(float(np.sum(dist(r[n - 1, :, sl - 1], pos) ** 2))) <= w_cell:
+                out.append(n)
+        return out
+    next_py = lambda n, sl: ((nxt[n - 1] if sl == M else n), mod1(sl + 1))
+
+    def terms_py(a, b):                                  # scale(interpolate(A, BSpline(Linear())), A_r1, A_r2)
+        h = (hi - lo) / (n_tab - 1)
+        ta, tb = (a - lo) / h, (b - lo) / h
+        ia, ib = min(max(int(math.floor(ta)), 0), n_tab - 2), min(max(int(math.floor(tb)), 0), n_tab - 2)
+        fa, fb = ta - ia, tb - ib
+        return (1 - fb) * ((1 - fa) * tab[ia, ib] + fa * tab[ia + 1, ib]) + fb * ((1 - fa) * tab[ia, ib + 1] + fa * tab[ia + 1, ib + 1])
+
+    def lnU_py(r1, r2):
+        p = 1 + terms_py(float(np.linalg.norm(r1)), float(np.linalg.norm(r2))) / (math.exp(-float((r1 - r2) @ (r1 - r2)) / (4 * tau)) / (4 * math.pi * tau))
+        return -mu if p < 0.0 else math.log(p)
+
+    def cycle(n):
+        pol, p = [n], nxt[n - 1]
+        while p != n:
+            pol.append(p); p = nxt[p - 1]
+        return pol
+    npair = nneg = 0
+    for trial in range(80):
+        n1 = int(rng.integers(1, N + 1)); n2 = int(rng.integers(1, N)); n2 += n2 >= n1
+        j0, m = int(rng.integers(1, M + 1)), int(rng.integers(2, M - 1))
+        jm = j0 + m
+        xi1, xi2 = 0.2 * rng.standard_normal((m - 1, 2)), 0.2 * rng.standard_normal((m - 1, 2))
+        pol1, pol2 = cycle(n1), cycle(n2)
+        fp = lambda pol, j: pol[((j - 1) // M) % len(pol)]
+        r1, r2 = np.zeros((m + 1, 2)), np.zeros((m + 1, 2))
+        r1[0], r2[0] = r[n1 - 1, :, j0 - 1], r[n2 - 1, :, j0 - 1]
+        r1[m], r2[m] = r[fp(pol2, jm) - 1, :, mod1(jm) - 1], r[fp(pol1, jm) - 1, :, mod1(jm) - 1]
+        b1, b2 = levy_py(r1, tau, L, lam, xi1), levy_py(r2, tau, L, lam, xi2)     # a = 8e-10: hardspherelevy! never redraws
+        w_i = 0.0
+        for j in range(j0, jm):
+            sl = mod1(j)
+            for pol in (pol1, pol2):
+                p = fp(pol, j)
+                w_i += V[p - 1, sl - 1]
+            for pol in (pol1, pol2):                       # old pairs of both strands
+                p = fp(pol, j)
+                pn, pj = next_py(p, sl)
+                for nn in find_nns_py(r[p - 1, :, sl - 1], sl, [p]):
+                    qn, qj = next_py(nn, sl)
+                    u_ = lnU_py(dist(r[nn - 1, :, sl - 1], r[p - 1, :, sl - 1]), dist(r[qn - 1, :, qj - 1], r[pn - 1, :, pj - 1]))
+                    w_i += u_; npair += 1; nneg += u_ == -mu
+        V1 = [_lnV_py(b1[k], b1[k + 1], tau, _harm) for k in range(m)]
+        V2 = [_lnV_py(b2[k], b2[k + 1], tau, _harm) for k in range(m)]
+        for j in range(j0, jm):                            # new pairs: added to w_initial as well (B4)
+            sl, k = mod1(j), j - j0
+            exc = [fp(pol1, j), fp(pol2, j)]
+            for b in (b1, b2):
+                for nn in find_nns_py(b[k], sl, exc):
+                    qn, qj = next_py(nn, sl)
+                    w_i += lnU_py(dist(r[nn - 1, :, sl - 1], b[k]), dist(r[qn - 1, :, qj - 1], b[k + 1])); npair += 1
+        w_u = sum(V1) + sum(V2)
+        wi, wu = C.c_double(), C.c_double()
+        u = float(rng.uniform())
+        acc = ob.lib().ora_reshape_swap_explicit(s.h, n1, n2, j0, m, ob._p(xi1), ob._p(xi2), u, 0, C.byref(wi), C.byref(wu))
+        assert abs(wi.value - w_i) <= 1e-11 * max(1, abs(w_i)) and abs(wu.value - w_u) <= 1e-12 * max(1, abs(w_u)), (trial, wi.value, w_i, wu.value, w_u)
+        d = math.exp(w_u - w_i)
+        assert bool(acc) == (d >= 1.0 or d > u), trial
+    assert npair > 500 and 0 < nneg < npair, (npair, nneg)
+
+
+def test_hardcore_bridge_redraws_against_numpy(oracle):
+    """hardspherelevy! (src/updates/helper.jl:141-181) inside ReshapeLinear on a dense hard-core System, restated from the Julia source: every
+    interior bead is redrawn (fresh Gaussians: the addressed draw (bead, retry) of the RNG spec) while the nearest other particle at that slice
+    -- find_nn over the 3 x 3 cell stencil of the TELEPORTED candidate, the moved worldline excluded (nearest_neighbours.jl:156-179) -- lies
+    closer than s.a; the candidate is stored un-teleported until the final wrap; more than s.ctr tries give up the proposal.  V = 0 and the
+    pair action does not enter ReshapeLinear as shipped, so a proposal is accepted iff its bridge could be laid; the committed rows must equal
+    the restated bridge bit for bit."""
+    ob = oracle
+    rng = np.random.default_rng(41)
+    M, N, L, lam, seed = 8, 7, 1.5, 0.5, 77
+    s = ob.System(ob.make_potential("zero", "identity"), dim=2, M=M, N=N, L=L, T=1.0, lam=lam, interactions=True, g=6.0, r_a=0.5, seed=seed,
+                  tab=np.zeros((4, 4)), tab_lo=1e-3, tab_hi=6.0)            # terms = 0: lnU = log(1) = 0, only the hard core acts
+    a = s.scalars()["a"]
+    assert abs(a - math.exp(-2 * math.pi / 6.0)) < 1e-15                    # a = interactions ? exp(-2 pi / g) : 0, system.jl:151
+    u = ob.Update(s, ob.UPD_RESHAPE_LINEAR, M - 2)
+    ob.lib().ora_set_ctr(s.h, 6)                                             # few tries: proposals that give up are exercised too
+    nb = int(math.floor(2 * L / 0.5)); w_cell = 2 * L / nb
+    mod1 = lambda j: (j - 1) % M + 1
+    bin_py = lambda p: tuple(min(max(int(math.floor((p[k] + L) / w_cell)), 0), nb - 1) for k in range(2))
+
+    def gauss(it, bead, retry):
+        g0, g1 = C.c_double(), C.c_double()
+        ob.lib().ora_gauss_pair(seed, 0, it, 0, 2, retry, bead, C.byref(g0), C.byref(g1))   # kind 2 = PIMC_K_BRIDGE, slot 0
+        return np.array([g0.value, g1.value])
+    nretry = nfail = nacc = 0
+    for it in range(1, 161):
+        ob.lib().ora_set_iter(s.h, it)
+        r, _, bins, nxt = s.paths()
+        n, j0 = int(rng.integers(1, N + 1)), int(rng.integers(1, M + 1))
+        bm0 = u.get()["bead_moves"]
+        acc = ob.lib().ora_update_call(s.h, u.h, 0, n, j0)
+        m = u.get()["bead_moves"] - bm0 + 1
+        own = lambda j: (n if j <= M else int(nxt[n - 1]), mod1(j))
+        rp = np.zeros((m + 1, 2))
+        rp[0] = r[n - 1, :, j0 - 1]
+        pe, je = own(j0 + m)
+        rp[m] = r[pe - 1, :, je - 1]
+        for k in range(2):
+            if abs(rp[0, k] - rp[m, k]) > L:
+                rp[m, k] += np.sign(rp[0, k]) * (2 * L)
+        ok = True
+        mi = m - 1                                                            # interior beads (rows - 2)
+        for j in range(1, mi + 1):
+            alpha = (mi + 1 - j) / (mi + 2 - j)
+            sl = mod1(j0 + j)
+            ctr, placed = 0, False
+            while True:
+                ctr += 1
+                if ctr > 6:
+                    break
+                rp[j] = alpha * rp[j - 1] + (1 - alpha) * rp[m] + gauss(it, j, ctr - 1) * math.sqrt(2 * lam * alpha * s.tau)
+                tp = np.array([teleport_py(rp[j, k], L) for k in range(2)])
+                bx, by = bin_py(tp)
+                cells = {((bx + dx) % nb, (by + dy) % nb) for dx in (-1, 0, 1) for dy in (-1, 0, 1)}
+                best = None
+                for q in range(1, N + 1):
+                    if q == n:
+                        continue
+                    b = int(bins[q - 1, sl - 1]) - 1
+                    if (b % nb, b // nb) not in cells:
+                        continue
+                    d = math.sqrt(sum(distance_py(tp[k], r[q - 1, k, sl - 1], L) ** 2 for k in range(2)))
+                    best = d if best is None else min(best, d)
+                if best is not None and best < a:
+                    nretry += 1
+                    continue
+                placed = True
+                break
+            if not placed:
+                ok = False
+                break
+        r2 = s.paths()[0]
+        if not ok:
+            nfail += 1
+            assert acc == 0 and np.array_equal(r2, r), it
+            continue
+        nacc += 1
+        exp_r = r.copy()
+        for k in range(m):                                                    # rows 1..m: the first end point is rewritten with its wrapped self
+            p, sl = own(j0 + k)
+            exp_r[p - 1, :, sl - 1] = [teleport_py(rp[k, 0], L), teleport_py(rp[k, 1], L)]
+        assert acc == 1 and np.array_equal(r2, exp_r), it
+    assert nretry > 30 and nfail > 0 and nacc > 60, (nretry, nfail, nacc)
+
+
+def test_hardcore_centre_of_mass_retries_against_numpy(oracle):
+    """move_polymer! (src/updates/helper.jl:368-395) inside SingleCenterOfMass (com.jl:136-224) on a dense hard-core System, restated from the
+    Julia source: a uniform displacement d = maxd * 2 * (rand(dim) - 0.5) is redrawn (the addressed draw `retry` of the RNG spec) while any
+    displaced, wrapped bead has its nearest other particle of the same slice closer than s.a; more than s.ctr tries give up.  V = 0: a
+    proposal whose displacement could be placed is accepted, and the committed worldline must equal teleport(r + d) bit for bit."""
+    ob = oracle
+    rng = np.random.default_rng(43)
+    M, N, L, seed = 6, 7, 1.5, 99
+    s = ob.System(ob.make_potential("zero", "identity"), dim=2, M=M, N=N, L=L, T=1.0, lam=0.5, interactions=True, g=6.0, r_a=0.5, seed=seed,
+                  tab=np.zeros((4, 4)), tab_lo=1e-3, tab_hi=6.0)
+    a = s.scalars()["a"]
+    u = ob.Update(s, ob.UPD_SINGLE_COM, 0.6)
+    ob.lib().ora_set_ctr(s.h, 4)
+    nb = int(math.floor(2 * L / 0.5)); w_cell = 2 * L / nb
+    bin_py = lambda p: tuple(min(max(int(math.floor((p[k] + L) / w_cell)), 0), nb - 1) for k in range(2))
+    nretry = nfail = nacc = 0
+    for it in range(1, 201):
+        ob.lib().ora_set_iter(s.h, it)
+        r, _, bins, nxt = s.paths()
+        n = int(rng.integers(1, N + 1))
+        maxd = u.get()["var"]
+        acc = ob.lib().ora_update_call(s.h, u.h, 0, n, 0)
+        new = None
+        for ctr in range(1, 5):
+            u0, u1 = C.c_double(), C.c_double()
+            ob.lib().ora_uniform_pair(seed, 0, it, 0, 4, ctr - 1, 0, C.byref(u0), C.byref(u1))      # kind 4 = PIMC_K_COM
+            d = np.array([maxd * 2 * (u0.value - 0.5), maxd * 2 * (u1.value - 0.5)])
+            cand = np.zeros((2, M)); hit = False
+            for j in range(1, M + 1):
+                c = np.array([teleport_py(r[n - 1, k, j - 1] + d[k], L) for k in range(2)])
+                cand[:, j - 1] = c
+                bx, by = bin_py(c)
+                cells = {((bx + dx) % nb, (by + dy) % nb) for dx in (-1, 0, 1) for dy in (-1, 0, 1)}
+                best = None
+                for q in range(1, N + 1):
+                    b = int(bins[q - 1, j - 1]) - 1
+                    if q == n or (b % nb, b // nb) not in cells:
+                        continue
+                    dq = math.sqrt(sum(distance_py(c[k], r[q - 1, k, j - 1], L) ** 2 for k in range(2)))
+                    best = dq if best is None else min(best, dq)
+                if best is not None and best < a:
+                    hit = True
+                    break
+            if not hit:
+                new = cand
+                break
+            nretry += 1
+        r2 = s.paths()[0]
+        if new is None:
+            nfail += 1
+            assert acc == 0 and np.array_equal(r2, r), it
+        else:
+            nacc += 1
+            exp_r = r.copy(); exp_r[n - 1] = new
+            assert acc == 1 and np.array_equal(r2, exp_r), it
+    assert nretry > 30 and nfail > 0 and nacc > 60, (nretry, nfail, nacc)
