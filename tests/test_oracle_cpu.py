@@ -839,3 +839,60 @@ def test_hardcore_centre_of_mass_retries_against_numpy(oracle):
             exp_r = r.copy(); exp_r[n - 1] = new
             assert acc == 1 and np.array_equal(r2, exp_r), it
     assert nretry > 30 and nfail > 0 and nacc > 60, (nretry, nfail, nacc)
+
+
+def test_init_world_against_numpy(oracle):
+    """init_world (src/system.jl:36-78) restated from the Julia source, with the addressed draws of the RNG spec (start point: kind INIT0,
+    retry = attempt; ring Gaussians: kind INIT, retry = index of the levy! call): uniform start, closed ring by levy! between two copies of the
+    start point, and the hard-core rejection loop as written -- a hit re-bridges r IN PLACE and the scan over slices and earlier particles
+    simply continues on the new ring before the whole attempt is repeated.  Positions bit for bit, link cache to 1e-14."""
+    ob = oracle
+    M, N, L, lam, seed, T = 6, 8, 1.5, 0.5, 1234, 1.0
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=M, N=N, L=L, T=T, lam=lam, interactions=True, g=6.0, r_a=0.5, seed=seed,
+                  tab=np.zeros((4, 4)), tab_lo=1e-3, tab_hi=6.0)
+    a, tau = s.scalars()["a"], s.tau
+    r_o, V_o, _, nxt = s.paths()
+
+    def start(slot, attempt):
+        u0, u1 = C.c_double(), C.c_double()
+        ob.lib().ora_uniform_pair(seed, 0, 0, slot, 7, attempt, 0, C.byref(u0), C.byref(u1))       # kind 7 = PIMC_K_INIT0
+        return np.array([2 * L * (u0.value - 0.5), 2 * L * (u1.value - 0.5)])
+
+    def ring(r, slot, call):
+        xi = np.zeros((M - 2, 2))
+        for t in range(1, M - 1):
+            g0, g1 = C.c_double(), C.c_double()
+            ob.lib().ora_gauss_pair(seed, 0, 0, slot, 6, call, t, C.byref(g0), C.byref(g1))        # kind 6 = PIMC_K_INIT
+            xi[t - 1] = g0.value, g1.value
+        return levy_py(r, tau, L, lam, xi)
+    world, nrebridge = [], 0
+    for n in range(1, N + 1):
+        slot, calls, ctr = n - 1, 0, 0
+        r = np.zeros((M, 2))
+        passed = n != 1
+        while passed:
+            passed = False
+            ctr += 1
+            assert ctr <= 10000
+            r[0] = start(slot, ctr - 1); r[-1] = r[0]
+            r = ring(r, slot, calls); calls += 1
+            for m in range(M):
+                for i in range(n - 1):
+                    d = math.sqrt(sum(distance_py(world[i][m, k], r[m, k], L) ** 2 for k in range(2)))
+                    if d < a:
+                        r = ring(r, slot, calls); calls += 1
+                        nrebridge += 1
+                        passed = True
+        if n == 1:
+            r[0] = start(slot, 0); r[-1] = r[0]
+            r = ring(r, slot, calls)
+        world.append(r)
+    mine = np.stack([w.T for w in world])                                       # [N][dim][M]
+    assert nrebridge > 3
+    assert np.array_equal(mine, r_o) and list(nxt) == list(range(1, N + 1))
+    V_mine = np.array([[_lnV_py(world[n][m], world[n][(m + 1) % M], tau, _harm) for m in range(M)] for n in range(N)])
+    assert np.allclose(V_o, V_mine, rtol=1e-14, atol=0)
+    for n in range(N):                                                          # the result respects the hard core at every slice
+        for i in range(n):
+            for m in range(M):
+                assert math.sqrt(sum(distance_py(world[i][m, k], world[n][m, k], L) ** 2 for k in range(2))) >= a
