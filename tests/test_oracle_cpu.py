@@ -896,3 +896,41 @@ def test_init_world_against_numpy(oracle):
         for i in range(n):
             for m in range(M):
                 assert math.sqrt(sum(distance_py(world[i][m, k], world[n][m, k], L) ** 2 for k in range(2))) >= a
+
+
+def test_run_update_choice_and_measurement_cadence(oracle):
+    """run! (src/simulation.jl:29-42) and measurement_Z_sector (src/measurement.jl:1-17) restated: per iteration one update drawn with
+    weights 1 ./ every by StatsBase's `sample(wv)` walk (t = rand() * sum(w); advance while the running sum is < t) from the chain-level
+    uniform of the RNG spec; every Ncycle-th iteration of runs WITH Zmeasurements takes a measurement, the counter carrying over between
+    calls; s.ctr = 1000 with measurements, 10000 without."""
+    ob = oracle
+    seed, Ncycle = 4321, 3
+    s = ob.System(ob.make_potential("harmonic", "identity"), dim=2, M=6, N=3, L=4.0, T=1.0, lam=0.5, Ncycle=Ncycle, seed=seed)
+    every = [1, 2, 4]
+    ups = [(every[0], ob.Update(s, ob.UPD_SINGLE_COM, 0.5)), (every[1], ob.Update(s, ob.UPD_RESHAPE_LINEAR, 3)), (every[2], ob.Update(s, ob.UPD_RESHAPE_SWAP, 3))]
+    en = ob.Energy(200)
+    w = [1.0 / e for e in every]
+
+    def picks(it0, n):
+        cnt = [0, 0, 0]
+        for it in range(it0, it0 + n):
+            u0, u1 = C.c_double(), C.c_double()
+            ob.lib().ora_uniform_pair(seed, 0, it, 0xFFFF, 0, 0, 0, C.byref(u0), C.byref(u1))   # slot PIMC_SLOT_CHAIN, kind PIMC_K_ITER
+            t, i, cw = u0.value * sum(w), 0, w[0]
+            while cw < t and i < 2:
+                i += 1; cw += w[i]
+            cnt[i] += 1
+        return cnt
+    it0 = s.scalars()["iter"]
+    s.run(40, ups)                                            # thermalisation: no measurements, no cadence
+    sc = s.scalars()
+    assert sc["ctr"] == 10000 and sc["N_MC"] == 0 and sc["Nctr"] == 0 and sc["iter"] == it0 + 40
+    assert [u.get()["tries"] for _, u in ups] == picks(it0, 40)
+    s.run(47, ups, energies=[en])
+    sc = s.scalars()
+    assert sc["ctr"] == 1000 and sc["N_MC"] == 47 // Ncycle and sc["Nctr"] == 47 % Ncycle
+    s.run(10, ups, energies=[en])                             # 2 carried over + 10 = 4 more measurements
+    sc = s.scalars()
+    assert sc["N_MC"] == 57 // Ncycle and sc["Nctr"] == 57 % Ncycle and len(en.read()[0]) == 57 // Ncycle
+    tot = picks(it0, 97)
+    assert [u.get()["tries"] for _, u in ups] == tot and sum(tot) == 97 and min(tot) > 5
