@@ -224,7 +224,8 @@ int pimc_run_ex(pimc_handle *h, int64_t n, const int32_t *update_ids, const int6
  *      data-path collective; the reference's analogue is `pmap` over independent runs (examples/density_SRL_lattice.jl:1-2,46).  With a
  *      communicator attached the library all-reduces the estimator accumulators itself (NCCL over NVLink, on a side stream: the block
  *      reduced at the end of pimc_run overlaps the next block's moves) and the read-outs become collective and global:
- *      pimc_energy_read* with chain = -1 -> mean over the chains of ALL ranks; pimc_density_read -> counters and ndata summed over the ranks.
+ *      pimc_energy_read* with chain = -1 -> mean over the chains of ALL ranks; pimc_density_read / pimc_paircorr_read / pimc_structure_read
+ *      (and pimc_compressibility, which reads the structure factor) -> counters / sums and ndata summed over the ranks.
  *      Every rank must issue the same read-outs in the same order.  One rank per process (torchrun, MPI, Julia Distributed workers): rank 0
  *      calls pimc_comm_get_unique_id and ships the 128 bytes to the others, every rank calls pimc_comm_init.  One process, several GPUs:
  *      pimc_comm_init_all on handles created on different devices, then one host thread per handle. ---- */
