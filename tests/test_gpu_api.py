@@ -333,3 +333,33 @@ def test_library_communicator_single_rank():
     assert s0[1] == s1[1] == 15 * 16 * 6 and np.array_equal(s0[0], s1[0]) and k0 == k1 and k0[0] > 0   # structure-factor sums through ncclAllReduce (double)
     assert np.allclose(E0, E1, rtol=1e-14, atol=0) and np.allclose(Ev0, Ev1, rtol=1e-14, atol=0) and np.allclose(b0, b1, rtol=1e-14, atol=0)
     assert np.allclose(E1, pc1.mean(axis=0), rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_todo_estimators_through_the_mirror():
+    """PairCorrelation, Winding and StructureFactor (the `#TODO`s of src/measurement.jl:125-127) listed in Zmeasurements of run! through the
+    host-side mirror, on an ideal gas of distinguishable particles in the periodic box (V = 0, no swap move): S(k) = 1 at every k != 0,
+    kappa_T = beta / rho, g(r) = 1, winding numbers are integers.  Statistical bars are wide (256 chains, 60 measurement events)."""
+    from pimc_jl_b200.pimc import PairCorrelation, Winding, StructureFactor
+    s = System(zero_potential(), dV="identity", lam=0.5, L=4.0, M=8, N=8, T=1.0, length_measurement_cycle=5, chains=256, seed=11, schedule="sweep")
+    ups = [(1, SingleCenterOfMass(s, 1.0)), (1, ReshapeLinear(s, 4))]
+    run_b(s, 200, ups)
+    g, w, sk, en = PairCorrelation(s, nbins=40, rmax=4.0), Winding(s, 100), StructureFactor(s, kmax=3), Energy(s, 100)
+    run_b(s, 300, ups, Zmeasurements=[en, g, w, sk])
+    assert s.N_MC[s.N] == 60 and sk.ndata == 60 * 8 * 256 and g.ndata == 60 * 8 * 256
+    S = sk.S
+    a, b = np.meshgrid(np.arange(4), np.arange(-3, 4), indexing="ij")
+    half = (a > 0) | (b > 0)
+    assert S.shape == (4, 7) and np.all(np.isnan(S[~half])) and np.all(np.isfinite(S[half]))
+    assert np.all(np.abs(S[half] - 1.0) < 0.2), S
+    assert abs(S[half].mean() - 1.0) < 0.05
+    assert np.allclose(sk.k[1, 3], math.pi / 4.0) and np.allclose(sk.k[2, 5], math.pi / 4.0 * math.hypot(2, 2))
+    kappa = sk.compressibility()
+    rho, beta = 8 / 64.0, 1.0
+    assert abs(kappa * rho / beta - 0.5 * (S[1, 3] + S[0, 4])) < 1e-9 and abs(kappa * rho / beta - 1.0) < 0.2
+    gr = g.g
+    assert gr.shape == (40,) and abs(gr[10:].mean() - 1.0) < 0.1, gr      # beyond the first bins (few counts) the ideal gas is flat
+    W2 = w.W2
+    W0 = w.series(0)
+    assert len(W2) == 60 and W0.shape == (60, 2) and np.allclose(W0, np.rint(W0), atol=1e-9) and np.all(W2 >= 0)
+    assert np.isfinite(w.superfluid_fraction())
