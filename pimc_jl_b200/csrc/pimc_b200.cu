@@ -1097,6 +1097,7 @@ static int run_core(pimc_handle *h, int64_t n, const int32_t *update_ids, const 
     // FAITHFUL: warp 0 owns the proposal; large chains get three more warps for the estimators (Energy / Density stream N*M beads)
     int threads = sched == PIMC_SCHED_SWEEP ? 64 : ((size_t)S.N * S.M >= 2048 && (S.need_cells || (nen + nde > 0 && S.C <= 1184)) ? (S.need_cells ? PIMC_CELLS_THREADS : 64) : 32);
     if (sched == PIMC_SCHED_SWEEP) { while (threads < S.N && threads < 256) threads *= 2; }
+    if (sched == PIMC_SCHED_SWEEP && S.N == 1 && !S.need_cells) threads = 32;   // one-particle systems (the shipped trapped example): one warp per chain, twice the resident chains
     if (S.need_cells && threads > PIMC_CELLS_THREADS) threads = PIMC_CELLS_THREADS;   // launch bound of k_run_cells
     size_t smem = 96 * sizeof(double) + (size_t)S.N + 16;
     P.fimpl = h->opt_faithful_impl; P.fscr = nullptr;
