@@ -118,3 +118,16 @@ int main(){ pimc_u4 o;
     x = g.ravel()
     assert abs(x.mean()) < 0.03 and abs(x.var() - 1) < 0.03 and abs((x ** 4).mean() - 3) < 0.15
     assert abs(np.corrcoef(g[:, 0], g[:, 1])[0, 1]) < 0.03
+
+
+def test_header_is_plain_c_and_the_c_driver_links(tmp_path):
+    """include/pimc_b200.h must be consumable by a C compiler (the drop-in boundary is a C ABI: `ccall` / cgo / ctypes bind plain symbols),
+    and the plain-C driver of examples/density_SRL_lattice.jl (tests/c/) must compile and link against libpimc_b200.so with -Wall -Werror
+    -- no GPU needed: nothing is executed here."""
+    import subprocess
+    inc, so_dir = os.path.join(ROOT, "include"), os.path.join(ROOT, "pimc_jl_b200")
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "pimc_b200.h"\n#include "pimc_rng.h"\nint main(void) { pimc_config c; (void)c; return sizeof(pimc_measurements) > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + inc, "-c", "-o", str(tmp_path / "probe.o"), str(probe)])
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + inc, "-o", str(tmp_path / "example_srl"),
+                           os.path.join(ROOT, "tests", "c", "example_density_srl_lattice.c"), "-L" + so_dir, "-lpimc_b200", "-lm", "-Wl,-rpath," + so_dir])
