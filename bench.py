@@ -49,9 +49,15 @@ WORKLOADS = {
     "c4": dict(name="C4 lattice density N=128 M=256 L=8 V0=6 l25, non-interacting", pot=_LAT, dim=2, N=128, M=256, L=8.0, T=0.2,
                lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024, updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)], measure="density",
                nbins=500, sched="sweep", F_alg=149.0),
-    "c4i": dict(name="C4 with interactions as the script (g=2, a=exp(-pi), lnU table, r_a from the propagator)", pot=_LAT, dim=2, N=128, M=256, L=8.0,
+    "c4i": dict(name="C4 with interactions, g=2 forwarded to System (hard core a=exp(-pi), lnU table, r_a from the propagator)", pot=_LAT, dim=2, N=128, M=256, L=8.0,
                 T=0.2, lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024, updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)],
                 measure="density", nbins=500, sched="faithful", interactions=True, g=2.0, r_a=0.0, F_alg=149.0),
+    # examples/density_SRL_lattice.jl:17-19 AS SHIPPED: g enters build_prop_int only and is not forwarded to System, so a = exp(-2 pi / 0.0) = 0
+    # (src/system.jl:151): pair action through the lnU table (swap move), no hard core
+    "c4i0": dict(name="C4 with interactions exactly as the script ships (g=2 in the pair-propagator table only: a = 0, lnU table, r_a from the propagator)",
+                 pot=_LAT, dim=2, N=128, M=256, L=8.0, T=0.2, lam=1.0 / 9.869604401089358, Ncycle=3, chains=1024,
+                 updates=[("com", 1, 1.0), ("reshape", 1, 5), ("swap", 20, 20)], measure="density", nbins=500, sched="faithful", interactions=True,
+                 g=2.0, g_system=0.0, r_a=0.0, F_alg=149.0),
     "c5": dict(name="C5 2D trapped gas N=1024 M=64", pot=dict(kind="harmonic", dv="identity"), dim=2, N=1024, M=64, L=100.0, T=1.0, lam=0.5, Ncycle=10,
                chains=512, updates=[("com", 1, 1.0), ("reshape", 1, 2)], measure="energy", sched="sweep", F_alg=51.0),
 }
@@ -68,7 +74,7 @@ def interaction_args(wl):
     tau = (1.0 / wl["T"]) / wl["M"]
     p = propint.build_prop_int(math.ceil(math.sqrt(2) * wl["L"]), g, tau)   # examples/density_SRL_lattice.jl:17
     r_a = wl["r_a"] or propint.determine_nnrange(p, tau, 1e-20, wl["L"])
-    return dict(interactions=True, g=g, r_a=r_a, tab=p["tab"], tab_lo=p["lo"], tab_hi=p["hi"])
+    return dict(interactions=True, g=wl.get("g_system", g), r_a=r_a, tab=p["tab"], tab_lo=p["lo"], tab_hi=p["hi"])   # g_system: what System(...) itself receives
 
 
 def peaks():
